@@ -114,6 +114,7 @@ class ProblemData:
             assert self.ao.shape[0] == (1 if self.xctype == XC_LDA else 4)
         if self.restricted:
             assert np.array_equal(self.mo_coeff[0], self.mo_coeff[1])
+            assert np.array_equal(self.mo_energy[0], self.mo_energy[1])
 
     # ---- aux / grid sharding: sigma is linear in P and in g -------------------
     def shard(self, rank: int, world: int) -> "ProblemData":
