@@ -74,7 +74,7 @@ def test_davidson_kat(nroots):
 def test_davidson_restart_and_pick():
     rng = np.random.default_rng(1)
     n = 200
-    a = np.diag(np.linspace(-0.5, 4.0, n)) + 0.02 * rng.standard_normal((n, n))
+    a = np.diag(np.linspace(0.05, 4.0, n)) + 0.02 * rng.standard_normal((n, n))
     a = 0.5 * (a + a.T)
     hd = a.diagonal().copy()
     ref = np.linalg.eigvalsh(a)
