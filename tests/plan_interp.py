@@ -1,0 +1,139 @@
+"""NumPy interpreter of a sigma-build `Plan` (TEST INFRASTRUCTURE).
+
+Executes the same generic steps as the CUDA engine -- MO-resident DF blocks, block-weighted exchange,
+J blocks with mixing, half-transformed grid contraction, local GEMM / rank-1 / diagonal terms, sparse layout
+maps -- with dense NumPy, so plan construction (xtddft_b200/plan.py) can be checked against the oracle on a
+machine without a GPU.  Never imported by the product.
+"""
+import numpy as np
+
+es = lambda *a: np.einsum(*a, optimize=True)
+
+
+def _gather_cols(c, idx):
+    out = np.zeros((c.shape[0], len(idx)))
+    m = idx >= 0
+    out[:, m] = c[:, idx[m]]
+    return out
+
+
+class PlanInterpreter:
+    def __init__(self, plan, p):
+        self.plan, self.p = plan, p
+        self.co, self.cv = [], []
+        for ch in plan.channels:
+            self.co.append(_gather_cols(p.mo_coeff[ch.spin_o], ch.occ_idx))
+            self.cv.append(_gather_cols(p.mo_coeff[ch.spin_v], ch.vir_idx))
+        self.tensors = [p.cderi, p.cderi_lr]
+        self.loo, self.lvv = {}, {}
+        for kt in plan.k_terms:
+            key = (kt.tensor, kt.ch)
+            if key not in self.loo:
+                L = self.tensors[kt.tensor]
+                self.loo[key] = es("Pmn,mi,nj->Pij", L, self.co[kt.ch], self.co[kt.ch])
+                self.lvv[key] = es("Pmn,ma,nb->Pab", L, self.cv[kt.ch], self.cv[kt.ch])
+        self.ljb = []
+        for jb in plan.j_blocks:
+            co = self.co[jb.ch][:, jb.r0:jb.r0 + jb.nr]
+            cv = self.cv[jb.ch][:, jb.c0:jb.c0 + jb.nc]
+            self.ljb.append(es("Pmn,mi,na->Pia", p.cderi, co, cv))
+        if plan.xc_kind != "none":
+            self.phi = [es("cgm,mo->cgo", p.ao, co) for co in self.co]
+
+    # ---- layout -------------------------------------------------------------------------------
+    def pack(self, z_ext):
+        plan = self.plan
+        x = z_ext.shape[0]
+        zs = [np.zeros((x, ch.no, ch.nv)) for ch in plan.channels]
+        ent, coef = plan.layout_entries, plan.layout_coefs
+        for k in range(ent.shape[0]):
+            e, c, i, a = ent[k]
+            zs[c][:, i, a] += coef[k] * z_ext[:, e]
+        return zs
+
+    def unpack(self, sig):
+        plan = self.plan
+        x = sig[0].shape[0]
+        out = np.zeros((x, plan.ext_dim))
+        ent, coef = plan.layout_entries, plan.layout_coefs
+        for k in range(ent.shape[0]):
+            e, c, i, a = ent[k]
+            out[:, e] += coef[k] * sig[c][:, i, a]
+        return out
+
+    def jblock_diag(self, jbi):
+        return es("Pia,Pia->ia", self.ljb[jbi], self.ljb[jbi])
+
+    # ---- sigma --------------------------------------------------------------------------------
+    def sigma(self, z_ext):
+        plan, p = self.plan, self.p
+        z_ext = np.atleast_2d(np.asarray(z_ext, dtype=float))
+        zs = self.pack(z_ext)
+        sig = [np.zeros_like(z) for z in zs]
+        # exchange with block weights
+        for kt in plan.k_terms:
+            ch = plan.channels[kt.ch]
+            loo, lvv = self.loo[(kt.tensor, kt.ch)], self.lvv[(kt.tensor, kt.ch)]
+            z = zs[kt.ch]
+            for ib, (i0, ni) in enumerate(ch.o_blocks):
+                for ab, (a0, na) in enumerate(ch.v_blocks):
+                    zt = np.zeros_like(z)
+                    for jb, (j0, nj) in enumerate(ch.o_blocks):
+                        for bb, (b0, nbb) in enumerate(ch.v_blocks):
+                            zt[:, j0:j0 + nj, b0:b0 + nbb] = kt.weights[ib, ab, jb, bb] * z[:, j0:j0 + nj, b0:b0 + nbb]
+                    u = es("Pij,xjb->Pxib", loo[:, i0:i0 + ni, :], zt)
+                    sig[kt.ch][:, i0:i0 + ni, a0:a0 + na] += es("Pxib,Pba->xia", u, lvv[:, :, a0:a0 + na])
+        # Coulomb blocks
+        if plan.j_blocks:
+            rho = [es("Pia,xia->xP", self.ljb[k], zs[jb.ch][:, jb.r0:jb.r0 + jb.nr, jb.c0:jb.c0 + jb.nc])
+                   for k, jb in enumerate(plan.j_blocks)]
+            for t, jb in enumerate(plan.j_blocks):
+                mixed = sum(plan.j_mix[t, s] * rho[s] for s in range(len(rho)))
+                sig[jb.ch][:, jb.r0:jb.r0 + jb.nr, jb.c0:jb.c0 + jb.nc] += es("xP,Pia->xia", mixed, self.ljb[t])
+        # grid kernel, half-transformed: Y = ao . (Cv z^T), rho via phi_o, A-buffers, R = ao^T A, project with Cv
+        if plan.xc_kind != "none":
+            nvar = p.ao.shape[0]
+            ys = [es("cgm,mv,xov->cgxo", p.ao, self.cv[c], zs[c]) for c in range(len(zs))]
+            rhos = []
+            for c in range(len(zs)):
+                y, ph = ys[c], self.phi[c]
+                r = np.zeros((nvar,) + y.shape[1:3])                   # [c, g, x]
+                r[0] = es("gxo,go->gx", y[0], ph[0])
+                for k in range(1, nvar):
+                    r[k] = es("gxo,go->gx", y[k], ph[0]) + es("gxo,go->gx", y[0], ph[k])
+                rhos.append(r)
+            wvs = []
+            if plan.xc_kind == "uks":
+                rho1 = np.stack(rhos)                                  # [s, c, g, x]
+                wv = es("scgx,sctdg->tdgx", rho1, p.fxc_uks) * p.weights[None, None, :, None]
+                wvs = [wv[0], wv[1]]
+            elif plan.xc_kind == "alda0":
+                wv = np.zeros_like(rhos[0])
+                wv[0] = rhos[0][0] * p.fxc_alda0[:, None]
+                wvs = [wv]
+            elif plan.xc_kind == "mcol":
+                wvs = [es("bgx,bag->agx", rhos[0], 2.0 * p.fxc_mcol) * p.weights[None, :, None]]
+            for c in range(len(zs)):
+                wv, ph = wvs[c], self.phi[c]
+                a = np.zeros_like(ys[c])
+                a[0] = es("gx,go->gxo", wv[0], ph[0])
+                for k in range(1, nvar):
+                    a[0] += es("gx,go->gxo", wv[k], ph[k])
+                    a[k] = es("gx,go->gxo", wv[k], ph[0])
+                rt = es("cgxo,cgm->xom", a, p.ao)
+                sig[c] += es("xom,mv->xov", rt, self.cv[c])
+        # local terms
+        for lg in plan.local_gemms:
+            dc, r0, nr, c0, ncol = lg.dst
+            sc, sr0, sc0 = lg.src
+            if lg.side == "R":
+                k = lg.mat.shape[0]
+                sig[dc][:, r0:r0 + nr, c0:c0 + ncol] += lg.alpha * es("xrb,bc->xrc", zs[sc][:, sr0:sr0 + nr, sc0:sc0 + k], lg.mat)
+            else:
+                k = lg.mat.shape[1]
+                sig[dc][:, r0:r0 + nr, c0:c0 + ncol] += lg.alpha * es("rj,xjc->xrc", lg.mat, zs[sc][:, sr0:sr0 + k, sc0:sc0 + ncol])
+        for r1 in plan.rank1s:
+            sig[r1.dst_ch] += es("x,ia->xia", es("ia,xia->x", r1.v, zs[r1.src_ch]), r1.u)
+        for d in plan.diags:
+            sig[d.ch] += d.d[None] * zs[d.ch]
+        return self.unpack(sig)
