@@ -1,0 +1,125 @@
+/* xtd_sigma.h -- C-ABI of the B200-native Davidson sigma-vector engine (libxtdsigma.so).
+ *
+ * Drop-in boundary.  The reference has no FFI: its operator interface is the Python pair
+ * `vind, hdiag = obj.gen_vind()` (xtddft/XTDA.py:694-698, xtddft/SF_TDA.py:162-244, xtddft/XSF_TDA.py:1029-1277,
+ * xtddft/XSF_TDA_GPU.py:357-729) whose `vind(zs[nvec,dim]) -> [nvec,dim]` is handed to the Davidson solver
+ * (xtddft/utils/Davidson.py:21).  This library is what a `vind` implemented on a B200 binds through ctypes:
+ * plain pointers and sizes, no torch / numpy types, return code 0 = OK, negative = error
+ * (`xtd_last_error()` has the message); nothing throws across the boundary.
+ *
+ * Conventions
+ *   - fp64 everywhere; matrices are row-major with an explicit leading dimension.
+ *   - pointers named *_dev are device pointers owned by the caller (kept alive until xtd_destroy);
+ *     pointers named *_host are host arrays copied during the call.
+ *   - one engine per GPU per process; not thread-safe per engine; all work is enqueued on the stream given to
+ *     xtd_set_stream (default: the legacy default stream).
+ *   - The engine executes a generic *plan* (channels, exchange block weights, Coulomb blocks, grid kernel,
+ *     local terms, layout maps); `xtddft_b200/plan.py` compiles X-TDA / SF-TDA / XSF-TDA into it.
+ */
+#ifndef XTD_SIGMA_H
+#define XTD_SIGMA_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct xtd_engine* xtd_handle;
+
+enum { XTD_FXC_NONE = 0, XTD_FXC_UKS = 1, XTD_FXC_ALDA0 = 2, XTD_FXC_MCOL = 3 };
+enum { XTD_SIDE_RIGHT = 0, XTD_SIDE_LEFT = 1 };
+
+typedef struct {
+  double flops_gemm;          /* useful FP64 flops issued through the DMMA GEMM since the last reset */
+  unsigned long long launches; /* kernels launched by this library since the last reset */
+  double ms[12];              /* device time per phase of the last xtd_sigma* call (see XTD_T_* below) */
+} xtd_stats;
+enum { XTD_T_PACK = 0, XTD_T_XC_GEMM = 1, XTD_T_XC_STREAM = 2, XTD_T_K1 = 3, XTD_T_K2 = 4, XTD_T_J = 5,
+       XTD_T_LOCAL = 6, XTD_T_UNPACK = 7, XTD_T_TOTAL = 8 };
+
+const char* xtd_last_error(void);
+int xtd_version(void);
+
+/* life cycle -------------------------------------------------------------------------------------------*/
+int xtd_create(xtd_handle* out, int nao, long workspace_bytes);
+int xtd_destroy(xtd_handle h);
+int xtd_set_stream(xtd_handle h, void* cuda_stream);
+
+/* orbitals: C[nao, nmo] of spin 0/1 (replaces the captured mo_coeff of XTDA.py:564-586) */
+int xtd_set_mo(xtd_handle h, int spin, const double* c_dev, long ld, int nmo);
+
+/* a trial-vector block z[no, nv]; idx = MO column per internal position, -1 = zero pad orbital.
+ * blocks = (start, n) pairs of the 1 or 2 sub-blocks of the occ / vir positions.  Returns the channel id. */
+int xtd_add_channel(xtd_handle h, int spin_o, const int* occ_idx_host, int no, int spin_v, const int* vir_idx_host, int nv,
+                    const int* o_blocks_host, int nob, const int* v_blocks_host, int nvb);
+/* address of channel `ch` inside the internal sigma buffer for `nvec` vectors: element (x,i,a) at
+ * base + x*vec_stride + i*ld + a (doubles) */
+int xtd_channel_layout(xtd_handle h, int ch, int nvec, long* base, long* vec_stride, long* ld);
+
+/* density fitting (replaces mf.get_jk / get_j / get_k with mf.density_fit(), XTDA.py:520-539, SF_TDA.py:273-276,
+ * XSF_TDA.py:857,996).  Declare every exchange term and Coulomb block first, then stream the 3-centre tensor
+ * in aux chunks: L[np, nao, nao] (ld_row, stride_p) or lower-triangular packed rows (packed=1, stride_p).
+ * The chunk is transformed to the MO blocks each term needs and is not kept. */
+int xtd_add_kterm(xtd_handle h, int tensor, int ch, const double* weights_host, int nob, int nvb);
+int xtd_add_jblock(xtd_handle h, int ch, int r0, int nr, int c0, int nc);
+int xtd_set_jmix(xtd_handle h, const double* mix_host, int n);
+int xtd_df_begin(xtd_handle h, int tensor, long naux_local);
+int xtd_df_add(xtd_handle h, int tensor, const double* l_dev, long np, long ld_row, long stride_p, int packed);
+int xtd_jblock_diag(xtd_handle h, int jb, double* out_dev);   /* out[nr*nc] = sum_P L_ia^2 */
+
+/* grid (replaces ni.block_loop / nr_uks_fxc / nr_uks_fxc_sf_tda(_mc), XTDA.py:514, SF_TDA.py:90-160, 976-1047):
+ * ao[nvar, ng, nao] with row stride ld_row and component stride stride_comp, weights[ng], cached kernel:
+ *   XTD_FXC_UKS   fxc[2,nvar,2,nvar,ng] unweighted   (numint.cache_xc_kernel)
+ *   XTD_FXC_ALDA0 f[ng] weighted                     (SF_TDA.cache_xc_kernel_sf)
+ *   XTD_FXC_MCOL  fxc[nvar,nvar,ng] unweighted       (cache_xc_kernel_sf_mc) */
+int xtd_set_grid(xtd_handle h, const double* ao_dev, int nvar, long ng, long ld_row, long stride_comp, const double* w_dev);
+int xtd_set_fxc(xtd_handle h, int kind, const double* fxc_dev);
+
+/* local terms (Fock blocks, Delta-A couplings; XTDA.py:628-687, XSF_TDA.py:1146-1274):
+ *   RIGHT: dst[r,c] += alpha * sum_b src[r,b] M[b,c]   M[mrows=k, mcols=nc]
+ *   LEFT : dst[r,c] += alpha * sum_j M[r,j] src[j,c]   M[mrows=nr, mcols=k] */
+int xtd_add_local_gemm(xtd_handle h, int side, int dst_ch, int r0, int nr, int c0, int nc, int src_ch, int sr0, int sc0,
+                       const double* mat_host, int mrows, int mcols, double alpha);
+int xtd_add_rank1(xtd_handle h, int dst_ch, const double* u_host, int src_ch, const double* v_host); /* dense [no,nv] */
+int xtd_add_diag(xtd_handle h, int ch, const double* d_host);                                        /* dense [no,nv] */
+
+/* layout maps between the caller's vector (ext_dim) and the internal blocks.
+ * gather (per channel): rows = i*nv+a, CSR over external indices.
+ * scatter: rows = external index, CSR over (channel, i*ld+a) */
+int xtd_set_gather(xtd_handle h, int ch, const long* indptr_host, const long* cols_host, const double* vals_host, long nnz);
+int xtd_set_scatter(xtd_handle h, long ext_dim, const long* indptr_host, const long* offs_host, const signed char* chans_host,
+                    const double* vals_host, long nnz);
+
+int xtd_finalize(xtd_handle h, int max_nvec);
+
+/* the operator: hz = A z for nvec trial vectors (device pointers, [nvec, ext_dim] contiguous) */
+int xtd_sigma(xtd_handle h, int nvec, const double* z_dev, double* hz_dev);
+/* multi-GPU: rank-local part (linear in this rank's aux block and grid batch) -> internal buffer; the caller
+ * all-reduces xtd_partial_buffer() (NCCL) and calls xtd_sigma_finish, which adds the replicated local terms. */
+int xtd_sigma_partial(xtd_handle h, int nvec, const double* z_dev);
+int xtd_partial_buffer(xtd_handle h, int nvec, double** ptr, long* nelem);
+int xtd_sigma_finish(xtd_handle h, int nvec, double* hz_dev);
+/* end-to-end entry with HOST vectors (pinned staging, H2D + sigma + D2H on the engine stream, synchronous) */
+int xtd_sigma_host(xtd_handle h, int nvec, const double* z_host, double* hz_host);
+
+int xtd_get_stats(xtd_handle h, xtd_stats* out);
+int xtd_reset_stats(xtd_handle h);
+
+/* Davidson subspace algebra on device vectors (Davidson.py:152-271): all row vectors of length n */
+int xtd_vec_dots(void* stream, double* g_dev, int ldg, const double* a_dev, long lda, int m, const double* b_dev, long ldb, int k, long n);
+int xtd_vec_lincomb(void* stream, double* y_dev, long ldy, const double* x_dev, long ldx, const double* c_dev, int ldc, int m, int k,
+                    long n, double beta);
+int xtd_vec_residual(void* stream, double* r_dev, const double* ax_dev, const double* x_dev, long ld, const double* e_dev,
+                     double* nrm2_dev, int k, long n);
+int xtd_vec_precond(void* stream, double* x_dev, long ld, const double* hdiag_dev, const double* shift_dev, double* nrm2_dev, int k,
+                    long n);
+int xtd_vec_scale(void* stream, double* x_dev, long ld, const double* s_dev, int k, long n);
+
+/* plain GEMM entry (tests / benchmarks of the DMMA kernel): C[M,N] = alpha * A[M,K] * B[N,K]^T */
+int xtd_dgemm_tn(void* stream, int m, int n, int k, double alpha, const double* a_dev, long lda, const double* b_dev, long ldb,
+                 double* c_dev, long ldc, int accumulate);
+unsigned long long xtd_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

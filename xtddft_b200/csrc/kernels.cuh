@@ -1,0 +1,455 @@
+// Streaming (HBM-bound) kernels of the sigma path: layout pack/unpack, transposes, the grid f_xc weighting
+// with warp-shuffle reductions, density-fitted Coulomb blocks, rank-1 / diagonal local terms and the
+// Davidson vector primitives.  All fp64, coalesced along the contiguous index, grids sized from the data.
+#pragma once
+#include "common.cuh"
+
+namespace xtd {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum; result valid in thread 0 (and broadcast through smem to all when bcast)
+template <int THREADS>
+__device__ __forceinline__ double block_sum(double v, double* sm) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sm[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (w == 0) {
+    r = (l < THREADS / 32) ? sm[l] : 0.0;
+    r = warp_sum(r);
+    if (l == 0) sm[0] = r;
+  }
+  __syncthreads();
+  r = sm[0];
+  __syncthreads();
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// layout: external vector <-> padded internal block  (sparse maps built by the host plan)
+// ------------------------------------------------------------------------------------------------------
+// Z[x][i][a] (ld) = sum_k val[k] * zext[x][col[k]],  rows r = i*nv + a
+__global__ void pack_kernel(double* __restrict__ Z, long ldz, long z_vec_stride, int nv, long nrows,
+                            const long* __restrict__ indptr, const long* __restrict__ cols, const double* __restrict__ vals,
+                            const double* __restrict__ zext, long ext_dim, int nvec) {
+  const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int x = blockIdx.y;
+  if (r >= nrows || x >= nvec) return;
+  const long k0 = indptr[r], k1 = indptr[r + 1];
+  double acc = 0.0;
+  const double* zx = zext + (long)x * ext_dim;
+  for (long k = k0; k < k1; ++k) acc += vals[k] * zx[cols[k]];
+  const long i = r / nv, a = r - i * nv;
+  Z[(long)x * z_vec_stride + i * ldz + a] = acc;
+}
+
+// hz[x][e] = sum_k val[k] * SIG[ chan_base[ch[k]] + x*chan_vec_stride[ch[k]] + off[k] ]
+struct UnpackChan {
+  long base[2];
+  long vec_stride[2];
+};
+__global__ void unpack_kernel(double* __restrict__ hz, long ext_dim, int nvec, const long* __restrict__ indptr,
+                              const long* __restrict__ offs, const signed char* __restrict__ chans,
+                              const double* __restrict__ vals, const double* __restrict__ sig, UnpackChan uc) {
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int x = blockIdx.y;
+  if (e >= ext_dim || x >= nvec) return;
+  double acc = 0.0;
+  for (long k = indptr[e]; k < indptr[e + 1]; ++k) {
+    const int c = chans[k];
+    acc += vals[k] * sig[uc.base[c] + (long)x * uc.vec_stride[c] + offs[k]];
+  }
+  hz[(long)x * ext_dim + e] = acc;
+}
+
+// dst[b][c][r] = src[b][r][c]   (32x32 tiles through shared memory)
+__global__ void transpose_kernel(double* __restrict__ dst, long ldd, long dst_batch, const double* __restrict__ src, long lds,
+                                 long src_batch, int rows, int cols) {
+  __shared__ double tile[32][33];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const double* s = src + (long)b * src_batch;
+  double* d = dst + (long)b * dst_batch;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int r = r0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (r < rows && c < cols) ? s[(long)r * lds + c] : 0.0;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int c = c0 + j, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) d[(long)c * ldd + r] = tile[threadIdx.x][j];
+  }
+}
+
+// ZTs[x][a][j] = w[jblk(j)][bblk(a)] * ZT[x][a][j]   (block weights of the exchange build)
+struct BlockSplit {
+  int o2off;   // start of the 2nd occ block (>= no means single block)
+  int v2off;
+  double w[2][2];  // [jblk][bblk]
+};
+__global__ void scale_blocks_kernel(double* __restrict__ dst, const double* __restrict__ src, long ld, long batch, int nv, int no,
+                                    BlockSplit bs) {
+  const int x = blockIdx.z;
+  const int a = blockIdx.y;
+  const int bb = a >= bs.v2off ? 1 : 0;
+  const double* s = src + (long)x * batch + (long)a * ld;
+  double* d = dst + (long)x * batch + (long)a * ld;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < no; j += gridDim.x * blockDim.x)
+    d[j] = s[j] * bs.w[j >= bs.o2off ? 1 : 0][bb];
+}
+
+// dst[r][c] (ldd) = src[r][c] (lds), optional lower-triangular packed source (PySCF cderi rows)
+__global__ void pad_copy_kernel(double* __restrict__ dst, long ldd, long dst_batch, const double* __restrict__ src, long lds,
+                                long src_batch, int rows, int cols) {
+  const int b = blockIdx.z;
+  const int r = blockIdx.y;
+  const double* s = src + (long)b * src_batch + (long)r * lds;
+  double* d = dst + (long)b * dst_batch + (long)r * ldd;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x) d[c] = s[c];
+}
+__global__ void unpack_tril_kernel(double* __restrict__ dst, long ldd, long dst_batch, const double* __restrict__ src,
+                                   long src_batch, int n) {
+  const int b = blockIdx.z;
+  const int r = blockIdx.y;
+  const double* s = src + (long)b * src_batch;
+  double* d = dst + (long)b * dst_batch + (long)r * ldd;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+    const long hi = r > c ? r : c, lo = r > c ? c : r;
+    d[c] = s[hi * (hi + 1) / 2 + lo];
+  }
+}
+
+// dst[i][p] = (idx[p] >= 0) ? C[i][idx[p]] : 0   (gather MO columns; zero pad orbitals)
+__global__ void gather_cols_kernel(double* __restrict__ dst, long ldd, const double* __restrict__ C, long ldc, int nao,
+                                   const int* __restrict__ idx, int n) {
+  const int i = blockIdx.y;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+    const int k = idx[p];
+    dst[(long)i * ldd + p] = k >= 0 ? C[(long)i * ldc + k] : 0.0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// grid kernel weighting: Y (half-transformed trial density on the grid) -> A (weighted occupied values)
+//   rho^s_c(g,x) = sum_o Y^s_c[g,x,o] phi^s_0[g,o] (+ Y^s_0 phi^s_c for gradient components)   warp-shuffle reduction
+//   wv = f_xc . rho  (kernel kind), A^s_0 = wv_0 phi_0 + sum_k wv_k phi_k,  A^s_k = wv_k phi_0
+// One warp per grid point, lanes over the occupied index, loop over trial vectors.  In place (A overwrites Y).
+// ------------------------------------------------------------------------------------------------------
+enum { XC_KIND_UKS = 1, XC_KIND_ALDA0 = 2, XC_KIND_MCOL = 3 };
+
+struct XcArgs {
+  int nch, nvec, gb;
+  long g0;                 // first grid point of this chunk (index into phi / kernel arrays)
+  double* Y[2];            // [nvar][gb][ldY]
+  long ldY[2];
+  long y_comp[2];          // component stride of Y
+  const double* phi[2];    // [nvar][ng][ldphi]
+  long ldphi[2];
+  long phi_comp[2];
+  int no[2];
+  const double* wf;        // per-point kernel data: UKS [ng][(2 nvar)^2] (weighted), ALDA0 [ng], MCOL [ng][nvar^2] (2 w f)
+};
+
+template <int NVAR, int KIND>
+__global__ void __launch_bounds__(256) xc_weight_kernel(const XcArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long g = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (g >= a.gb) return;
+  constexpr int NCH = (KIND == XC_KIND_UKS) ? 2 : 1;
+  constexpr int NR = NCH * NVAR;
+  // kernel row for this grid point (kept in registers across the vector loop)
+  double fk[(KIND == XC_KIND_UKS) ? NR : (KIND == XC_KIND_MCOL ? NVAR : 1)];
+  if (KIND == XC_KIND_UKS) {
+    // lane l < NR owns output component l = t*NVAR + d and needs wf[g][l][*]
+    const double* row = a.wf + (a.g0 + g) * (long)(NR * NR);
+#pragma unroll
+    for (int q = 0; q < NR; ++q) fk[q] = (lane < NR) ? row[lane * NR + q] : 0.0;
+  } else if (KIND == XC_KIND_MCOL) {
+    const double* row = a.wf + (a.g0 + g) * (long)(NVAR * NVAR);
+#pragma unroll
+    for (int q = 0; q < NVAR; ++q) fk[q] = (lane < NVAR) ? row[lane * NVAR + q] : 0.0;
+  } else {
+    fk[0] = a.wf[a.g0 + g];
+  }
+  for (int x = 0; x < a.nvec; ++x) {
+    double rho[NR];
+#pragma unroll
+    for (int q = 0; q < NR; ++q) rho[q] = 0.0;
+#pragma unroll
+    for (int s = 0; s < NCH; ++s) {
+      const double* y = a.Y[s] + g * a.ldY[s] + (long)x * a.no[s];
+      const double* p = a.phi[s] + (a.g0 + g) * a.ldphi[s];
+      for (int o = lane; o < a.no[s]; o += 32) {
+        const double y0 = y[o], p0 = p[o];
+        rho[s * NVAR] += y0 * p0;
+#pragma unroll
+        for (int k = 1; k < NVAR; ++k)
+          rho[s * NVAR + k] += y[k * a.y_comp[s] + o] * p0 + y0 * p[k * a.phi_comp[s] + o];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NR; ++q) rho[q] = warp_sum(rho[q]);
+    double wv[NR];
+    if (KIND == XC_KIND_UKS) {
+      double mine = 0.0;
+#pragma unroll
+      for (int q = 0; q < NR; ++q) mine += fk[q] * rho[q];      // wv[t,d] = sum_{s,c} wf[g][t,d][s,c] rho[s,c]
+#pragma unroll
+      for (int q = 0; q < NR; ++q) wv[q] = __shfl_sync(0xffffffffu, mine, q);
+    } else if (KIND == XC_KIND_MCOL) {
+      double mine = 0.0;
+#pragma unroll
+      for (int q = 0; q < NVAR; ++q) mine += fk[q] * rho[q];    // wv[a] = sum_b (2 w f[b,a]) rho[b]
+#pragma unroll
+      for (int q = 0; q < NVAR; ++q) wv[q] = __shfl_sync(0xffffffffu, mine, q);
+    } else {
+      wv[0] = rho[0] * fk[0];
+    }
+#pragma unroll
+    for (int s = 0; s < NCH; ++s) {
+      double* y = a.Y[s] + g * a.ldY[s] + (long)x * a.no[s];
+      const double* p = a.phi[s] + (a.g0 + g) * a.ldphi[s];
+      for (int o = lane; o < a.no[s]; o += 32) {
+        const double p0 = p[o];
+        double a0 = wv[s * NVAR] * p0;
+        if (KIND != XC_KIND_ALDA0) {
+#pragma unroll
+          for (int k = 1; k < NVAR; ++k) {
+            a0 += wv[s * NVAR + k] * p[k * a.phi_comp[s] + o];
+            y[k * a.y_comp[s] + o] = wv[s * NVAR + k] * p0;
+          }
+        }
+        y[o] = a0;
+      }
+    }
+  }
+}
+
+// per-point kernel tables (once per solve)
+// UKS: wf[g][t*nvar+d][s*nvar+c] = w[g] * fxc[s,c,t,d,g]
+__global__ void build_wf_uks_kernel(double* __restrict__ wf, const double* __restrict__ fxc, const double* __restrict__ w, long ng,
+                                    int nvar) {
+  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ng) return;
+  const int nr = 2 * nvar;
+  for (int td = 0; td < nr; ++td)
+    for (int sc = 0; sc < nr; ++sc) wf[g * nr * nr + td * nr + sc] = w[g] * fxc[((long)sc * nr + td) * ng + g];
+}
+// MCOL: wf[g][a][b] = 2 w[g] fxc[b,a,g]
+__global__ void build_wf_mcol_kernel(double* __restrict__ wf, const double* __restrict__ fxc, const double* __restrict__ w, long ng,
+                                     int nvar) {
+  const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ng) return;
+  for (int a = 0; a < nvar; ++a)
+    for (int b = 0; b < nvar; ++b) wf[g * nvar * nvar + a * nvar + b] = 2.0 * w[g] * fxc[((long)b * nvar + a) * ng + g];
+}
+
+// ------------------------------------------------------------------------------------------------------
+// density-fitted Coulomb blocks
+// ------------------------------------------------------------------------------------------------------
+// R[x][P] = sum_{i,a in block} L[P][i][a] * Z[x][r0+i][c0+a]        one CTA per aux function
+template <int XC>
+__global__ void __launch_bounds__(256) j_rho_kernel(double* __restrict__ R, long r_vec_stride, const double* __restrict__ L, long ldl,
+                                                    long l_slice, const double* __restrict__ Z, long ldz, long z_vec_stride, int nr,
+                                                    int nc, int nvec) {
+  __shared__ double sm[8];
+  const long P = blockIdx.x;
+  const double* lp = L + P * l_slice;
+  for (int x0 = 0; x0 < nvec; x0 += XC) {
+    double acc[XC];
+#pragma unroll
+    for (int q = 0; q < XC; ++q) acc[q] = 0.0;
+    for (long e = threadIdx.x; e < (long)nr * nc; e += blockDim.x) {
+      const long i = e / nc, c = e - i * nc;
+      const double l = lp[i * ldl + c];
+#pragma unroll
+      for (int q = 0; q < XC; ++q)
+        if (x0 + q < nvec) acc[q] += l * Z[(long)(x0 + q) * z_vec_stride + i * ldz + c];
+    }
+#pragma unroll
+    for (int q = 0; q < XC; ++q) {
+      const double t = block_sum<256>(acc[q], sm);
+      if (threadIdx.x == 0 && x0 + q < nvec) R[(long)(x0 + q) * r_vec_stride + P] = t;
+    }
+  }
+}
+
+// Rm[x][t][P] = sum_s mix[t][s] R[x][s][P]
+__global__ void j_mix_kernel(double* __restrict__ Rm, const double* __restrict__ R, const double* __restrict__ mix, int njb, long naux,
+                             int nvec) {
+  const long P = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int x = blockIdx.y;
+  if (P >= naux || x >= nvec) return;
+  for (int t = 0; t < njb; ++t) {
+    double acc = 0.0;
+    for (int s = 0; s < njb; ++s) acc += mix[t * njb + s] * R[((long)x * njb + s) * naux + P];
+    Rm[((long)x * njb + t) * naux + P] = acc;
+  }
+}
+
+// S[x][r0+i][c0+a] += sum_P Rm[x][P] * L[P][i][a]      each thread owns one block element, XC vectors at a time
+template <int XC>
+__global__ void __launch_bounds__(256) j_apply_kernel(double* __restrict__ S, long lds, long s_vec_stride, const double* __restrict__ L,
+                                                      long ldl, long l_slice, const double* __restrict__ Rm, long r_vec_stride, long naux,
+                                                      int nr, int nc, int nvec) {
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int x0 = blockIdx.y * XC;
+  if (e >= (long)nr * nc) return;
+  const long i = e / nc, c = e - i * nc;
+  double acc[XC];
+#pragma unroll
+  for (int q = 0; q < XC; ++q) acc[q] = 0.0;
+  const double* lp = L + i * ldl + c;
+  for (long P = 0; P < naux; ++P) {
+    const double l = lp[P * l_slice];
+#pragma unroll
+    for (int q = 0; q < XC; ++q)
+      if (x0 + q < nvec) acc[q] += l * Rm[(long)(x0 + q) * r_vec_stride + P];
+  }
+#pragma unroll
+  for (int q = 0; q < XC; ++q)
+    if (x0 + q < nvec) S[(long)(x0 + q) * s_vec_stride + i * lds + c] += acc[q];
+}
+
+// out[i][a] = sum_P L[P][i][a]^2   (Coulomb diagonals (ia|ia) for the XSF preconditioner)
+__global__ void jblock_diag_kernel(double* __restrict__ out, const double* __restrict__ L, long ldl, long l_slice, long naux, int nr,
+                                   int nc, int accumulate) {
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long)nr * nc) return;
+  const long i = e / nc, c = e - i * nc;
+  double acc = 0.0;
+  for (long P = 0; P < naux; ++P) {
+    const double l = L[P * l_slice + i * ldl + c];
+    acc += l * l;
+  }
+  out[e] = acc + (accumulate ? out[e] : 0.0);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// local terms
+// ------------------------------------------------------------------------------------------------------
+// d[x] = <V, Zsrc[x]>   over a dense [no][nv] block (ld shared)
+__global__ void __launch_bounds__(256) block_dot_kernel(double* __restrict__ d, const double* __restrict__ V, const double* __restrict__ Z,
+                                                        long ld, long z_vec_stride, int no, int nv) {
+  __shared__ double sm[8];
+  const int x = blockIdx.x;
+  double acc = 0.0;
+  for (long e = threadIdx.x; e < (long)no * nv; e += blockDim.x) {
+    const long i = e / nv, a = e - i * nv;
+    acc += V[i * ld + a] * Z[(long)x * z_vec_stride + i * ld + a];
+  }
+  const double t = block_sum<256>(acc, sm);
+  if (threadIdx.x == 0) d[x] = t;
+}
+// S[x] += d[x] * U
+__global__ void block_axpy_kernel(double* __restrict__ S, const double* __restrict__ U, const double* __restrict__ d, long ld,
+                                  long s_vec_stride, int no, int nv) {
+  const int x = blockIdx.y;
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long)no * nv) return;
+  const long i = e / nv, a = e - i * nv;
+  S[(long)x * s_vec_stride + i * ld + a] += d[x] * U[i * ld + a];
+}
+// S[x] += D o Z[x]
+__global__ void block_diag_kernel(double* __restrict__ S, const double* __restrict__ D, const double* __restrict__ Z, long ld,
+                                  long vec_stride, int no, int nv) {
+  const int x = blockIdx.y;
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long)no * nv) return;
+  const long i = e / nv, a = e - i * nv;
+  const long o = (long)x * vec_stride + i * ld + a;
+  S[o] += D[i * ld + a] * Z[o];
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Davidson vector primitives (subspace orthogonalisation, projected matrix, Ritz vectors, residuals)
+// ------------------------------------------------------------------------------------------------------
+// G[i][j] = <A_i, B_j>    one CTA per (i, j) pair
+__global__ void __launch_bounds__(512) vec_dots_kernel(double* __restrict__ G, int ldg, const double* __restrict__ A, long lda,
+                                                       const double* __restrict__ B, long ldb, long n) {
+  __shared__ double sm[16];
+  const double* a = A + (long)blockIdx.y * lda;
+  const double* b = B + (long)blockIdx.x * ldb;
+  double acc0 = 0.0, acc1 = 0.0;
+  long e = threadIdx.x;
+  for (; e + 512 < n; e += 1024) {
+    acc0 += a[e] * b[e];
+    acc1 += a[e + 512] * b[e + 512];
+  }
+  for (; e < n; e += 512) acc0 += a[e] * b[e];
+  const double t = block_sum<512>(acc0 + acc1, sm);
+  if (threadIdx.x == 0) G[blockIdx.y * ldg + blockIdx.x] = t;
+}
+
+// Y[i] = beta*Y[i] + sum_j C[i][j] X[j]   (m outputs, k inputs)
+template <int MB>
+__global__ void __launch_bounds__(256) vec_lincomb_kernel(double* __restrict__ Y, long ldy, const double* __restrict__ X, long ldx,
+                                                          const double* __restrict__ C, int ldc, int m, int k, long n, double beta) {
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int i0 = blockIdx.y * MB;
+  if (e >= n) return;
+  double acc[MB];
+#pragma unroll
+  for (int q = 0; q < MB; ++q) acc[q] = 0.0;
+  for (int j = 0; j < k; ++j) {
+    const double xv = X[(long)j * ldx + e];
+#pragma unroll
+    for (int q = 0; q < MB; ++q)
+      if (i0 + q < m) acc[q] += C[(i0 + q) * ldc + j] * xv;
+  }
+#pragma unroll
+  for (int q = 0; q < MB; ++q)
+    if (i0 + q < m) {
+      double* y = Y + (long)(i0 + q) * ldy + e;
+      *y = (beta != 0.0 ? beta * *y : 0.0) + acc[q];
+    }
+}
+
+// r[k] = ax[k] - e[k]*x[k];  nrm2[k] = |r[k]|^2
+__global__ void __launch_bounds__(512) vec_residual_kernel(double* __restrict__ R, const double* __restrict__ AX, const double* __restrict__ X,
+                                                           long ld, const double* __restrict__ e, double* __restrict__ nrm2, long n) {
+  __shared__ double sm[16];
+  const int k = blockIdx.x;
+  const double ek = e[k];
+  double acc = 0.0;
+  for (long i = threadIdx.x; i < n; i += 512) {
+    const double r = AX[(long)k * ld + i] - ek * X[(long)k * ld + i];
+    R[(long)k * ld + i] = r;
+    acc += r * r;
+  }
+  const double t = block_sum<512>(acc, sm);
+  if (threadIdx.x == 0) nrm2[k] = t;
+}
+
+// x[k] = x[k] / clamp(hdiag - shift[k]);  nrm2[k] = |x[k]|^2   (diagonal preconditioner, make_diag_precond)
+__global__ void __launch_bounds__(512) vec_precond_kernel(double* __restrict__ X, long ld, const double* __restrict__ hdiag,
+                                                          const double* __restrict__ shift, double* __restrict__ nrm2, long n) {
+  __shared__ double sm[16];
+  const int k = blockIdx.x;
+  const double sh = shift[k];
+  double acc = 0.0;
+  for (long i = threadIdx.x; i < n; i += 512) {
+    double d = hdiag[i] - sh;
+    if (fabs(d) < 1e-8) d = 1e-8;
+    const double v = X[(long)k * ld + i] / d;
+    X[(long)k * ld + i] = v;
+    acc += v * v;
+  }
+  const double t = block_sum<512>(acc, sm);
+  if (threadIdx.x == 0) nrm2[k] = t;
+}
+
+// x[k] *= s[k]
+__global__ void vec_scale_kernel(double* __restrict__ X, long ld, const double* __restrict__ s, long n) {
+  const int k = blockIdx.y;
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) X[(long)k * ld + i] *= s[k];
+}
+
+}  // namespace xtd

@@ -1,0 +1,1121 @@
+// libxtdsigma.so: engine + C-ABI (include/xtd_sigma.h).  sm_100a only.
+//
+// Data layout in HBM (all fp64, leading dimensions padded to 16 doubles):
+//   per channel   Co/Cv [nao][ld], CoT/CvT [n][ldN]        AO <-> internal MO positions (zero pad orbitals)
+//   per (tensor, channel) with an exchange term
+//                 Loo [naux_loc][no][ld_oo], Lvv [naux_loc][nv][ld_vv]   MO-resident 3-centre blocks
+//   per Coulomb block  Ljb [naux_loc][nr][ld]
+//   grid          ao (caller's buffer, [nvar][ng][ld]), phi [ch][nvar][ng][ld_o] = ao . Co, per-point kernel table wf
+//   per call (workspace arena)  Z, ZT, ZTs, SIG, mo1T, RT, Y/U chunk, split-K partials
+#include "../../include/xtd_sigma.h"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+namespace xtd {
+thread_local char g_last_error[512] = {0};
+unsigned long long g_launch_count = 0;
+
+struct DevBuf {
+  double* p = nullptr;
+  size_t bytes = 0;
+  int alloc(size_t n_doubles) {
+    release();
+    bytes = std::max<size_t>(n_doubles, 2) * 8;
+    XTD_CUDA(cudaMalloc(&p, bytes));
+    XTD_CUDA(cudaMemset(p, 0, bytes));
+    return XTD_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+};
+
+struct Channel {
+  int spin_o, spin_v, no, nv;
+  std::vector<int> occ_idx, vir_idx;
+  std::vector<std::pair<int, int>> o_blocks, v_blocks;
+  long ldz, ldzt, ldco, ldcv, ldN;
+  DevBuf Co, Cv, CoT, CvT;          // [nao][ldco], [nao][ldcv], [no][ldN], [nv][ldN]
+  DevBuf Loo[2], Lvv[2];            // per DF tensor
+  long ldoo, ldvv;
+  bool need_k[2] = {false, false};
+  DevBuf phi;                       // [nvar_eff][ng][ldphi]
+  long ldphi = 0;
+  // gather CSR
+  long *g_indptr = nullptr, *g_cols = nullptr;
+  double* g_vals = nullptr;
+  long g_nnz = 0;
+};
+
+struct KTermRec {
+  int tensor, ch, nob, nvb;
+  double w[2][2][2][2];
+  bool uniform;
+};
+struct JBlockRec {
+  int ch, r0, nr, c0, nc;
+  long ld;
+  DevBuf L;   // [naux_loc][nr][ld]
+};
+struct LocalGemmRec {
+  int side, dch, r0, nr, c0, nc, sch, sr0, sc0, mrows, mcols;
+  long ldm;
+  double alpha;
+  DevBuf M;
+};
+struct Rank1Rec {
+  int dch, sch;
+  DevBuf U, V;
+};
+struct DiagRec {
+  int ch;
+  DevBuf D;
+};
+
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, used = 0;
+  double* take(size_t n_doubles) {
+    size_t b = (n_doubles * 8 + 255) & ~(size_t)255;
+    if (used + b > cap) return nullptr;
+    double* p = (double*)(base + used);
+    used += b;
+    return p;
+  }
+  size_t left() const { return cap - used; }
+};
+
+}  // namespace xtd
+
+using namespace xtd;
+
+struct xtd_engine {
+  int nao = 0;
+  long ldN = 0;
+  cudaStream_t stream = 0;
+  GemmContext gemm;
+  Arena arena;
+  size_t split_ws_bytes = 0;
+  // orbitals
+  const double* C[2] = {nullptr, nullptr};
+  long ldC[2] = {0, 0};
+  int nmo[2] = {0, 0};
+  std::vector<Channel*> ch;
+  std::vector<KTermRec> kterms;
+  std::vector<JBlockRec*> jblocks;
+  std::vector<double> jmix;
+  DevBuf jmix_dev;
+  long naux[2] = {0, 0};       // local aux count per tensor
+  long naux_filled[2] = {0, 0};
+  // grid
+  const double* ao = nullptr;
+  const double* wgrid = nullptr;
+  int nvar = 0, nvar_eff = 0;
+  long ng = 0, ao_ld = 0, ao_comp = 0;
+  int fxc_kind = XTD_FXC_NONE;
+  const double* fxc = nullptr;
+  DevBuf wf;
+  // local terms
+  std::vector<LocalGemmRec*> lgemms;
+  std::vector<Rank1Rec*> rank1s;
+  std::vector<DiagRec*> diags;
+  // scatter
+  long ext_dim = 0;
+  long *s_indptr = nullptr, *s_offs = nullptr;
+  signed char* s_chans = nullptr;
+  double* s_vals = nullptr;
+  // state
+  bool finalized = false;
+  int max_nvec = 0;
+  int cur_nvec = 0;
+  // per-call buffers (arena)
+  double *Z[2] = {nullptr, nullptr}, *ZT[2] = {nullptr, nullptr}, *ZTs[2] = {nullptr, nullptr};
+  double* SIG = nullptr;
+  long sig_base[2] = {0, 0};
+  double *mo1T[2] = {nullptr, nullptr}, *RT[2] = {nullptr, nullptr};
+  double* scratch = nullptr;      // Y / U chunk region
+  size_t scratch_doubles = 0;
+  double *jR = nullptr, *jRm = nullptr, *r1d = nullptr;
+  // pinned staging for the host entry
+  double *pin_in = nullptr, *pin_out = nullptr, *dev_in = nullptr, *dev_out = nullptr;
+  size_t pin_doubles = 0;
+  // timers
+  cudaEvent_t ev[2 * 12];
+  bool ev_ok = false;
+  float ms[12] = {0};
+  unsigned long long launches0 = 0;
+  double flops0 = 0;
+};
+
+namespace {
+
+struct PhaseTimer {
+  xtd_engine* h;
+  int id;
+  PhaseTimer(xtd_engine* h_, int id_) : h(h_), id(id_) {
+    if (h->ev_ok) cudaEventRecord(h->ev[2 * id], h->stream);
+  }
+  ~PhaseTimer() {
+    if (h->ev_ok) cudaEventRecord(h->ev[2 * id + 1], h->stream);
+  }
+};
+
+inline dim3 grid1d(long n, int threads, int y = 1, int z = 1) { return dim3((unsigned)cdiv(n, threads), y, z); }
+
+#define LAUNCH_CHECK()              \
+  do {                              \
+    XTD_COUNT_LAUNCH();             \
+    XTD_CUDA(cudaGetLastError());   \
+  } while (0)
+
+int upload_padded(DevBuf& dst, long& ld, const double* host, int rows, int cols, cudaStream_t s) {
+  ld = pad_ld(cols);
+  XTD_TRY(dst.alloc((size_t)std::max(rows, 1) * ld));
+  if (rows > 0 && cols > 0)
+    XTD_CUDA(cudaMemcpy2D(dst.p, ld * 8, host, (size_t)cols * 8, (size_t)cols * 8, rows, cudaMemcpyHostToDevice));
+  return XTD_OK;
+}
+
+template <typename T>
+int upload_array(T** dst, const T* host, size_t n) {
+  if (*dst) cudaFree(*dst);
+  *dst = nullptr;
+  XTD_CUDA(cudaMalloc((void**)dst, std::max<size_t>(n, 1) * sizeof(T)));
+  if (n) XTD_CUDA(cudaMemcpy(*dst, host, n * sizeof(T), cudaMemcpyHostToDevice));
+  return XTD_OK;
+}
+
+// ---- layout of the internal sigma / Z buffers for nvec vectors: channel-major, each [nvec*no][ldz] -----
+void sig_layout(const xtd_engine* h, int nvec, long* base, long* total) {
+  long off = 0;
+  for (size_t c = 0; c < h->ch.size(); ++c) {
+    base[c] = off;
+    off += (long)nvec * h->ch[c]->no * h->ch[c]->ldz;
+  }
+  *total = off;
+}
+
+int build_channel_matrices(xtd_engine* h, Channel* c) {
+  XTD_REQUIRE(h->C[c->spin_o] && h->C[c->spin_v], XTD_ERR_STATE, "xtd_set_mo must precede xtd_add_channel");
+  const int N = h->nao;
+  c->ldco = pad_ld(c->no);
+  c->ldcv = pad_ld(c->nv);
+  c->ldN = h->ldN;
+  XTD_TRY(c->Co.alloc((size_t)N * c->ldco));
+  XTD_TRY(c->Cv.alloc((size_t)N * c->ldcv));
+  XTD_TRY(c->CoT.alloc((size_t)c->no * c->ldN));
+  XTD_TRY(c->CvT.alloc((size_t)c->nv * c->ldN));
+  int *d_oi = nullptr, *d_vi = nullptr;
+  XTD_TRY(upload_array(&d_oi, c->occ_idx.data(), c->occ_idx.size()));
+  XTD_TRY(upload_array(&d_vi, c->vir_idx.data(), c->vir_idx.size()));
+  gather_cols_kernel<<<dim3((unsigned)cdiv(c->no, 128), N), 128, 0, h->stream>>>(c->Co.p, c->ldco, h->C[c->spin_o], h->ldC[c->spin_o], N,
+                                                                               d_oi, c->no);
+  LAUNCH_CHECK();
+  gather_cols_kernel<<<dim3((unsigned)cdiv(c->nv, 128), N), 128, 0, h->stream>>>(c->Cv.p, c->ldcv, h->C[c->spin_v], h->ldC[c->spin_v], N,
+                                                                               d_vi, c->nv);
+  LAUNCH_CHECK();
+  dim3 tb(32, 8);
+  transpose_kernel<<<dim3((unsigned)cdiv(c->no, 32), (unsigned)cdiv(N, 32), 1), tb, 0, h->stream>>>(c->CoT.p, c->ldN, 0, c->Co.p, c->ldco,
+                                                                                                    0, N, c->no);
+  LAUNCH_CHECK();
+  transpose_kernel<<<dim3((unsigned)cdiv(c->nv, 32), (unsigned)cdiv(N, 32), 1), tb, 0, h->stream>>>(c->CvT.p, c->ldN, 0, c->Cv.p, c->ldcv,
+                                                                                                    0, N, c->nv);
+  LAUNCH_CHECK();
+  XTD_CUDA(cudaStreamSynchronize(h->stream));
+  cudaFree(d_oi);
+  cudaFree(d_vi);
+  return XTD_OK;
+}
+
+MatView view2d(const double* base, long ld, int rows, int cols, int row0 = 0, int col0 = 0) {
+  MatView v;
+  v.base = base; v.ld = ld; v.sq = 0; v.row0 = row0; v.col0 = col0; v.rows = rows; v.cols = cols; v.q0 = 0; v.nq = 1;
+  return v;
+}
+MatView view3d(const double* base, long ld, long sq, int nq, int rows, int cols, int row0 = 0, int col0 = 0, int q0 = 0) {
+  MatView v = view2d(base, ld, rows, cols, row0, col0);
+  v.sq = sq; v.nq = nq; v.q0 = q0;
+  return v;
+}
+
+}  // namespace
+
+// =========================================================================================================
+// C-ABI
+// =========================================================================================================
+extern "C" {
+
+const char* xtd_last_error(void) { return g_last_error; }
+int xtd_version(void) { return 100; }
+unsigned long long xtd_launch_count(void) { return g_launch_count; }
+
+int xtd_create(xtd_handle* out, int nao, long workspace_bytes) {
+  XTD_REQUIRE(out && nao > 0 && workspace_bytes >= (64L << 20), XTD_ERR_ARG, "xtd_create: bad arguments (workspace >= 64 MiB)");
+  int dev = 0, major = 0;
+  XTD_CUDA(cudaGetDevice(&dev));
+  XTD_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  XTD_REQUIRE(major >= 10, XTD_ERR_UNSUPPORTED, "xtd_create: needs an sm_100a device (found compute capability %d.x)", major);
+  xtd_engine* h = new xtd_engine();
+  h->nao = nao;
+  h->ldN = pad_ld(nao);
+  int r = gemm_context_init(h->gemm);
+  if (r != XTD_OK) { delete h; return r; }
+  cudaError_t e = cudaMalloc((void**)&h->arena.base, (size_t)workspace_bytes);
+  if (e != cudaSuccess) {
+    XTD_SET_ERR("xtd_create: cannot allocate %ld workspace bytes: %s", workspace_bytes, cudaGetErrorString(e));
+    delete h;
+    return XTD_ERR_NOMEM;
+  }
+  h->arena.cap = (size_t)workspace_bytes;
+  for (int i = 0; i < 24; ++i) cudaEventCreate(&h->ev[i]);
+  h->ev_ok = true;
+  *out = h;
+  return XTD_OK;
+}
+
+int xtd_destroy(xtd_handle h) {
+  if (!h) return XTD_OK;
+  cudaDeviceSynchronize();
+  for (auto* c : h->ch) {
+    c->Co.release(); c->Cv.release(); c->CoT.release(); c->CvT.release(); c->phi.release();
+    for (int t = 0; t < 2; ++t) { c->Loo[t].release(); c->Lvv[t].release(); }
+    if (c->g_indptr) cudaFree(c->g_indptr);
+    if (c->g_cols) cudaFree(c->g_cols);
+    if (c->g_vals) cudaFree(c->g_vals);
+    delete c;
+  }
+  for (auto* j : h->jblocks) { j->L.release(); delete j; }
+  for (auto* l : h->lgemms) { l->M.release(); delete l; }
+  for (auto* r : h->rank1s) { r->U.release(); r->V.release(); delete r; }
+  for (auto* d : h->diags) { d->D.release(); delete d; }
+  h->jmix_dev.release(); h->wf.release();
+  if (h->s_indptr) cudaFree(h->s_indptr);
+  if (h->s_offs) cudaFree(h->s_offs);
+  if (h->s_chans) cudaFree(h->s_chans);
+  if (h->s_vals) cudaFree(h->s_vals);
+  if (h->arena.base) cudaFree(h->arena.base);
+  if (h->pin_in) cudaFreeHost(h->pin_in);
+  if (h->pin_out) cudaFreeHost(h->pin_out);
+  if (h->dev_in) cudaFree(h->dev_in);
+  if (h->dev_out) cudaFree(h->dev_out);
+  if (h->ev_ok) for (int i = 0; i < 24; ++i) cudaEventDestroy(h->ev[i]);
+  delete h;
+  return XTD_OK;
+}
+
+int xtd_set_stream(xtd_handle h, void* s) {
+  XTD_REQUIRE(h, XTD_ERR_ARG, "null handle");
+  h->stream = (cudaStream_t)s;
+  return XTD_OK;
+}
+
+int xtd_set_mo(xtd_handle h, int spin, const double* c_dev, long ld, int nmo) {
+  XTD_REQUIRE(h && (spin == 0 || spin == 1) && c_dev && ld >= nmo && nmo > 0, XTD_ERR_ARG, "xtd_set_mo: bad arguments");
+  h->C[spin] = c_dev; h->ldC[spin] = ld; h->nmo[spin] = nmo;
+  return XTD_OK;
+}
+
+int xtd_add_channel(xtd_handle h, int spin_o, const int* occ_idx, int no, int spin_v, const int* vir_idx, int nv, const int* o_blocks,
+                    int nob, const int* v_blocks, int nvb) {
+  XTD_REQUIRE(h && !h->finalized, XTD_ERR_STATE, "xtd_add_channel after finalize");
+  XTD_REQUIRE(h->ch.size() < 2, XTD_ERR_UNSUPPORTED, "at most two channels");
+  XTD_REQUIRE(no > 0 && nv > 0 && nob >= 1 && nob <= 2 && nvb >= 1 && nvb <= 2, XTD_ERR_ARG, "xtd_add_channel: bad sizes");
+  Channel* c = new Channel();
+  c->spin_o = spin_o; c->spin_v = spin_v; c->no = no; c->nv = nv;
+  c->occ_idx.assign(occ_idx, occ_idx + no);
+  c->vir_idx.assign(vir_idx, vir_idx + nv);
+  for (int i = 0; i < nob; ++i) c->o_blocks.push_back({o_blocks[2 * i], o_blocks[2 * i + 1]});
+  for (int i = 0; i < nvb; ++i) c->v_blocks.push_back({v_blocks[2 * i], v_blocks[2 * i + 1]});
+  for (int i = 1; i < nob; ++i)
+    if (c->o_blocks[i].first % 2) { delete c; XTD_SET_ERR("occ block start must be even"); return XTD_ERR_ALIGN; }
+  for (int i = 1; i < nvb; ++i)
+    if (c->v_blocks[i].first % 2) { delete c; XTD_SET_ERR("vir block start must be even"); return XTD_ERR_ALIGN; }
+  for (int i = 0; i < no; ++i)
+    if (occ_idx[i] >= h->nmo[spin_o]) { delete c; XTD_SET_ERR("occ index out of range"); return XTD_ERR_ARG; }
+  for (int i = 0; i < nv; ++i)
+    if (vir_idx[i] >= h->nmo[spin_v]) { delete c; XTD_SET_ERR("vir index out of range"); return XTD_ERR_ARG; }
+  c->ldz = pad_ld(nv);
+  c->ldzt = pad_ld(no);
+  c->ldoo = pad_ld(no);
+  c->ldvv = pad_ld(nv);
+  int r = build_channel_matrices(h, c);
+  if (r != XTD_OK) { delete c; return r; }
+  h->ch.push_back(c);
+  return (int)h->ch.size() - 1;
+}
+
+int xtd_channel_layout(xtd_handle h, int chn, int nvec, long* base, long* vec_stride, long* ld) {
+  XTD_REQUIRE(h && chn >= 0 && chn < (int)h->ch.size(), XTD_ERR_ARG, "bad channel");
+  long b[2], tot;
+  sig_layout(h, nvec, b, &tot);
+  if (base) *base = b[chn];
+  if (vec_stride) *vec_stride = (long)h->ch[chn]->no * h->ch[chn]->ldz;
+  if (ld) *ld = h->ch[chn]->ldz;
+  return XTD_OK;
+}
+
+int xtd_add_kterm(xtd_handle h, int tensor, int chn, const double* w, int nob, int nvb) {
+  XTD_REQUIRE(h && !h->finalized && (tensor == 0 || tensor == 1), XTD_ERR_ARG, "xtd_add_kterm: bad arguments");
+  XTD_REQUIRE(chn >= 0 && chn < (int)h->ch.size(), XTD_ERR_ARG, "bad channel");
+  Channel* c = h->ch[chn];
+  XTD_REQUIRE(nob == (int)c->o_blocks.size() && nvb == (int)c->v_blocks.size(), XTD_ERR_ARG, "weight table shape != channel blocks");
+  XTD_REQUIRE(h->naux_filled[tensor] == 0, XTD_ERR_STATE, "exchange terms must be declared before xtd_df_add");
+  KTermRec k;
+  k.tensor = tensor; k.ch = chn; k.nob = nob; k.nvb = nvb;
+  memset(k.w, 0, sizeof(k.w));
+  k.uniform = true;
+  for (int i = 0; i < nob; ++i)
+    for (int a = 0; a < nvb; ++a)
+      for (int j = 0; j < nob; ++j)
+        for (int b = 0; b < nvb; ++b) {
+          k.w[i][a][j][b] = w[((i * nvb + a) * nob + j) * nvb + b];
+          if (k.w[i][a][j][b] != w[0]) k.uniform = false;
+        }
+  h->kterms.push_back(k);
+  c->need_k[tensor] = true;
+  return XTD_OK;
+}
+
+int xtd_add_jblock(xtd_handle h, int chn, int r0, int nr, int c0, int nc) {
+  XTD_REQUIRE(h && !h->finalized && chn >= 0 && chn < (int)h->ch.size(), XTD_ERR_ARG, "xtd_add_jblock: bad arguments");
+  Channel* c = h->ch[chn];
+  XTD_REQUIRE(r0 >= 0 && nr > 0 && r0 + nr <= c->no && c0 >= 0 && nc > 0 && c0 + nc <= c->nv, XTD_ERR_ARG, "J block out of range");
+  XTD_REQUIRE(h->naux_filled[0] == 0, XTD_ERR_STATE, "Coulomb blocks must be declared before xtd_df_add");
+  JBlockRec* j = new JBlockRec();
+  j->ch = chn; j->r0 = r0; j->nr = nr; j->c0 = c0; j->nc = nc; j->ld = pad_ld(nc);
+  h->jblocks.push_back(j);
+  return (int)h->jblocks.size() - 1;
+}
+
+int xtd_set_jmix(xtd_handle h, const double* mix, int n) {
+  XTD_REQUIRE(h && n == (int)h->jblocks.size(), XTD_ERR_ARG, "xtd_set_jmix: size != number of J blocks");
+  h->jmix.assign(mix, mix + (size_t)n * n);
+  XTD_TRY(h->jmix_dev.alloc((size_t)n * n));
+  XTD_CUDA(cudaMemcpy(h->jmix_dev.p, mix, (size_t)n * n * 8, cudaMemcpyHostToDevice));
+  return XTD_OK;
+}
+
+int xtd_df_begin(xtd_handle h, int tensor, long naux_local) {
+  XTD_REQUIRE(h && (tensor == 0 || tensor == 1) && naux_local >= 0, XTD_ERR_ARG, "xtd_df_begin: bad arguments");
+  h->naux[tensor] = naux_local;
+  h->naux_filled[tensor] = 0;
+  for (auto* c : h->ch) {
+    if (!c->need_k[tensor]) continue;
+    XTD_TRY(c->Loo[tensor].alloc((size_t)naux_local * c->no * c->ldoo));
+    XTD_TRY(c->Lvv[tensor].alloc((size_t)naux_local * c->nv * c->ldvv));
+  }
+  if (tensor == 0)
+    for (auto* j : h->jblocks) XTD_TRY(j->L.alloc((size_t)naux_local * j->nr * j->ld));
+  return XTD_OK;
+}
+
+int xtd_df_add(xtd_handle h, int tensor, const double* l_dev, long np, long ld_row, long stride_p, int packed) {
+  XTD_REQUIRE(h && (tensor == 0 || tensor == 1) && l_dev && np > 0, XTD_ERR_ARG, "xtd_df_add: bad arguments");
+  XTD_REQUIRE(h->naux_filled[tensor] + np <= h->naux[tensor], XTD_ERR_ARG, "xtd_df_add: more aux rows than declared (%ld + %ld > %ld)",
+              h->naux_filled[tensor], np, h->naux[tensor]);
+  const int N = h->nao;
+  const long ldN = h->ldN;
+  cudaStream_t s = h->stream;
+  const bool direct = !packed && (ld_row % 2 == 0) && (stride_p % 2 == 0) && (((uintptr_t)l_dev & 15) == 0);
+  // per-aux workspace: staging copy (if needed) + the largest half-transformed block
+  int max_n = 0;
+  for (auto* c : h->ch) {
+    bool need_o = c->need_k[tensor];
+    if (tensor == 0)
+      for (auto* j : h->jblocks) need_o = need_o || (h->ch[j->ch] == c);
+    if (need_o) max_n = std::max(max_n, c->no);
+    if (c->need_k[tensor]) max_n = std::max(max_n, c->nv);
+  }
+  if (max_n == 0) { h->naux_filled[tensor] += np; return XTD_OK; }
+  h->arena.used = 0;
+  size_t split_bytes = std::min<size_t>(h->arena.cap / 4, (size_t)1 << 30);
+  h->gemm.split_ws = h->arena.take(split_bytes / 8);
+  h->gemm.split_ws_bytes = split_bytes;
+  const size_t per_p = ((size_t)(direct ? 0 : N) + (size_t)max_n) * ldN;
+  long pc = (long)(h->arena.left() / 8 / per_p);
+  XTD_REQUIRE(pc >= 1, XTD_ERR_NOMEM, "xtd_df_add: workspace too small for one aux function (%zu doubles needed)", per_p);
+  pc = std::min<long>(pc, np);
+  double* stage = direct ? nullptr : h->arena.take((size_t)pc * N * ldN);
+  double* half = h->arena.take((size_t)pc * max_n * ldN);
+  XTD_REQUIRE(half && (direct || stage), XTD_ERR_NOMEM, "xtd_df_add: workspace exhausted");
+
+  for (long p0 = 0; p0 < np; p0 += pc) {
+    const int pn = (int)std::min<long>(pc, np - p0);
+    const long P0 = h->naux_filled[tensor] + p0;
+    MatView Lv;
+    if (direct) {
+      Lv = view3d(l_dev + p0 * stride_p, ld_row, stride_p, pn, N, N);
+    } else {
+      if (packed) {
+        unpack_tril_kernel<<<dim3((unsigned)cdiv(N, 128), N, pn), 128, 0, s>>>(stage, ldN, (long)N * ldN, l_dev + p0 * stride_p, stride_p, N);
+      } else {
+        pad_copy_kernel<<<dim3((unsigned)cdiv(N, 128), N, pn), 128, 0, s>>>(stage, ldN, (long)N * ldN, l_dev + p0 * stride_p, ld_row,
+                                                                            stride_p, N, N);
+      }
+      LAUNCH_CHECK();
+      Lv = view3d(stage, ldN, (long)N * ldN, pn, N, N);
+    }
+    for (size_t ci = 0; ci < h->ch.size(); ++ci) {
+      Channel* c = h->ch[ci];
+      bool need_o = c->need_k[tensor];
+      if (tensor == 0)
+        for (auto* j : h->jblocks) need_o = need_o || (j->ch == (int)ci);
+      if (need_o) {
+        // HoT[P][i][mu] = sum_nu CoT[i][nu] L[P][mu][nu]
+        GemmDesc d;
+        d.A = view2d(c->CoT.p, ldN, c->no, N); d.B = Lv; d.M = c->no; d.N = N; d.K = N;
+        d.batches = pn; d.z_div = 1; d.a_hi = 0; d.b_hi = 1;
+        d.C = half; d.ldc = ldN; d.c_batch_stride = (long)c->no * ldN;
+        XTD_TRY(gemm(h->gemm, d, s));
+        MatView Hv = view3d(half, ldN, (long)c->no * ldN, pn, c->no, N);
+        if (c->need_k[tensor]) {
+          // Loo[P][i][j] = sum_mu HoT[P][i][mu] CoT[j][mu]
+          GemmDesc e;
+          e.A = Hv; e.B = view2d(c->CoT.p, ldN, c->no, N); e.M = c->no; e.N = c->no; e.K = N;
+          e.batches = pn; e.a_hi = 1; e.b_hi = 0;
+          e.C = c->Loo[tensor].p + P0 * c->no * c->ldoo; e.ldc = c->ldoo; e.c_batch_stride = (long)c->no * c->ldoo;
+          XTD_TRY(gemm(h->gemm, e, s));
+        }
+        if (tensor == 0)
+          for (auto* j : h->jblocks) {
+            if (j->ch != (int)ci) continue;
+            // Ljb[P][i][a] = sum_mu HoT[P][r0+i][mu] CvT[c0+a][mu]
+            GemmDesc e;
+            e.A = view3d(half, ldN, (long)c->no * ldN, pn, j->nr, N, j->r0, 0);
+            e.B = view2d(c->CvT.p, ldN, j->nc, N, j->c0, 0);
+            e.M = j->nr; e.N = j->nc; e.K = N; e.batches = pn; e.a_hi = 1; e.b_hi = 0;
+            e.C = j->L.p + P0 * j->nr * j->ld; e.ldc = j->ld; e.c_batch_stride = (long)j->nr * j->ld;
+            XTD_TRY(gemm(h->gemm, e, s));
+          }
+      }
+      if (c->need_k[tensor]) {
+        // HvT[P][a][mu] = sum_nu CvT[a][nu] L[P][mu][nu] ;  Lvv[P][a][b] = sum_mu HvT[P][a][mu] CvT[b][mu]
+        GemmDesc d;
+        d.A = view2d(c->CvT.p, ldN, c->nv, N); d.B = Lv; d.M = c->nv; d.N = N; d.K = N;
+        d.batches = pn; d.a_hi = 0; d.b_hi = 1;
+        d.C = half; d.ldc = ldN; d.c_batch_stride = (long)c->nv * ldN;
+        XTD_TRY(gemm(h->gemm, d, s));
+        GemmDesc e;
+        e.A = view3d(half, ldN, (long)c->nv * ldN, pn, c->nv, N); e.B = view2d(c->CvT.p, ldN, c->nv, N);
+        e.M = c->nv; e.N = c->nv; e.K = N; e.batches = pn; e.a_hi = 1; e.b_hi = 0;
+        e.C = c->Lvv[tensor].p + P0 * c->nv * c->ldvv; e.ldc = c->ldvv; e.c_batch_stride = (long)c->nv * c->ldvv;
+        XTD_TRY(gemm(h->gemm, e, s));
+      }
+    }
+  }
+  h->naux_filled[tensor] += np;
+  XTD_CUDA(cudaStreamSynchronize(s));   // the caller may free / overwrite its chunk
+  return XTD_OK;
+}
+
+int xtd_jblock_diag(xtd_handle h, int jb, double* out_dev) {
+  XTD_REQUIRE(h && jb >= 0 && jb < (int)h->jblocks.size() && out_dev, XTD_ERR_ARG, "xtd_jblock_diag: bad arguments");
+  JBlockRec* j = h->jblocks[jb];
+  jblock_diag_kernel<<<grid1d((long)j->nr * j->nc, 256), 256, 0, h->stream>>>(out_dev, j->L.p, j->ld, (long)j->nr * j->ld, h->naux[0], j->nr,
+                                                                             j->nc, 0);
+  LAUNCH_CHECK();
+  return XTD_OK;
+}
+
+int xtd_set_grid(xtd_handle h, const double* ao_dev, int nvar, long ng, long ld_row, long stride_comp, const double* w_dev) {
+  XTD_REQUIRE(h && !h->finalized, XTD_ERR_STATE, "xtd_set_grid after finalize");
+  XTD_REQUIRE(ao_dev && w_dev && (nvar == 1 || nvar == 4) && ng >= 0 && ld_row >= h->nao, XTD_ERR_ARG, "xtd_set_grid: bad arguments");
+  XTD_REQUIRE(ld_row % 2 == 0 && stride_comp % 2 == 0 && ((uintptr_t)ao_dev & 15) == 0, XTD_ERR_ALIGN,
+              "xtd_set_grid: ao needs even ld_row / stride_comp and a 16-byte aligned base (pad with xtd helpers)");
+  h->ao = ao_dev; h->nvar = nvar; h->ng = ng; h->ao_ld = ld_row; h->ao_comp = stride_comp; h->wgrid = w_dev;
+  return XTD_OK;
+}
+
+int xtd_set_fxc(xtd_handle h, int kind, const double* fxc_dev) {
+  XTD_REQUIRE(h && !h->finalized, XTD_ERR_STATE, "xtd_set_fxc after finalize");
+  XTD_REQUIRE(kind >= XTD_FXC_NONE && kind <= XTD_FXC_MCOL && (kind == XTD_FXC_NONE || fxc_dev), XTD_ERR_ARG, "xtd_set_fxc: bad arguments");
+  h->fxc_kind = kind; h->fxc = fxc_dev;
+  return XTD_OK;
+}
+
+int xtd_add_local_gemm(xtd_handle h, int side, int dch, int r0, int nr, int c0, int nc, int sch, int sr0, int sc0, const double* mat,
+                       int mrows, int mcols, double alpha) {
+  XTD_REQUIRE(h && !h->finalized && mat, XTD_ERR_ARG, "xtd_add_local_gemm: bad arguments");
+  XTD_REQUIRE(dch >= 0 && dch < (int)h->ch.size() && sch >= 0 && sch < (int)h->ch.size(), XTD_ERR_ARG, "bad channel");
+  Channel *dc = h->ch[dch], *sc = h->ch[sch];
+  XTD_REQUIRE(r0 >= 0 && r0 + nr <= dc->no && c0 >= 0 && c0 + nc <= dc->nv, XTD_ERR_ARG, "local gemm: destination out of range");
+  XTD_REQUIRE(c0 % 2 == 0 && sc0 % 2 == 0, XTD_ERR_ALIGN, "local gemm: column offsets must be even");
+  if (side == XTD_SIDE_RIGHT) {
+    XTD_REQUIRE(mcols == nc && sr0 + nr <= sc->no && sc0 + mrows <= sc->nv, XTD_ERR_ARG, "right gemm: shapes inconsistent");
+  } else {
+    XTD_REQUIRE(side == XTD_SIDE_LEFT && mrows == nr && sr0 + mcols <= sc->no && sc0 + nc <= sc->nv, XTD_ERR_ARG, "left gemm: shapes inconsistent");
+  }
+  LocalGemmRec* l = new LocalGemmRec();
+  l->side = side; l->dch = dch; l->r0 = r0; l->nr = nr; l->c0 = c0; l->nc = nc; l->sch = sch; l->sr0 = sr0; l->sc0 = sc0;
+  l->mrows = mrows; l->mcols = mcols; l->alpha = alpha;
+  int r = upload_padded(l->M, l->ldm, mat, mrows, mcols, h->stream);
+  if (r != XTD_OK) { delete l; return r; }
+  h->lgemms.push_back(l);
+  return XTD_OK;
+}
+
+int xtd_add_rank1(xtd_handle h, int dch, const double* u, int sch, const double* v) {
+  XTD_REQUIRE(h && !h->finalized && u && v && dch >= 0 && dch < (int)h->ch.size() && sch >= 0 && sch < (int)h->ch.size(), XTD_ERR_ARG,
+              "xtd_add_rank1: bad arguments");
+  Rank1Rec* r = new Rank1Rec();
+  r->dch = dch; r->sch = sch;
+  long ld;
+  XTD_TRY(upload_padded(r->U, ld, u, h->ch[dch]->no, h->ch[dch]->nv, h->stream));
+  XTD_TRY(upload_padded(r->V, ld, v, h->ch[sch]->no, h->ch[sch]->nv, h->stream));
+  h->rank1s.push_back(r);
+  return XTD_OK;
+}
+
+int xtd_add_diag(xtd_handle h, int chn, const double* d_host) {
+  XTD_REQUIRE(h && !h->finalized && d_host && chn >= 0 && chn < (int)h->ch.size(), XTD_ERR_ARG, "xtd_add_diag: bad arguments");
+  DiagRec* d = new DiagRec();
+  d->ch = chn;
+  long ld;
+  XTD_TRY(upload_padded(d->D, ld, d_host, h->ch[chn]->no, h->ch[chn]->nv, h->stream));
+  h->diags.push_back(d);
+  return XTD_OK;
+}
+
+int xtd_set_gather(xtd_handle h, int chn, const long* indptr, const long* cols, const double* vals, long nnz) {
+  XTD_REQUIRE(h && chn >= 0 && chn < (int)h->ch.size() && indptr && nnz >= 0, XTD_ERR_ARG, "xtd_set_gather: bad arguments");
+  Channel* c = h->ch[chn];
+  XTD_TRY(upload_array(&c->g_indptr, indptr, (size_t)c->no * c->nv + 1));
+  XTD_TRY(upload_array(&c->g_cols, cols, (size_t)nnz));
+  XTD_TRY(upload_array(&c->g_vals, vals, (size_t)nnz));
+  c->g_nnz = nnz;
+  return XTD_OK;
+}
+
+int xtd_set_scatter(xtd_handle h, long ext_dim, const long* indptr, const long* offs, const signed char* chans, const double* vals,
+                    long nnz) {
+  XTD_REQUIRE(h && ext_dim > 0 && indptr && nnz >= 0, XTD_ERR_ARG, "xtd_set_scatter: bad arguments");
+  h->ext_dim = ext_dim;
+  XTD_TRY(upload_array(&h->s_indptr, indptr, (size_t)ext_dim + 1));
+  XTD_TRY(upload_array(&h->s_offs, offs, (size_t)nnz));
+  XTD_TRY(upload_array(&h->s_chans, chans, (size_t)nnz));
+  XTD_TRY(upload_array(&h->s_vals, vals, (size_t)nnz));
+  return XTD_OK;
+}
+
+int xtd_finalize(xtd_handle h, int max_nvec) {
+  XTD_REQUIRE(h && max_nvec >= 1, XTD_ERR_ARG, "xtd_finalize: bad arguments");
+  XTD_REQUIRE(!h->ch.empty() && h->ext_dim > 0, XTD_ERR_STATE, "xtd_finalize: channels and layout maps are required");
+  for (auto* c : h->ch) XTD_REQUIRE(c->g_indptr, XTD_ERR_STATE, "xtd_finalize: gather map missing");
+  for (int t = 0; t < 2; ++t)
+    XTD_REQUIRE(h->naux_filled[t] == h->naux[t], XTD_ERR_STATE, "xtd_finalize: DF tensor %d incomplete (%ld of %ld)", t,
+                h->naux_filled[t], h->naux[t]);
+  if (!h->jblocks.empty()) XTD_REQUIRE(h->jmix.size() == h->jblocks.size() * h->jblocks.size(), XTD_ERR_STATE, "xtd_finalize: J mix missing");
+  cudaStream_t s = h->stream;
+  h->max_nvec = max_nvec;
+  const bool xc = (h->fxc_kind != XTD_FXC_NONE) && h->ng > 0;
+  if (h->fxc_kind != XTD_FXC_NONE) XTD_REQUIRE(h->ao, XTD_ERR_STATE, "xtd_finalize: kernel set but no grid");
+  if (xc) {
+    if (h->fxc_kind == XTD_FXC_UKS) XTD_REQUIRE(h->ch.size() == 2, XTD_ERR_ARG, "UKS kernel needs two channels");
+    else XTD_REQUIRE(h->ch.size() == 1, XTD_ERR_ARG, "spin-flip kernels need one channel");
+    h->nvar_eff = (h->fxc_kind == XTD_FXC_ALDA0) ? 1 : h->nvar;
+    // occupied values on the grid  phi[c][g][o] = sum_mu ao[c][g][mu] Co[mu][o]
+    h->arena.used = 0;
+    size_t split_bytes = std::min<size_t>(h->arena.cap / 4, (size_t)1 << 30);
+    h->gemm.split_ws = h->arena.take(split_bytes / 8);
+    h->gemm.split_ws_bytes = split_bytes;
+    for (auto* c : h->ch) {
+      c->ldphi = pad_ld(c->no);
+      XTD_TRY(c->phi.alloc((size_t)h->nvar_eff * h->ng * c->ldphi));
+      GemmDesc d;
+      d.A = view3d(h->ao, h->ao_ld, h->ao_comp, h->nvar_eff, (int)h->ng, h->nao);
+      d.B = view2d(c->CoT.p, h->ldN, c->no, h->nao);
+      d.M = (int)h->ng; d.N = c->no; d.K = h->nao; d.batches = h->nvar_eff; d.a_hi = 1; d.b_hi = 0;
+      d.C = c->phi.p; d.ldc = c->ldphi; d.c_batch_stride = h->ng * c->ldphi;
+      XTD_TRY(gemm(h->gemm, d, s));
+    }
+    if (h->fxc_kind == XTD_FXC_UKS) {
+      const int nr = 2 * h->nvar;
+      XTD_TRY(h->wf.alloc((size_t)h->ng * nr * nr));
+      build_wf_uks_kernel<<<grid1d(h->ng, 128), 128, 0, s>>>(h->wf.p, h->fxc, h->wgrid, h->ng, h->nvar);
+      LAUNCH_CHECK();
+    } else if (h->fxc_kind == XTD_FXC_MCOL) {
+      XTD_TRY(h->wf.alloc((size_t)h->ng * h->nvar * h->nvar));
+      build_wf_mcol_kernel<<<grid1d(h->ng, 128), 128, 0, s>>>(h->wf.p, h->fxc, h->wgrid, h->ng, h->nvar);
+      LAUNCH_CHECK();
+    }
+  }
+  XTD_CUDA(cudaStreamSynchronize(s));
+  // check that the fixed per-call buffers for max_nvec fit in the arena with room for a work chunk
+  size_t fixed = 0;
+  for (auto* c : h->ch) {
+    fixed += (size_t)max_nvec * c->no * c->ldz * 2;              // Z, SIG
+    fixed += (size_t)max_nvec * c->nv * c->ldzt * 2;             // ZT, ZTs
+    if (xc) fixed += (size_t)max_nvec * c->no * h->ldN * 2;      // mo1T, RT
+  }
+  XTD_REQUIRE(fixed * 8 + (32u << 20) < h->arena.cap, XTD_ERR_NOMEM, "xtd_finalize: workspace of %zu bytes too small for %d vectors (%zu fixed)",
+              h->arena.cap, max_nvec, fixed * 8);
+  h->finalized = true;
+  return XTD_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// sigma
+// ---------------------------------------------------------------------------------------------------------
+static int setup_call_buffers(xtd_engine* h, int nvec) {
+  h->arena.used = 0;
+  const bool xc = (h->fxc_kind != XTD_FXC_NONE) && h->ng > 0;
+  long base[2], total;
+  sig_layout(h, nvec, base, &total);
+  h->SIG = h->arena.take((size_t)total);
+  double* zall = h->arena.take((size_t)total);
+  XTD_REQUIRE(h->SIG && zall, XTD_ERR_NOMEM, "workspace exhausted (sigma buffers)");
+  for (size_t c = 0; c < h->ch.size(); ++c) {
+    Channel* ch = h->ch[c];
+    h->sig_base[c] = base[c];
+    h->Z[c] = zall + base[c];
+    h->ZT[c] = h->arena.take((size_t)nvec * ch->nv * ch->ldzt);
+    h->ZTs[c] = h->arena.take((size_t)nvec * ch->nv * ch->ldzt);
+    XTD_REQUIRE(h->ZT[c] && h->ZTs[c], XTD_ERR_NOMEM, "workspace exhausted (transposed trial vectors)");
+    if (xc) {
+      h->mo1T[c] = h->arena.take((size_t)nvec * ch->no * h->ldN);
+      h->RT[c] = h->arena.take((size_t)nvec * ch->no * h->ldN);
+      XTD_REQUIRE(h->mo1T[c] && h->RT[c], XTD_ERR_NOMEM, "workspace exhausted (half-transformed densities)");
+    }
+  }
+  const size_t njb = h->jblocks.size();
+  if (njb) {
+    h->jR = h->arena.take((size_t)nvec * njb * std::max<long>(h->naux[0], 1));
+    h->jRm = h->arena.take((size_t)nvec * njb * std::max<long>(h->naux[0], 1));
+    XTD_REQUIRE(h->jR && h->jRm, XTD_ERR_NOMEM, "workspace exhausted (Coulomb vectors)");
+  }
+  h->r1d = h->arena.take((size_t)nvec + 8);
+  size_t split_bytes = std::min<size_t>(h->arena.left() / 4, (size_t)1 << 30);
+  h->gemm.split_ws = h->arena.take(split_bytes / 8);
+  h->gemm.split_ws_bytes = split_bytes;
+  h->scratch_doubles = h->arena.left() / 8 - 64;
+  h->scratch = h->arena.take(h->scratch_doubles);
+  XTD_REQUIRE(h->scratch && h->scratch_doubles > (1u << 20), XTD_ERR_NOMEM, "workspace exhausted (chunk scratch)");
+  h->cur_nvec = nvec;
+  return XTD_OK;
+}
+
+template <int NVAR, int KIND>
+static void launch_xc(const XcArgs& a, cudaStream_t s) {
+  xc_weight_kernel<NVAR, KIND><<<(unsigned)cdiv(a.gb, 8), 256, 0, s>>>(a);
+}
+
+static int run_xc(xtd_engine* h, int nvec) {
+  cudaStream_t s = h->stream;
+  const int nch = (int)h->ch.size();
+  const int N = h->nao;
+  const int nve = h->nvar_eff;
+  {
+    PhaseTimer t(h, XTD_T_XC_GEMM);
+    for (int c = 0; c < nch; ++c) {
+      Channel* ch = h->ch[c];
+      // mo1T[(x,o)][mu] = sum_v Z[(x,o)][v] Cv[mu][v]      (MO -> AO back-transformation of the trial vectors)
+      GemmDesc d;
+      d.A = view2d(h->Z[c], ch->ldz, nvec * ch->no, ch->nv);
+      d.B = view2d(ch->Cv.p, ch->ldcv, N, ch->nv);
+      d.M = nvec * ch->no; d.N = N; d.K = ch->nv;
+      d.C = h->mo1T[c]; d.ldc = h->ldN;
+      XTD_TRY(gemm(h->gemm, d, s));
+      XTD_CUDA(cudaMemsetAsync(h->RT[c], 0, (size_t)nvec * ch->no * h->ldN * 8, s));
+    }
+  }
+  // grid chunk: Y buffers for all channels must fit the scratch region
+  size_t per_g = 0;
+  long ldY[2] = {0, 0};
+  for (int c = 0; c < nch; ++c) {
+    ldY[c] = pad_ld((long)nvec * h->ch[c]->no);
+    per_g += (size_t)nve * ldY[c];
+  }
+  long GB = (long)(h->scratch_doubles / per_g);
+  GB = std::min<long>(GB, 1 << 16);
+  GB = (GB / 128) * 128;
+  XTD_REQUIRE(GB >= 128, XTD_ERR_NOMEM, "workspace too small for a 128-point grid chunk");
+  for (long g0 = 0; g0 < h->ng; g0 += GB) {
+    const int gb = (int)std::min<long>(GB, h->ng - g0);
+    double* Y[2];
+    double* cur = h->scratch;
+    for (int c = 0; c < nch; ++c) {
+      Y[c] = cur;
+      cur += (size_t)nve * gb * ldY[c];
+    }
+    {
+      PhaseTimer t(h, XTD_T_XC_GEMM);
+      for (int c = 0; c < nch; ++c) {
+        Channel* ch = h->ch[c];
+        // Y[cmp][g][(x,o)] = sum_mu ao[cmp][g0+g][mu] mo1T[(x,o)][mu]
+        GemmDesc d;
+        d.A = view3d(h->ao, h->ao_ld, h->ao_comp, nve, gb, N, (int)g0, 0);
+        d.B = view2d(h->mo1T[c], h->ldN, nvec * ch->no, N);
+        d.M = gb; d.N = nvec * ch->no; d.K = N; d.batches = nve; d.a_hi = 1; d.b_hi = 0;
+        d.C = Y[c]; d.ldc = ldY[c]; d.c_batch_stride = (long)gb * ldY[c];
+        XTD_TRY(gemm(h->gemm, d, s));
+      }
+    }
+    {
+      PhaseTimer t(h, XTD_T_XC_STREAM);
+      XcArgs a;
+      a.nch = nch; a.nvec = nvec; a.gb = gb; a.g0 = g0;
+      for (int c = 0; c < nch; ++c) {
+        a.Y[c] = Y[c]; a.ldY[c] = ldY[c]; a.y_comp[c] = (long)gb * ldY[c];
+        a.phi[c] = h->ch[c]->phi.p; a.ldphi[c] = h->ch[c]->ldphi; a.phi_comp[c] = h->ng * h->ch[c]->ldphi;
+        a.no[c] = h->ch[c]->no;
+      }
+      if (nch == 1) { a.Y[1] = nullptr; a.phi[1] = nullptr; a.no[1] = 0; a.ldY[1] = a.y_comp[1] = a.ldphi[1] = a.phi_comp[1] = 0; }
+      a.wf = (h->fxc_kind == XTD_FXC_ALDA0) ? h->fxc : h->wf.p;
+      if (h->fxc_kind == XTD_FXC_UKS) {
+        if (nve == 1) launch_xc<1, XC_KIND_UKS>(a, s); else launch_xc<4, XC_KIND_UKS>(a, s);
+      } else if (h->fxc_kind == XTD_FXC_ALDA0) {
+        launch_xc<1, XC_KIND_ALDA0>(a, s);
+      } else {
+        if (nve == 1) launch_xc<1, XC_KIND_MCOL>(a, s); else launch_xc<4, XC_KIND_MCOL>(a, s);
+      }
+      LAUNCH_CHECK();
+    }
+    {
+      PhaseTimer t(h, XTD_T_XC_GEMM);
+      for (int c = 0; c < nch; ++c) {
+        Channel* ch = h->ch[c];
+        // RT[(x,o)][mu] += sum_cmp sum_g A[cmp][g][(x,o)] ao[cmp][g0+g][mu]      (integration back to AO)
+        GemmDesc d;
+        d.a_kc = false; d.b_kc = false;
+        d.A = view3d(Y[c], ldY[c], (long)gb * ldY[c], nve, gb, nvec * ch->no);
+        d.B = view3d(h->ao, h->ao_ld, h->ao_comp, nve, gb, N, (int)g0, 0);
+        d.M = nvec * ch->no; d.N = N; d.K = gb; d.nouter = nve;
+        d.C = h->RT[c]; d.ldc = h->ldN; d.accumulate = true;
+        XTD_TRY(gemm(h->gemm, d, s));
+      }
+    }
+  }
+  {
+    PhaseTimer t(h, XTD_T_XC_GEMM);
+    for (int c = 0; c < nch; ++c) {
+      Channel* ch = h->ch[c];
+      // SIG[(x,o)][v] += sum_mu RT[(x,o)][mu] CvT[v][mu]      (AO -> MO projection)
+      GemmDesc d;
+      d.A = view2d(h->RT[c], h->ldN, nvec * ch->no, N);
+      d.B = view2d(ch->CvT.p, h->ldN, ch->nv, N);
+      d.M = nvec * ch->no; d.N = ch->nv; d.K = N;
+      d.C = h->SIG + h->sig_base[c]; d.ldc = ch->ldz; d.accumulate = true;
+      XTD_TRY(gemm(h->gemm, d, s));
+    }
+  }
+  return XTD_OK;
+}
+
+static int run_k(xtd_engine* h, int nvec) {
+  cudaStream_t s = h->stream;
+  for (const KTermRec& k : h->kterms) {
+    Channel* ch = h->ch[k.ch];
+    const long naux = h->naux[k.tensor];
+    if (naux == 0) continue;
+    const double* Loo = ch->Loo[k.tensor].p;
+    const double* Lvv = ch->Lvv[k.tensor].p;
+    // aux chunk so that U[pc][nvec][no][ldz] fits the scratch region
+    const size_t per_p = (size_t)nvec * ch->no * ch->ldz;
+    long pc = (long)(h->scratch_doubles / per_p);
+    XTD_REQUIRE(pc >= 1, XTD_ERR_NOMEM, "workspace too small for the exchange intermediate of one aux function");
+    pc = std::min<long>(pc, naux);
+    if ((long)pc * nvec > 65535) pc = 65535 / nvec;
+    double* U = h->scratch;
+    std::vector<std::pair<int, int>> iblks, ablks;
+    const int o2off = ch->o_blocks.size() > 1 ? ch->o_blocks[1].first : ch->no;
+    const int v2off = ch->v_blocks.size() > 1 ? ch->v_blocks[1].first : ch->nv;
+    if (k.uniform) { iblks.push_back({0, ch->no}); ablks.push_back({0, ch->nv}); }
+    else {
+      // block ranges extended over the zero pad position so every row / column of U and SIG is written
+      iblks.push_back({0, o2off});
+      if (ch->o_blocks.size() > 1) iblks.push_back({o2off, ch->no - o2off});
+      ablks.push_back({0, v2off});
+      if (ch->v_blocks.size() > 1) ablks.push_back({v2off, ch->nv - v2off});
+    }
+    for (size_t ab = 0; ab < ablks.size(); ++ab) {
+      for (long P0 = 0; P0 < naux; P0 += pc) {
+        const int pn = (int)std::min<long>(pc, naux - P0);
+        {
+          PhaseTimer t(h, XTD_T_K1);
+          for (size_t ib = 0; ib < iblks.size(); ++ib) {
+            const double* zt = h->ZT[k.ch];
+            if (!k.uniform) {
+              BlockSplit bs;
+              bs.o2off = o2off; bs.v2off = v2off;
+              for (int j = 0; j < 2; ++j)
+                for (int b = 0; b < 2; ++b) bs.w[j][b] = k.w[ib][ab][j < k.nob ? j : 0][b < k.nvb ? b : 0];
+              scale_blocks_kernel<<<dim3((unsigned)cdiv(ch->no, 128), ch->nv, nvec), 128, 0, s>>>(h->ZTs[k.ch], h->ZT[k.ch], ch->ldzt,
+                                                                                                (long)ch->nv * ch->ldzt, ch->nv, ch->no, bs);
+              LAUNCH_CHECK();
+              zt = h->ZTs[k.ch];
+            }
+            // U[P][x][i][b] = sum_j Loo[P][i][j] zt[x][b][j]        (exchange half-transform of the trial vectors)
+            GemmDesc d;
+            d.A = view3d(Loo, ch->ldoo, (long)ch->no * ch->ldoo, (int)(naux - P0), iblks[ib].second, ch->no, iblks[ib].first, 0, (int)P0);
+            d.B = view3d(zt, ch->ldzt, (long)ch->nv * ch->ldzt, nvec, ch->nv, ch->no);
+            d.M = iblks[ib].second; d.N = ch->nv; d.K = ch->no;
+            d.batches = pn * nvec; d.z_div = nvec; d.a_hi = 1; d.a_lo = 0; d.b_hi = 0; d.b_lo = 1;
+            d.C = U + (long)iblks[ib].first * ch->ldz; d.ldc = ch->ldz; d.c_batch_stride = (long)ch->no * ch->ldz;
+            XTD_TRY(gemm(h->gemm, d, s));
+          }
+        }
+        {
+          PhaseTimer t(h, XTD_T_K2);
+          // SIG[(x,i)][a] += w * sum_P sum_b U[P][(x,i)][b] Lvv[P][a][b]
+          GemmDesc d;
+          d.A = view3d(U, ch->ldz, (long)nvec * ch->no * ch->ldz, pn, nvec * ch->no, ch->nv);
+          d.B = view3d(Lvv, ch->ldvv, (long)ch->nv * ch->ldvv, (int)(naux - P0), ablks[ab].second, ch->nv, ablks[ab].first, 0, (int)P0);
+          d.M = nvec * ch->no; d.N = ablks[ab].second; d.K = ch->nv; d.nouter = pn;
+          d.C = h->SIG + h->sig_base[k.ch] + ablks[ab].first; d.ldc = ch->ldz; d.accumulate = true;
+          d.alpha = k.uniform ? k.w[0][0][0][0] : 1.0;
+          XTD_TRY(gemm(h->gemm, d, s));
+        }
+      }
+    }
+  }
+  return XTD_OK;
+}
+
+static int run_j(xtd_engine* h, int nvec) {
+  cudaStream_t s = h->stream;
+  const int njb = (int)h->jblocks.size();
+  const long naux = h->naux[0];
+  if (!njb || naux == 0) return XTD_OK;
+  PhaseTimer t(h, XTD_T_J);
+  for (int b = 0; b < njb; ++b) {
+    JBlockRec* j = h->jblocks[b];
+    Channel* ch = h->ch[j->ch];
+    // R[x][b][P] = <L_b[P], z block>
+    j_rho_kernel<8><<<(unsigned)naux, 256, 0, s>>>(h->jR + (long)b * naux, (long)njb * naux, j->L.p, j->ld, (long)j->nr * j->ld,
+                                                  h->Z[j->ch] + (long)j->r0 * ch->ldz + j->c0, ch->ldz, (long)ch->no * ch->ldz, j->nr, j->nc,
+                                                  nvec);
+    LAUNCH_CHECK();
+  }
+  j_mix_kernel<<<dim3((unsigned)cdiv(naux, 128), nvec), 128, 0, s>>>(h->jRm, h->jR, h->jmix_dev.p, njb, naux, nvec);
+  LAUNCH_CHECK();
+  for (int b = 0; b < njb; ++b) {
+    JBlockRec* j = h->jblocks[b];
+    Channel* ch = h->ch[j->ch];
+    j_apply_kernel<8><<<dim3((unsigned)cdiv((long)j->nr * j->nc, 256), (unsigned)cdiv(nvec, 8)), 256, 0, s>>>(
+        h->SIG + h->sig_base[j->ch] + (long)j->r0 * ch->ldz + j->c0, ch->ldz, (long)ch->no * ch->ldz, j->L.p, j->ld, (long)j->nr * j->ld,
+        h->jRm + (long)b * naux, (long)njb * naux, naux, j->nr, j->nc, nvec);
+    LAUNCH_CHECK();
+  }
+  return XTD_OK;
+}
+
+static int run_local(xtd_engine* h, int nvec) {
+  cudaStream_t s = h->stream;
+  PhaseTimer t(h, XTD_T_LOCAL);
+  for (auto* l : h->lgemms) {
+    Channel *dc = h->ch[l->dch], *sc = h->ch[l->sch];
+    double* dst = h->SIG + h->sig_base[l->dch] + (long)l->r0 * dc->ldz + l->c0;
+    GemmDesc d;
+    d.alpha = l->alpha; d.accumulate = true; d.ldc = dc->ldz;
+    if (l->side == XTD_SIDE_RIGHT) {
+      const bool flat = (l->r0 == 0 && l->nr == dc->no && l->sr0 == 0 && sc->no == dc->no);
+      d.b_kc = false;
+      d.B = view2d(l->M.p, l->ldm, l->mrows, l->mcols);
+      d.N = l->nc; d.K = l->mrows;
+      if (flat) {
+        d.A = view2d(h->Z[l->sch], sc->ldz, nvec * sc->no, l->mrows, 0, l->sc0);
+        d.M = nvec * dc->no; d.C = dst;
+      } else {
+        d.A = view3d(h->Z[l->sch], sc->ldz, (long)sc->no * sc->ldz, nvec, l->nr, l->mrows, l->sr0, l->sc0);
+        d.M = l->nr; d.batches = nvec; d.a_hi = 1; d.b_hi = 0; d.C = dst; d.c_batch_stride = (long)dc->no * dc->ldz;
+      }
+    } else {
+      d.A = view2d(l->M.p, l->ldm, l->mrows, l->mcols);
+      d.b_kc = false;
+      d.B = view3d(h->Z[l->sch], sc->ldz, (long)sc->no * sc->ldz, nvec, l->mcols, l->nc, l->sr0, l->sc0);
+      d.M = l->nr; d.N = l->nc; d.K = l->mcols; d.batches = nvec; d.a_hi = 0; d.b_hi = 1;
+      d.C = dst; d.c_batch_stride = (long)dc->no * dc->ldz;
+    }
+    XTD_TRY(gemm(h->gemm, d, s));
+  }
+  for (auto* r : h->rank1s) {
+    Channel *dc = h->ch[r->dch], *sc = h->ch[r->sch];
+    block_dot_kernel<<<nvec, 256, 0, s>>>(h->r1d, r->V.p, h->Z[r->sch], sc->ldz, (long)sc->no * sc->ldz, sc->no, sc->nv);
+    LAUNCH_CHECK();
+    block_axpy_kernel<<<dim3((unsigned)cdiv((long)dc->no * dc->nv, 256), nvec), 256, 0, s>>>(h->SIG + h->sig_base[r->dch], r->U.p, h->r1d,
+                                                                                           dc->ldz, (long)dc->no * dc->ldz, dc->no, dc->nv);
+    LAUNCH_CHECK();
+  }
+  for (auto* dg : h->diags) {
+    Channel* c = h->ch[dg->ch];
+    block_diag_kernel<<<dim3((unsigned)cdiv((long)c->no * c->nv, 256), nvec), 256, 0, s>>>(h->SIG + h->sig_base[dg->ch], dg->D.p, h->Z[dg->ch],
+                                                                                         c->ldz, (long)c->no * c->ldz, c->no, c->nv);
+    LAUNCH_CHECK();
+  }
+  return XTD_OK;
+}
+
+extern "C" {
+
+int xtd_sigma_partial(xtd_handle h, int nvec, const double* z_dev) {
+  XTD_REQUIRE(h && h->finalized, XTD_ERR_STATE, "xtd_sigma before xtd_finalize");
+  XTD_REQUIRE(nvec >= 1 && nvec <= h->max_nvec && z_dev, XTD_ERR_ARG, "xtd_sigma: nvec %d outside 1..%d", nvec, h->max_nvec);
+  cudaStream_t s = h->stream;
+  if (h->ev_ok) cudaEventRecord(h->ev[2 * XTD_T_TOTAL], s);
+  XTD_TRY(setup_call_buffers(h, nvec));
+  long base[2], total;
+  sig_layout(h, nvec, base, &total);
+  {
+    PhaseTimer t(h, XTD_T_PACK);
+    XTD_CUDA(cudaMemsetAsync(h->SIG, 0, (size_t)total * 8, s));
+    XTD_CUDA(cudaMemsetAsync(h->Z[0], 0, (size_t)total * 8, s));
+    for (size_t c = 0; c < h->ch.size(); ++c) {
+      Channel* ch = h->ch[c];
+      const long nrows = (long)ch->no * ch->nv;
+      pack_kernel<<<dim3((unsigned)cdiv(nrows, 256), nvec), 256, 0, s>>>(h->Z[c], ch->ldz, (long)ch->no * ch->ldz, ch->nv, nrows, ch->g_indptr,
+                                                                         ch->g_cols, ch->g_vals, z_dev, h->ext_dim, nvec);
+      LAUNCH_CHECK();
+      if (!h->kterms.empty()) {
+        XTD_CUDA(cudaMemsetAsync(h->ZT[c], 0, (size_t)nvec * ch->nv * ch->ldzt * 8, s));
+        transpose_kernel<<<dim3((unsigned)cdiv(ch->nv, 32), (unsigned)cdiv(ch->no, 32), nvec), dim3(32, 8), 0, s>>>(
+            h->ZT[c], ch->ldzt, (long)ch->nv * ch->ldzt, h->Z[c], ch->ldz, (long)ch->no * ch->ldz, ch->no, ch->nv);
+        LAUNCH_CHECK();
+      }
+    }
+  }
+  if (h->fxc_kind != XTD_FXC_NONE && h->ng > 0) XTD_TRY(run_xc(h, nvec));
+  XTD_TRY(run_k(h, nvec));
+  XTD_TRY(run_j(h, nvec));
+  return XTD_OK;
+}
+
+int xtd_partial_buffer(xtd_handle h, int nvec, double** ptr, long* nelem) {
+  XTD_REQUIRE(h && h->finalized && h->cur_nvec == nvec, XTD_ERR_STATE, "xtd_partial_buffer: call xtd_sigma_partial(nvec) first");
+  long base[2], total;
+  sig_layout(h, nvec, base, &total);
+  if (ptr) *ptr = h->SIG;
+  if (nelem) *nelem = total;
+  return XTD_OK;
+}
+
+int xtd_sigma_finish(xtd_handle h, int nvec, double* hz_dev) {
+  XTD_REQUIRE(h && h->finalized && h->cur_nvec == nvec && hz_dev, XTD_ERR_STATE, "xtd_sigma_finish: call xtd_sigma_partial(nvec) first");
+  cudaStream_t s = h->stream;
+  XTD_TRY(run_local(h, nvec));
+  {
+    PhaseTimer t(h, XTD_T_UNPACK);
+    UnpackChan uc;
+    for (int c = 0; c < 2; ++c) {
+      uc.base[c] = c < (int)h->ch.size() ? h->sig_base[c] : 0;
+      uc.vec_stride[c] = c < (int)h->ch.size() ? (long)h->ch[c]->no * h->ch[c]->ldz : 0;
+    }
+    unpack_kernel<<<dim3((unsigned)cdiv(h->ext_dim, 256), nvec), 256, 0, s>>>(hz_dev, h->ext_dim, nvec, h->s_indptr, h->s_offs, h->s_chans,
+                                                                             h->s_vals, h->SIG, uc);
+    LAUNCH_CHECK();
+  }
+  if (h->ev_ok) cudaEventRecord(h->ev[2 * XTD_T_TOTAL + 1], s);
+  return XTD_OK;
+}
+
+int xtd_sigma(xtd_handle h, int nvec, const double* z_dev, double* hz_dev) {
+  XTD_TRY(xtd_sigma_partial(h, nvec, z_dev));
+  return xtd_sigma_finish(h, nvec, hz_dev);
+}
+
+int xtd_sigma_host(xtd_handle h, int nvec, const double* z_host, double* hz_host) {
+  XTD_REQUIRE(h && h->finalized && z_host && hz_host, XTD_ERR_ARG, "xtd_sigma_host: bad arguments");
+  const size_t n = (size_t)nvec * h->ext_dim;
+  if (n > h->pin_doubles) {
+    if (h->pin_in) cudaFreeHost(h->pin_in);
+    if (h->pin_out) cudaFreeHost(h->pin_out);
+    if (h->dev_in) cudaFree(h->dev_in);
+    if (h->dev_out) cudaFree(h->dev_out);
+    const size_t cap = (size_t)h->max_nvec * h->ext_dim;
+    XTD_CUDA(cudaMallocHost((void**)&h->pin_in, cap * 8));
+    XTD_CUDA(cudaMallocHost((void**)&h->pin_out, cap * 8));
+    XTD_CUDA(cudaMalloc((void**)&h->dev_in, cap * 8));
+    XTD_CUDA(cudaMalloc((void**)&h->dev_out, cap * 8));
+    h->pin_doubles = cap;
+  }
+  memcpy(h->pin_in, z_host, n * 8);
+  XTD_CUDA(cudaMemcpyAsync(h->dev_in, h->pin_in, n * 8, cudaMemcpyHostToDevice, h->stream));
+  XTD_TRY(xtd_sigma(h, nvec, h->dev_in, h->dev_out));
+  XTD_CUDA(cudaMemcpyAsync(h->pin_out, h->dev_out, n * 8, cudaMemcpyDeviceToHost, h->stream));
+  XTD_CUDA(cudaStreamSynchronize(h->stream));
+  memcpy(hz_host, h->pin_out, n * 8);
+  return XTD_OK;
+}
+
+int xtd_get_stats(xtd_handle h, xtd_stats* out) {
+  XTD_REQUIRE(h && out, XTD_ERR_ARG, "xtd_get_stats: bad arguments");
+  XTD_CUDA(cudaStreamSynchronize(h->stream));
+  out->flops_gemm = h->gemm.flops - h->flops0;
+  out->launches = g_launch_count - h->launches0;
+  for (int i = 0; i < 12; ++i) out->ms[i] = 0.0;
+  // only the last recorded interval of each phase is available from the events; phases that ran several
+  // times per call (chunk loops) report their last interval -- the bench times whole calls with its own events
+  for (int i = 0; i <= XTD_T_TOTAL; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev[2 * i], h->ev[2 * i + 1]) == cudaSuccess) out->ms[i] = ms;
+    else cudaGetLastError();
+  }
+  return XTD_OK;
+}
+
+int xtd_reset_stats(xtd_handle h) {
+  XTD_REQUIRE(h, XTD_ERR_ARG, "null handle");
+  h->flops0 = h->gemm.flops;
+  h->launches0 = g_launch_count;
+  return XTD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Davidson vector primitives
+// ---------------------------------------------------------------------------------------------------------
+int xtd_vec_dots(void* stream, double* g, int ldg, const double* a, long lda, int m, const double* b, long ldb, int k, long n) {
+  if (m <= 0 || k <= 0) return XTD_OK;
+  vec_dots_kernel<<<dim3(k, m), 512, 0, (cudaStream_t)stream>>>(g, ldg, a, lda, b, ldb, n);
+  LAUNCH_CHECK();
+  return XTD_OK;
+}
+int xtd_vec_lincomb(void* stream, double* y, long ldy, const double* x, long ldx, const double* c, int ldc, int m, int k, long n,
+                    double beta) {
+  if (m <= 0) return XTD_OK;
+  vec_lincomb_kernel<8><<<dim3((unsigned)cdiv(n, 256), (unsigned)cdiv(m, 8)), 256, 0, (cudaStream_t)stream>>>(y, ldy, x, ldx, c, ldc, m, k, n,
+                                                                                                         beta);
+  LAUNCH_CHECK();
+  return XTD_OK;
+}
+int xtd_vec_residual(void* stream, double* r, const double* ax, const double* x, long ld, const double* e, double* nrm2, int k, long n) {
+  if (k <= 0) return XTD_OK;
+  vec_residual_kernel<<<k, 512, 0, (cudaStream_t)stream>>>(r, ax, x, ld, e, nrm2, n);
+  LAUNCH_CHECK();
+  return XTD_OK;
+}
+int xtd_vec_precond(void* stream, double* x, long ld, const double* hdiag, const double* shift, double* nrm2, int k, long n) {
+  if (k <= 0) return XTD_OK;
+  vec_precond_kernel<<<k, 512, 0, (cudaStream_t)stream>>>(x, ld, hdiag, shift, nrm2, n);
+  LAUNCH_CHECK();
+  return XTD_OK;
+}
+int xtd_vec_scale(void* stream, double* x, long ld, const double* sc, int k, long n) {
+  if (k <= 0) return XTD_OK;
+  vec_scale_kernel<<<dim3((unsigned)cdiv(n, 256), k), 256, 0, (cudaStream_t)stream>>>(x, ld, sc, n);
+  LAUNCH_CHECK();
+  return XTD_OK;
+}
+
+int xtd_dgemm_tn(void* stream, int m, int n, int k, double alpha, const double* a, long lda, const double* b, long ldb, double* c,
+                 long ldc, int accumulate) {
+  static GemmContext ctx;
+  static double* ws = nullptr;
+  if (!ctx.encode) {
+    XTD_TRY(gemm_context_init(ctx));
+    XTD_CUDA(cudaMalloc((void**)&ws, (size_t)256 << 20));
+    ctx.split_ws = ws; ctx.split_ws_bytes = (size_t)256 << 20;
+  }
+  GemmDesc d;
+  d.A = view2d(a, lda, m, k); d.B = view2d(b, ldb, n, k);
+  d.M = m; d.N = n; d.K = k; d.C = c; d.ldc = ldc; d.alpha = alpha; d.accumulate = accumulate != 0;
+  return gemm(ctx, d, (cudaStream_t)stream);
+}
+
+}  // extern "C"

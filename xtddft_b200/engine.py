@@ -1,0 +1,288 @@
+"""SigmaEngine: the host-side owner of one libxtdsigma engine on one B200.
+
+PyTorch is used only for buffer ownership (device tensors whose raw pointers cross the C-ABI), stream
+identity and the NCCL process group.  All arithmetic of the sigma path runs in hand-written sm_100a kernels
+inside libxtdsigma.so; if the library is missing, construction fails (no CPU fallback).
+
+    eng = SigmaEngine.from_problem(plan, problem)      # upload once per solve
+    hz  = eng.sigma(z)                                 # z: torch cuda [nvec, dim] -> torch cuda [nvec, dim]
+    vind = eng.as_vind()                               # NumPy-in / NumPy-out callable with the reference's `vind` contract
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import numpy as np
+
+from . import _lib
+from .dist import SigmaReducer, split_range
+from .plan import Plan, finish_xsf_hdiag
+from .problem import ProblemData
+
+_KIND = {"none": _lib.XTD_FXC_NONE, "uks": _lib.XTD_FXC_UKS, "alda0": _lib.XTD_FXC_ALDA0, "mcol": _lib.XTD_FXC_MCOL}
+
+
+def _ptr(t) -> C.c_void_p:
+    return C.c_void_p(t.data_ptr())
+
+
+def _np_ptr(a: np.ndarray) -> C.c_void_p:
+    return C.c_void_p(a.ctypes.data)
+
+
+def _pad16(n: int) -> int:
+    return (max(n, 1) + 15) // 16 * 16
+
+
+class SigmaEngine:
+    def __init__(self, plan: Plan, nao: int, mo_coeff: np.ndarray, *, workspace_bytes: int = 2 << 30, device=None,
+                 reducer: Optional[SigmaReducer] = None):
+        import torch
+        if not torch.cuda.is_available():
+            raise _lib.XtdError("SigmaEngine needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.torch = torch
+        self.lib = _lib.load()
+        self.plan = plan
+        self.nao = int(nao)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        torch.cuda.set_device(self.device)
+        self.reducer = reducer
+        self._keep: List[object] = []          # device tensors the engine holds raw pointers to
+        self._h = C.c_void_p()
+        _lib.check(self.lib.xtd_create(C.byref(self._h), self.nao, int(workspace_bytes)), "xtd_create")
+        self._set_stream()
+        self.finalized = False
+        self.max_nvec = 0
+        self.ext_dim = int(plan.ext_dim)
+        self._naux_total = [0, 0]
+        # orbitals
+        mo_coeff = np.ascontiguousarray(mo_coeff, dtype=np.float64)
+        for spin in (0, 1):
+            c = torch.from_numpy(mo_coeff[spin]).to(self.device)
+            self._keep.append(c)
+            _lib.check(self.lib.xtd_set_mo(self._h, spin, _ptr(c), c.shape[1], c.shape[1]), "xtd_set_mo")
+        # channels
+        for ch in plan.channels:
+            occ = np.ascontiguousarray(ch.occ_idx, dtype=np.int32)
+            vir = np.ascontiguousarray(ch.vir_idx, dtype=np.int32)
+            ob = np.ascontiguousarray(np.array(ch.o_blocks, dtype=np.int32).ravel())
+            vb = np.ascontiguousarray(np.array(ch.v_blocks, dtype=np.int32).ravel())
+            _lib.check(self.lib.xtd_add_channel(self._h, ch.spin_o, _np_ptr(occ), len(occ), ch.spin_v, _np_ptr(vir), len(vir),
+                                                _np_ptr(ob), len(ch.o_blocks), _np_ptr(vb), len(ch.v_blocks)), "xtd_add_channel")
+        # exchange terms and Coulomb blocks must be declared before the tensor is streamed in
+        for kt in plan.k_terms:
+            w = np.ascontiguousarray(kt.weights, dtype=np.float64)
+            _lib.check(self.lib.xtd_add_kterm(self._h, kt.tensor, kt.ch, _np_ptr(w), w.shape[0], w.shape[1]), "xtd_add_kterm")
+        for jb in plan.j_blocks:
+            _lib.check(self.lib.xtd_add_jblock(self._h, jb.ch, jb.r0, jb.nr, jb.c0, jb.nc), "xtd_add_jblock")
+        if plan.j_blocks:
+            m = np.ascontiguousarray(plan.j_mix, dtype=np.float64)
+            _lib.check(self.lib.xtd_set_jmix(self._h, _np_ptr(m), m.shape[0]), "xtd_set_jmix")
+        self.tensors_used = sorted({kt.tensor for kt in plan.k_terms} | ({0} if plan.j_blocks else set()))
+
+    # ---- plumbing ---------------------------------------------------------------------------------
+    def _set_stream(self):
+        s = self.torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.xtd_set_stream(self._h, C.c_void_p(s)), "xtd_set_stream")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.xtd_destroy(self._h)
+            self._h = C.c_void_p()
+        self._keep = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- density fitting ----------------------------------------------------------------------------
+    def df_begin(self, tensor: int, naux_local: int):
+        _lib.check(self.lib.xtd_df_begin(self._h, tensor, int(naux_local)), "xtd_df_begin")
+
+    def df_add(self, tensor: int, chunk, packed: bool = False):
+        """chunk: torch cuda fp64 [np, nao, nao] (any row stride) or packed lower-triangular [np, nao(nao+1)/2]."""
+        assert chunk.is_cuda and chunk.dtype == self.torch.float64
+        if packed:
+            assert chunk.dim() == 2 and chunk.stride(1) == 1
+            _lib.check(self.lib.xtd_df_add(self._h, tensor, _ptr(chunk), chunk.shape[0], 0, chunk.stride(0), 1), "xtd_df_add")
+        else:
+            assert chunk.dim() == 3 and chunk.stride(2) == 1
+            _lib.check(self.lib.xtd_df_add(self._h, tensor, _ptr(chunk), chunk.shape[0], chunk.stride(1), chunk.stride(0), 0),
+                       "xtd_df_add")
+
+    def load_cderi(self, tensor: int, cderi: np.ndarray, chunk: int = 64):
+        """Stream a host tensor [naux_local, nao, nao] through the device in aux chunks."""
+        torch = self.torch
+        naux = cderi.shape[0]
+        self.df_begin(tensor, naux)
+        for p0 in range(0, naux, chunk):
+            blk = torch.from_numpy(np.ascontiguousarray(cderi[p0:p0 + chunk])).to(self.device)
+            self.df_add(tensor, blk)
+
+    # ---- grid ---------------------------------------------------------------------------------------
+    def set_grid(self, ao, weights):
+        """ao: torch cuda [nvar, ng, nao(+pad)] fp64, weights: torch cuda [ng]."""
+        torch = self.torch
+        nvar, ng, n = ao.shape
+        if ao.stride(2) != 1 or ao.stride(1) % 2 or ao.stride(0) % 2 or ao.data_ptr() % 16:
+            ld = _pad16(self.nao)
+            buf = torch.zeros((nvar, ng, ld), dtype=torch.float64, device=self.device)
+            buf[:, :, :self.nao] = ao[:, :, :self.nao]
+            ao = buf
+        self._keep += [ao, weights]
+        _lib.check(self.lib.xtd_set_grid(self._h, _ptr(ao), nvar, ng, ao.stride(1), ao.stride(0), _ptr(weights)), "xtd_set_grid")
+
+    def set_fxc(self, kind: str, fxc):
+        if kind != "none":
+            assert fxc.is_contiguous()
+            self._keep.append(fxc)
+        _lib.check(self.lib.xtd_set_fxc(self._h, _KIND[kind], _ptr(fxc) if kind != "none" else None), "xtd_set_fxc")
+
+    # ---- finalize -----------------------------------------------------------------------------------
+    def finalize(self, max_nvec: int = 40):
+        plan = self.plan
+        for lg in plan.local_gemms:
+            m = np.ascontiguousarray(lg.mat, dtype=np.float64)
+            dc, r0, nr, c0, ncol = lg.dst
+            sc, sr0, sc0 = lg.src
+            side = _lib.XTD_SIDE_RIGHT if lg.side == "R" else _lib.XTD_SIDE_LEFT
+            _lib.check(self.lib.xtd_add_local_gemm(self._h, side, dc, r0, nr, c0, ncol, sc, sr0, sc0, _np_ptr(m), m.shape[0], m.shape[1],
+                                                   float(lg.alpha)), "xtd_add_local_gemm")
+        for r1 in plan.rank1s:
+            u = np.ascontiguousarray(r1.u, dtype=np.float64)
+            v = np.ascontiguousarray(r1.v, dtype=np.float64)
+            _lib.check(self.lib.xtd_add_rank1(self._h, r1.dst_ch, _np_ptr(u), r1.src_ch, _np_ptr(v)), "xtd_add_rank1")
+        for dg in plan.diags:
+            d = np.ascontiguousarray(dg.d, dtype=np.float64)
+            _lib.check(self.lib.xtd_add_diag(self._h, dg.ch, _np_ptr(d)), "xtd_add_diag")
+        # layout maps
+        lds, offs = [], []
+        for ci in range(len(plan.channels)):
+            base, vs, ld = C.c_long(), C.c_long(), C.c_long()
+            _lib.check(self.lib.xtd_channel_layout(self._h, ci, 1, C.byref(base), C.byref(vs), C.byref(ld)), "xtd_channel_layout")
+            lds.append(ld.value)
+            offs.append(0)                      # scatter offsets are channel-local; the engine adds the channel base
+            g = plan.gather_map(ci)
+            _lib.check(self.lib.xtd_set_gather(self._h, ci, _np_ptr(g.indptr), _np_ptr(g.cols), _np_ptr(g.vals), len(g.cols)),
+                       "xtd_set_gather")
+        sm = plan.scatter_map(offs, lds)
+        ent = plan.layout_entries
+        order = np.argsort(ent[:, 0], kind="stable")
+        chans = np.ascontiguousarray(ent[order, 1].astype(np.int8))
+        _lib.check(self.lib.xtd_set_scatter(self._h, plan.ext_dim, _np_ptr(sm.indptr), _np_ptr(sm.cols), _np_ptr(chans), _np_ptr(sm.vals),
+                                            len(sm.cols)), "xtd_set_scatter")
+        _lib.check(self.lib.xtd_finalize(self._h, int(max_nvec)), "xtd_finalize")
+        self.max_nvec = int(max_nvec)
+        self.finalized = True
+
+    @classmethod
+    def from_problem(cls, plan: Plan, p: ProblemData, *, max_nvec: int = 40, workspace_bytes: int = 2 << 30, device=None,
+                     reducer: Optional[SigmaReducer] = None, rank: int = 0, world: int = 1, df_chunk: int = 64) -> "SigmaEngine":
+        """Upload a host ProblemData; with world > 1 this rank keeps only its aux block and grid batch."""
+        import torch
+        eng = cls(plan, p.nao, p.mo_coeff, workspace_bytes=workspace_bytes, device=device, reducer=reducer)
+        for t in eng.tensors_used:
+            full = p.cderi if t == 0 else p.cderi_lr
+            p0, p1 = split_range(full.shape[0], rank, world)
+            eng.load_cderi(t, full[p0:p1], chunk=df_chunk)
+        if plan.xc_kind != "none":
+            g0, g1 = split_range(p.ng, rank, world)
+            ld = _pad16(p.nao)
+            ao = torch.zeros((p.nvar, g1 - g0, ld), dtype=torch.float64, device=eng.device)
+            ao[:, :, :p.nao] = torch.from_numpy(np.ascontiguousarray(p.ao[:, g0:g1])).to(eng.device)
+            w = torch.from_numpy(np.ascontiguousarray(p.weights[g0:g1])).to(eng.device)
+            eng.set_grid(ao, w)
+            if plan.xc_kind == "uks":
+                f = torch.from_numpy(np.ascontiguousarray(p.fxc_uks[..., g0:g1])).to(eng.device)
+            elif plan.xc_kind == "alda0":
+                f = torch.from_numpy(np.ascontiguousarray(p.fxc_alda0[g0:g1])).to(eng.device)
+            else:
+                f = torch.from_numpy(np.ascontiguousarray(p.fxc_mcol[..., g0:g1])).to(eng.device)
+            eng.set_fxc(plan.xc_kind, f)
+        eng.finalize(max_nvec)
+        return eng
+
+    # ---- preconditioner diagonal ----------------------------------------------------------------------
+    def jblock_diag(self, jb: int) -> np.ndarray:
+        torch = self.torch
+        blk = self.plan.j_blocks[jb]
+        out = torch.zeros(blk.nr * blk.nc, dtype=torch.float64, device=self.device)
+        self._set_stream()
+        _lib.check(self.lib.xtd_jblock_diag(self._h, jb, _ptr(out)), "xtd_jblock_diag")
+        if self.reducer is not None:
+            self.reducer.allreduce_(out)
+        return out.cpu().numpy().reshape(blk.nr, blk.nc)
+
+    def hdiag(self) -> np.ndarray:
+        plan = self.plan
+        if plan.hdiag_needs_jdiag is None:
+            return np.asarray(plan.hdiag)
+        co_j = ov_j = None
+        if plan.hdiag_needs_jdiag["pending"] is not None:
+            co_j, ov_j = self.jblock_diag(0), self.jblock_diag(1)
+        return finish_xsf_hdiag(plan, co_j, ov_j)
+
+    # ---- the operator -----------------------------------------------------------------------------------
+    def sigma(self, z, out=None):
+        """z: torch cuda fp64 [nvec, dim] (contiguous).  Returns torch cuda [nvec, dim]."""
+        torch = self.torch
+        assert self.finalized
+        assert z.is_cuda and z.dtype == torch.float64 and z.dim() == 2 and z.shape[1] == self.ext_dim and z.is_contiguous()
+        nvec = z.shape[0]
+        if out is None:
+            out = torch.empty_like(z)
+        self._set_stream()
+        for x0 in range(0, nvec, self.max_nvec):
+            x1 = min(nvec, x0 + self.max_nvec)
+            zz, oo = z[x0:x1], out[x0:x1]
+            if self.reducer is None or not self.reducer.enabled:
+                _lib.check(self.lib.xtd_sigma(self._h, x1 - x0, _ptr(zz), _ptr(oo)), "xtd_sigma")
+            else:
+                _lib.check(self.lib.xtd_sigma_partial(self._h, x1 - x0, _ptr(zz)), "xtd_sigma_partial")
+                ptr, n = C.c_void_p(), C.c_long()
+                _lib.check(self.lib.xtd_partial_buffer(self._h, x1 - x0, C.byref(ptr), C.byref(n)), "xtd_partial_buffer")
+                part = _as_tensor(torch, ptr.value, n.value, self.device)
+                self.reducer.allreduce_(part)          # one all-reduce(sum, fp64) of the MO-space partial per call
+                _lib.check(self.lib.xtd_sigma_finish(self._h, x1 - x0, _ptr(oo)), "xtd_sigma_finish")
+        return out
+
+    def sigma_host(self, z: np.ndarray) -> np.ndarray:
+        """Reference-facing entry with HOST vectors: H2D + sigma + D2H inside the C-ABI call (single rank)."""
+        z = np.ascontiguousarray(z, dtype=np.float64)
+        if z.ndim == 1:
+            z = z[None]
+        out = np.empty_like(z)
+        if self.reducer is not None and self.reducer.enabled:
+            t = self.torch.from_numpy(z).to(self.device)
+            return self.sigma(t).cpu().numpy()
+        self._set_stream()
+        for x0 in range(0, z.shape[0], self.max_nvec):
+            x1 = min(z.shape[0], x0 + self.max_nvec)
+            _lib.check(self.lib.xtd_sigma_host(self._h, x1 - x0, _np_ptr(z[x0:x1]), _np_ptr(out[x0:x1])), "xtd_sigma_host")
+        return out
+
+    def as_vind(self):
+        """`vind(zs)` with the reference's contract (XTDA.py:615, SF_TDA.py:224): list / array in, new array out."""
+        def vind(zs):
+            return self.sigma_host(np.asarray(zs, dtype=np.float64).reshape(-1, self.ext_dim))
+        return vind
+
+    def stats(self) -> dict:
+        st = _lib.XtdStats()
+        _lib.check(self.lib.xtd_get_stats(self._h, C.byref(st)), "xtd_get_stats")
+        return dict(flops_gemm=st.flops_gemm, launches=int(st.launches), ms={n: st.ms[i] for i, n in enumerate(_lib.T_NAMES)})
+
+    def reset_stats(self):
+        _lib.check(self.lib.xtd_reset_stats(self._h), "xtd_reset_stats")
+
+
+def _as_tensor(torch, ptr: int, n: int, device):
+    """Wrap a raw device pointer (owned by the engine's workspace) as a torch tensor, without copying."""
+    class _Holder:
+        pass
+    h = _Holder()
+    h.__cuda_array_interface__ = dict(shape=(n,), typestr="<f8", data=(ptr, False), version=3, strides=None)
+    return torch.as_tensor(h, device=device)
