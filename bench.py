@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- Davidson sigma-vector throughput of the B200-native path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            (N=1 directly; N>1 under torchrun, one rank per GPU)
+    python bench.py --impl reference ...                     CPU arm: the oracle port of the reference path on host cores
+
+A "step" is one `vind` call: sigma = A.X for `nvec` trial vectors (default: the workload's number of roots) of
+the named BASELINE configuration, on seeded synthetic inputs generated on the device.  At N>1 the auxiliary
+functions and grid points are sharded over ranks (strong scaling of the same problem) and every call ends in one
+NCCL all-reduce of the MO-space partial sigma.
+
+One JSON line on stdout (rank 0).  `value` = sigma-vectors/s with vectors resident in HBM; `e2e` = the same
+through the reference-facing `vind` with HOST vectors (H2D + D2H inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FP64_PEAK_TFLOPS = 37.1      # measured DMMA.8x8x4 issue rate on this pool's B200 (profiles/fp64_peaks_r01.json)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=int(os.environ.get("XTD_BENCH_CONFIG", "5")))
+    ap.add_argument("--scale", type=float, default=float(os.environ.get("XTD_BENCH_SCALE", "1.0")))
+    ap.add_argument("--nvec", type=int, default=0)
+    ap.add_argument("--workspace-gb", type=float, default=0.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--davidson", type=int, default=int(os.environ.get("XTD_BENCH_DAVIDSON", "1")))
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        # the busy samples: SM clock above the idle floor
+        busy = [s for s in sm if s > 500] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm (oracle port of the reference algorithm), bounded sample + linear extrapolation
+# ---------------------------------------------------------------------------------------------------------
+def cpu_reference_rate(dp, nvec_sample: int = 1, target_s: float = 12.0):
+    """Time the oracle's AO-route sigma build (reference algorithm: back-transform, (L_P D) L_P exchange, grid
+    contraction, projection) on the host cores for a SAMPLE of the aux functions / grid points of this workload;
+    sigma is linear in both, so the full-size time per vector is t_k*naux/naux_s + t_xc*ng/ng_s + t_rest."""
+    from oracle import jk, numint
+    from xtddft_b200.synth_device import host_sample
+    from xtddft_b200.workloads import oracle_vind_for
+    try:
+        from threadpoolctl import threadpool_info
+        info = threadpool_info()
+        threads = max([i.get("num_threads", 1) for i in info] or [1])
+        blas = ",".join(sorted({i.get("internal_api", "?") for i in info}))
+    except Exception:
+        threads, blas = os.cpu_count(), "?"
+    n = dp.p.nao
+    # calibrate the sample so the K part takes a few seconds: ~4*N^3 flops per aux function per density
+    t0 = time.perf_counter()
+    a = np.random.default_rng(0).standard_normal((min(n, 1500), min(n, 1500)))
+    _ = a @ a
+    gf = 2.0 * a.shape[0] ** 3 / (time.perf_counter() - t0) / 1e9
+    per_aux = 4.0 * n ** 3 / 1e9 / max(gf, 1.0)
+    ndens = 2 if dp.method == "xtda" else (5 if dp.method == "xsf" else 1)
+    naux_s = int(max(1, min(dp.naux, (target_s * 0.6) / max(per_aux * ndens, 1e-9))))
+    per_g = 4.0 * n ** 2 * (2 if dp.nvar == 4 else 1) / 1e9 / max(gf, 1.0)
+    ng_s = int(max(64, min(dp.ng, (target_s * 0.3) / max(per_g * (2 if dp.method == "xtda" else 1), 1e-9))))
+    ps = host_sample(dp, naux_s, ng_s)
+    vind, hd = oracle_vind_for(ps, dp.method)
+    z = np.random.default_rng(1).standard_normal((nvec_sample, hd.size))
+    # whole sampled call
+    t0 = time.perf_counter(); vind(z); t_all = time.perf_counter() - t0
+    # parts: exchange/Coulomb on the sampled tensor, grid on the sampled points
+    ps_nodf = host_sample(dp, naux_s, ng_s); ps_nodf.cderi = None
+    v2, _ = oracle_vind_for(ps_nodf, dp.method) if dp.method != "xsf" else (None, None)
+    if v2 is not None:
+        t0 = time.perf_counter(); v2(z); t_nodf = time.perf_counter() - t0
+        t_df = max(t_all - t_nodf, 1e-9)
+    else:
+        # XSF needs the tensor for Delta A: time its J/K builds directly (5 densities per vector)
+        dm = np.random.default_rng(2).standard_normal((5 * nvec_sample, n, n))
+        t0 = time.perf_counter(); jk.get_jk(ps.cderi, dm); t_df = time.perf_counter() - t0
+        t_nodf = max(t_all - t_df, 1e-9)
+    ps_nogrid = host_sample(dp, naux_s, ng_s)
+    t_grid = 0.0
+    if dp.fxc_kind != "none":
+        dm = np.random.default_rng(3).standard_normal((nvec_sample, n, n))
+        t0 = time.perf_counter()
+        if dp.fxc_kind == "alda0":
+            numint.nr_uks_fxc_sf(ps.ao, ps.fxc_alda0, dm)
+        elif dp.fxc_kind == "mcol":
+            numint.nr_uks_fxc_sf_mc(ps.ao, ps.weights, ps.fxc_mcol, dm)
+        else:
+            numint.nr_uks_fxc(ps.ao, ps.weights, ps.fxc_uks, np.stack([dm, dm]))
+        t_grid = time.perf_counter() - t0
+    t_rest = max(t_nodf - t_grid, 0.0)
+    t_full = (t_df * dp.naux / naux_s + t_grid * dp.ng / ng_s + t_rest) / nvec_sample
+    return {"value": 1.0 / t_full, "unit": "sigma-vectors/s", "cores": int(threads), "kind": "port",
+            "sample": f"oracle AO-route sigma build of {nvec_sample} vector(s) on {naux_s}/{dp.naux} aux functions and {ng_s}/{dp.ng} "
+                      f"grid points, extrapolated linearly (sigma is linear in both); {blas} {threads} threads, host DGEMM {gf:.0f} GF/s; "
+                      f"t_df={t_df:.2f}s t_grid={t_grid:.2f}s t_rest={t_rest:.2f}s",
+            "seconds_per_vector_full_size": t_full}
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU implementation of the path.  PySCF is not installable here (no wheel,
+    no network) and the reference tree does not import without it, so this arm times the oracle port (kind "port")."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from xtddft_b200.synth_device import make_device_problem
+    dp = make_device_problem(args.config, args.scale)
+    nvec = args.nvec or dp.nroots
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_reference_rate(dp, 1, target_s=6.0)
+        if i >= args.warmup:
+            vals.append(r)
+    v = float(np.mean([r["value"] for r in vals]))
+    cb = dict(vals[-1]); cb["value"] = v
+    out = {"impl": "reference", "metric": "davidson_sigma_vectors_per_s", "value": v, "unit": "sigma-vectors/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * nvec / v, "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": dp.name, "method": dp.method, "nvec_per_step": nvec, "nao": dp.p.nao, "naux": dp.naux, "ng": dp.ng},
+           "cpu_baseline": cb, "e2e": {"value": v, "unit": "sigma-vectors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    import torch
+    from xtddft_b200 import _lib
+    from xtddft_b200.dist import SigmaReducer, init_process_group_from_env
+    from xtddft_b200.synth_device import make_device_problem
+    from xtddft_b200.workloads import engine_for_device_problem
+
+    rank, local_rank, world = init_process_group_from_env()
+    if not torch.cuda.is_available():
+        raise _lib.XtdError("bench.py needs a B200: the sigma path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    reducer = SigmaReducer() if world > 1 else None
+    dp = make_device_problem(args.config, args.scale)
+    nvec = args.nvec or dp.nroots
+    free, total_mem = torch.cuda.mem_get_info()
+    # workspace: what is left after the resident tensors, capped
+    if args.workspace_gb > 0:
+        ws = int(args.workspace_gb * (1 << 30))
+    else:
+        p = dp.p
+        nv_i, no_i = p.nvir_b + 2, p.nocc_a + 2
+        resident = (dp.naux // world + 1) * (nv_i * ((nv_i + 15) // 16 * 16) + no_i * ((no_i + 15) // 16 * 16)) * 8 * (2 if dp.method == "xtda" else 1)
+        resident += (dp.ng // world + 1) * ((p.nao + 15) // 16 * 16) * dp.nvar * 8 * 1.25
+        ws = int(min(24 << 30, max(1 << 30, (free - resident) * 0.55)))
+    t_setup0 = time.perf_counter()
+    eng = engine_for_device_problem(dp, max_nvec=max(nvec, 16), workspace_bytes=ws, rank=rank, world=world, reducer=reducer)
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t_setup0
+    dim = eng.ext_dim
+
+    g = torch.Generator(device=dev); g.manual_seed(4242)
+    z = torch.randn((nvec, dim), generator=g, device=dev, dtype=torch.float64)
+    z /= z.norm(dim=1, keepdim=True)
+    out = torch.empty_like(z)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        eng.sigma(z, out)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # ---- resident-vector timing -------------------------------------------------------------------------
+    eng.reset_stats()
+    launches0 = eng.lib.xtd_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    phase = {}
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        eng.sigma(z, out)
+        st = eng.stats()                       # syncs the stream; per-phase device times of this call
+        for k, v in st["ms"].items():
+            phase[k] = phase.get(k, 0.0) + v
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = eng.lib.xtd_launch_count() - launches0
+    flops = eng.stats()["flops_gemm"]
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = nvec / (ms_step / 1000.0)
+    # ---- end to end: host vectors through the vind boundary ------------------------------------------------
+    z_host = z.cpu().numpy()
+    if world == 1:
+        eng.sigma_host(z_host)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            hz_host = eng.sigma_host(z_host)
+        e2e_s = (time.perf_counter() - t0) / args.steps
+    else:
+        pin_in = torch.from_numpy(z_host).pin_memory()
+        pin_out = torch.empty_like(pin_in).pin_memory()
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            zd = pin_in.to(dev, non_blocking=True)
+            pin_out.copy_(eng.sigma(zd), non_blocking=True)
+            torch.cuda.synchronize()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        e2e_s = float(t.item()) / 1000.0 / args.steps
+    clocks = sampler.stop() if rank == 0 else {}
+
+    # ---- Davidson time-to-roots ---------------------------------------------------------------------------
+    dav = None
+    if args.davidson:
+        try:
+            from xtddft_b200.davidson import davidson_for_engine
+            barrier()
+            t0 = time.perf_counter()
+            conv, e, x, info = davidson_for_engine(eng, dp.nroots, dp.method)
+            torch.cuda.synchronize()
+            dav = {"time_to_roots_s": time.perf_counter() - t0, "nroots": dp.nroots, "converged": bool(np.all(conv)),
+                   "cycles": int(info[0]), "sigma_vectors": int(info[1]), "lowest_root_ha": float(e[0])}
+        except ImportError:
+            dav = None
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+    # ---- roofline of the dominant kernel (the DMMA GEMM; K2 = exchange contraction launches) -------------------
+    gemm_ms = phase.get("k2", 0.0) / args.steps
+    k2_flops = 0.0
+    p = dp.p
+    for kt in eng.plan.k_terms:
+        ch = eng.plan.channels[kt.ch]
+        naux_loc = dp.naux // world + (1 if rank < dp.naux % world else 0)
+        k2_flops += 2.0 * naux_loc * nvec * ch.no * ch.nv * ch.nv
+    roof = {"bound": "tensor", "kernel": "dgemm_dmma_tma_kernel (exchange contraction sigma += U . Lvv)",
+            "achieved": (k2_flops / (gemm_ms * 1e-3) / 1e12) if gemm_ms > 0 else None, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+            "frac": (k2_flops / (gemm_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS) if gemm_ms > 0 else None, "traffic": None,
+            "peak_source": "measured DMMA.8x8x4 issue rate, profiles/fp64_peaks_r01.json (MEASURED_PEAKS.json has no FP64 entry; "
+                           "cuBLAS DGEMM on the same box: 35.4 TFLOP/s)",
+            "flops_per_launch_group": k2_flops, "ms_per_step_in_kernel": gemm_ms,
+            "all_gemm_flops_per_step": flops / args.steps, "all_gemm_tflops_over_step": flops / args.steps / (ms_step * 1e-3) / 1e12}
+    out_json = {
+        "metric": "davidson_sigma_vectors_per_s", "value": value, "unit": "sigma-vectors/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": dp.name, "method": dp.method, "nvec_per_step": nvec, "nao": p.nao, "nc": p.nc, "no": p.no, "nv": p.nv,
+                   "dim": dim, "naux": dp.naux, "ng": dp.ng, "grid_components": dp.nvar, "hyb": p.hyb,
+                   "parallelism": f"aux+grid sharded x{world}, one all-reduce of [nvec,dim] per call",
+                   "l2": "inputs larger than L2 (DF tensor and AO values stream from HBM every call)"},
+        "clocks": clocks,
+        "e2e": {"value": nvec / e2e_s, "unit": "sigma-vectors/s", "h2d_bytes_per_step": nvec * dim * 8, "d2h_bytes_per_step": nvec * dim * 8},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "phase_ms_per_step": {k: v / args.steps for k, v in phase.items()},
+        "setup_s": setup_s,
+    }
+    if dav is not None:
+        out_json["davidson"] = dav
+    if world == 1 and not args.no_cpu_baseline:
+        out_json["cpu_baseline"] = cpu_reference_rate(dp)
+    print(json.dumps(out_json))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

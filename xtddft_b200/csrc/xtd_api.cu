@@ -145,10 +145,12 @@ struct xtd_engine {
   // pinned staging for the host entry
   double *pin_in = nullptr, *pin_out = nullptr, *dev_in = nullptr, *dev_out = nullptr;
   size_t pin_doubles = 0;
-  // timers
-  cudaEvent_t ev[2 * 12];
+  // timers: a pool of event pairs, one per phase occurrence of the last call, summed per phase on query
+  struct EvRec { cudaEvent_t a, b; int id; };
+  std::vector<EvRec> evpool;
+  size_t ev_used = 0;
+  cudaEvent_t ev_total[2];
   bool ev_ok = false;
-  float ms[12] = {0};
   unsigned long long launches0 = 0;
   double flops0 = 0;
 };
@@ -157,12 +159,23 @@ namespace {
 
 struct PhaseTimer {
   xtd_engine* h;
-  int id;
-  PhaseTimer(xtd_engine* h_, int id_) : h(h_), id(id_) {
-    if (h->ev_ok) cudaEventRecord(h->ev[2 * id], h->stream);
+  size_t slot = (size_t)-1;
+  PhaseTimer(xtd_engine* h_, int id) : h(h_) {
+    if (!h->ev_ok) return;
+    if (h->ev_used == h->evpool.size()) {
+      if (h->evpool.size() >= 4096) return;
+      xtd_engine::EvRec r;
+      cudaEventCreate(&r.a);
+      cudaEventCreate(&r.b);
+      r.id = id;
+      h->evpool.push_back(r);
+    }
+    slot = h->ev_used++;
+    h->evpool[slot].id = id;
+    cudaEventRecord(h->evpool[slot].a, h->stream);
   }
   ~PhaseTimer() {
-    if (h->ev_ok) cudaEventRecord(h->ev[2 * id + 1], h->stream);
+    if (slot != (size_t)-1) cudaEventRecord(h->evpool[slot].b, h->stream);
   }
 };
 
@@ -273,7 +286,8 @@ int xtd_create(xtd_handle* out, int nao, long workspace_bytes) {
     return XTD_ERR_NOMEM;
   }
   h->arena.cap = (size_t)workspace_bytes;
-  for (int i = 0; i < 24; ++i) cudaEventCreate(&h->ev[i]);
+  cudaEventCreate(&h->ev_total[0]);
+  cudaEventCreate(&h->ev_total[1]);
   h->ev_ok = true;
   *out = h;
   return XTD_OK;
@@ -304,7 +318,11 @@ int xtd_destroy(xtd_handle h) {
   if (h->pin_out) cudaFreeHost(h->pin_out);
   if (h->dev_in) cudaFree(h->dev_in);
   if (h->dev_out) cudaFree(h->dev_out);
-  if (h->ev_ok) for (int i = 0; i < 24; ++i) cudaEventDestroy(h->ev[i]);
+  if (h->ev_ok) {
+    cudaEventDestroy(h->ev_total[0]);
+    cudaEventDestroy(h->ev_total[1]);
+    for (auto& r : h->evpool) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  }
   delete h;
   return XTD_OK;
 }
@@ -959,7 +977,8 @@ int xtd_sigma_partial(xtd_handle h, int nvec, const double* z_dev) {
   XTD_REQUIRE(h && h->finalized, XTD_ERR_STATE, "xtd_sigma before xtd_finalize");
   XTD_REQUIRE(nvec >= 1 && nvec <= h->max_nvec && z_dev, XTD_ERR_ARG, "xtd_sigma: nvec %d outside 1..%d", nvec, h->max_nvec);
   cudaStream_t s = h->stream;
-  if (h->ev_ok) cudaEventRecord(h->ev[2 * XTD_T_TOTAL], s);
+  h->ev_used = 0;
+  if (h->ev_ok) cudaEventRecord(h->ev_total[0], s);
   XTD_TRY(setup_call_buffers(h, nvec));
   long base[2], total;
   sig_layout(h, nvec, base, &total);
@@ -1011,7 +1030,7 @@ int xtd_sigma_finish(xtd_handle h, int nvec, double* hz_dev) {
                                                                              h->s_vals, h->SIG, uc);
     LAUNCH_CHECK();
   }
-  if (h->ev_ok) cudaEventRecord(h->ev[2 * XTD_T_TOTAL + 1], s);
+  if (h->ev_ok) cudaEventRecord(h->ev_total[1], s);
   return XTD_OK;
 }
 
@@ -1050,13 +1069,14 @@ int xtd_get_stats(xtd_handle h, xtd_stats* out) {
   out->flops_gemm = h->gemm.flops - h->flops0;
   out->launches = g_launch_count - h->launches0;
   for (int i = 0; i < 12; ++i) out->ms[i] = 0.0;
-  // only the last recorded interval of each phase is available from the events; phases that ran several
-  // times per call (chunk loops) report their last interval -- the bench times whole calls with its own events
-  for (int i = 0; i <= XTD_T_TOTAL; ++i) {
+  for (size_t i = 0; i < h->ev_used; ++i) {
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, h->ev[2 * i], h->ev[2 * i + 1]) == cudaSuccess) out->ms[i] = ms;
+    if (cudaEventElapsedTime(&ms, h->evpool[i].a, h->evpool[i].b) == cudaSuccess) out->ms[h->evpool[i].id] += ms;
     else cudaGetLastError();
   }
+  float tot = 0.f;
+  if (cudaEventElapsedTime(&tot, h->ev_total[0], h->ev_total[1]) == cudaSuccess) out->ms[XTD_T_TOTAL] = tot;
+  else cudaGetLastError();
   return XTD_OK;
 }
 

@@ -173,14 +173,14 @@ def _pos(blocks):
 def _k_weight_tables(p: ProblemData, ch: int, nob: int, nvb: int, w0: np.ndarray) -> List[KTerm]:
     """exchange of A: -hyb K (+ -(alpha-hyb) K_lr), plus Delta-A weights w0 (full-range tensor only)."""
     out = []
-    if p.cderi is None:
+    if not p.has_df:
         return out
     w = np.zeros((nob, nvb, nob, nvb)) if w0 is None else w0.copy()
     if p.hybrid:
         w -= p.hyb
     if np.any(w != 0):
         out.append(KTerm(0, ch, w))
-    if p.hybrid and p.omega != 0.0 and p.cderi_lr is not None:
+    if p.hybrid and p.omega != 0.0 and p.has_df_lr:
         out.append(KTerm(1, ch, np.full((nob, nvb, nob, nvb), -(p.alpha - p.hyb))))
     return out
 
@@ -210,7 +210,7 @@ def build_xtda_plan(p: ProblemData) -> Plan:
     v2off = vb_b[1][0] if len(vb_b) > 1 else 0
     o2off = ob_a[1][0] if len(ob_a) > 1 else 0
 
-    if p.cderi is not None:
+    if p.has_df:
         for ci, chs in enumerate((cha, chb)):
             plan.k_terms += _k_weight_tables(p, ci, len(chs.o_blocks), len(chs.v_blocks), None)
         plan.j_blocks = [JBlock(0, 0, cha.no, 0, cha.nv), JBlock(1, 0, chb.no, 0, chb.nv)]
@@ -403,7 +403,7 @@ def build_sf_plan(p: ProblemData, isf: int = -1, method: int = 0, sa: int = 0, l
             e = np.zeros((ch.no, ch.nv))
             e[oo_, vo] = 1.0
             plan.rank1s = [Rank1(0, w, 0, e), Rank1(0, e, 0, w)]
-        if p.cderi is not None:
+        if p.has_df:
             plan.j_blocks = [JBlock(0, 0, nc, 0, no), JBlock(0, o2off, no, v2off, nv)]     # co, ov
             plan.j_mix = jm
     plan.k_terms = _k_weight_tables(p, 0, nob, nvb, w_k)

@@ -54,6 +54,8 @@ class ProblemData:
     fxc_alda0: Optional[np.ndarray] = None  # [ng]  weighted (SF_TDA.py:82-84)
     fxc_mcol: Optional[np.ndarray] = None  # [nvar, nvar, ng]  unweighted
     level_shift: float = 0.0
+    df_external: bool = False             # the 3-centre tensor is streamed to the engine by the caller (device-resident data)
+    grid_external: bool = False           # AO values / kernel are given to the engine by the caller
     meta: dict = field(default_factory=dict)
 
     # ---- derived sizes -------------------------------------------------------------------
@@ -95,6 +97,14 @@ class ProblemData:
         return 0.5 * self.no
 
     @property
+    def has_df(self) -> bool:
+        return self.cderi is not None or self.df_external
+
+    @property
+    def has_df_lr(self) -> bool:
+        return self.cderi_lr is not None or (self.df_external and self.omega != 0.0)
+
+    @property
     def hybrid(self) -> bool:
         return self.hyb != 0.0 or (self.omega != 0.0 and self.alpha != 0.0)
 
@@ -108,7 +118,7 @@ class ProblemData:
             assert self.fock_hf.shape == (2, nmo, nmo)
         if self.cderi is not None:
             assert self.cderi.ndim == 3 and self.cderi.shape[1:] == (self.nao, self.nao)
-        if self.xctype != XC_NONE:
+        if self.xctype != XC_NONE and not self.grid_external:
             assert self.ao is not None and self.weights is not None
             assert self.ao.shape[2] == self.nao and self.ao.shape[1] == self.weights.shape[0]
             assert self.ao.shape[0] == (1 if self.xctype == XC_LDA else 4)
