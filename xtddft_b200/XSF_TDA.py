@@ -1,0 +1,73 @@
+"""XSF-TDA / USF-TDA driver (spin-adapted spin-flip-down TDA) on the B200 sigma engine.
+
+Same constructor, `kernel` signature, defaults and result attributes as `XSF_TDA` in xtddft/XSF_TDA.py:146-213,
+1455-1481, 1501-1554: block-order vectors cv|co|ov|oo, optional removal of the S_f = S_i OO component
+(`remove`, default True for ROKS), spin-adaptation level SA 0..3, `foo`, `d_lda` / `fglobal`.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import plan as planmod
+from . import utils
+from .adapters import problem_from_mf
+from .drivers_common import TimeCounter, make_engine, solve
+
+au2ev = utils.au2ev_xsf
+
+
+class XSF_TDA:
+    def __init__(self, mf, SA=None, davidson=True, method=0, collinear_samples=60, calculate_sp=False):
+        self.mf = mf
+        self.problem = problem_from_mf(mf, kernel={0: "alda0", 1: "mcol", 2: "none"}[method], collinear_samples=collinear_samples)
+        p = self.problem
+        self.type_u = not p.restricted
+        self.SA = (0 if self.type_u else 3) if SA is None else SA
+        self.davidson, self.method, self.collinear_samples = davidson, method, collinear_samples
+        self.nc, self.no, self.nv = p.nc, p.no, p.nv
+        self.nao = p.nao
+        self.ground_s = p.no / 2.0
+        self.omega, self.alpha, self.hyb = p.omega, p.alpha, p.hyb
+        if calculate_sp:
+            raise NotImplementedError("get_sp (spin-polarisation diagnostics) is outside the sigma hot path")
+        self.tc = TimeCounter()
+        self._engine = None
+        self._engine_key = None
+
+    def get_vect(self):
+        return utils.get_vect(self.no)
+
+    def _get_engine(self, foo, fglobal):
+        key = (self.re, self.SA, foo, fglobal)
+        if self._engine is None or self._engine_key != key:
+            if self._engine is not None:
+                self._engine.close()
+            self.plan = planmod.build_sf_plan(self.problem, isf=-1, method=self.method, sa=self.SA, layout=planmod.LAYOUT_BLOCK,
+                                              remove=self.re, foo=foo, fglobal=fglobal, hdiag_kind="xsf")
+            self._engine = make_engine(self.plan, self.problem, max_nvec=40)
+            self._engine_key = key
+        return self._engine
+
+    def gen_tda_operation_sf(self, foo, fglobal):
+        eng = self._get_engine(foo, fglobal)
+        return eng.as_vind(), eng.hdiag()
+
+    def get_Amat(self, *a, **k):
+        raise NotImplementedError("get_Amat is the dense O(dim^2) path, outside the sigma hot path")
+
+    def kernel(self, nstates=1, remove=None, frozen=None, foo=1.0, d_lda=0.3, fglobal=None, fit=True):
+        self.re = (not self.type_u) if remove is None else remove
+        nov = (self.nc + self.no) * (self.no + self.nv)
+        self.nstates = min(nstates, nov)
+        if fglobal is None:
+            fglobal = planmod.xsf_default_fglobal(self.problem, self.method, d_lda, fit)
+        if frozen is not None or not self.davidson:
+            raise NotImplementedError("frozen / dense get_Amat paths are outside the sigma hot path")
+        if self.re:
+            self.vects = self.get_vect()
+        eng = self._get_engine(foo, fglobal)
+        self.converged, self.e, self.v, self.Davidcyc, _ = solve(eng, self.nstates, "xsf", tc=self.tc)
+        return self.e * au2ev, self.v
+
+    def deltaS2(self):
+        return utils.delta_s2_sf_roks(self.v, self.nc, self.no, self.nv, self.vects if self.re else None)

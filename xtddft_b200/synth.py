@@ -73,9 +73,24 @@ def gaussian_ao(rng, ng: int, nao: int, deriv: bool, dtype=np.float64):
     return ao, weights
 
 
+def _xc_norm_estimate(ao0: np.ndarray, co: np.ndarray, cv: np.ndarray, d: np.ndarray, iters: int = 12) -> float:
+    """Largest eigenvalue of X[(ia),(jb)] = sum_g d_g (phi_i phi_a)(g) (phi_j phi_b)(g), d >= 0, by power iteration."""
+    po, pv = ao0 @ co, ao0 @ cv
+    x = np.ones((co.shape[1], cv.shape[1])) / math.sqrt(co.shape[1] * cv.shape[1])
+    lam = 1.0
+    for _ in range(iters):
+        t = np.einsum("go,ov,gv->g", po, x, pv, optimize=True) * d
+        y = np.einsum("g,go,gv->ov", t, po, pv, optimize=True)
+        lam = float(np.linalg.norm(y))
+        if lam == 0.0:
+            return 1.0
+        x = y / lam
+    return lam
+
+
 def make_problem(nao: int, nc: int, no: int, nv: int, naux: int, ng: int, *, xctype: str = XC_GGA,
                  hyb: float = 0.2, restricted: bool = True, seed: int = 0, fxc_kinds=("uks", "alda0", "mcol"),
-                 coupling: float = 0.15, xc_strength: float = 0.1, omega: float = 0.0, alpha: float = 0.0,
+                 coupling: float = 0.5, xc_strength: float = 0.25, omega: float = 0.0, alpha: float = 0.0,
                  level_shift: float = 0.0) -> ProblemData:
     """Random well-conditioned problem (T0).  nao must equal nc+no+nv (square MO coefficient matrix)."""
     nmo = nc + no + nv
@@ -125,9 +140,10 @@ def make_problem(nao: int, nc: int, no: int, nv: int, naux: int, ng: int, *, xct
     if xctype != XC_NONE and ng > 0:
         ao, weights = gaussian_ao(rng, ng, nao, deriv=(xctype == XC_GGA))
         nvar = ao.shape[0]
-        # scale so that sum_g |f_g| (phi_i phi_a)(phi_j phi_b) stays a perturbation
-        amp = float(np.sqrt(np.mean(ao[0] ** 2))) + 1e-300
-        fscale = xc_strength / (np.mean(weights) * ng * amp ** 4 * (1.0 + math.sqrt((nc + no) * (no + nv) / ng)) ** 2)
+        # scale the kernels so that the grid term of A has norm ~ xc_strength (a perturbation of the gaps):
+        # power-iteration estimate for a unit kernel on the largest occ x vir block
+        est = _xc_norm_estimate(ao[0], ca[:, :nc + no], cb[:, nc:], weights)
+        fscale = xc_strength / max(est, 1e-300)
         if "uks" in fxc_kinds:
             f = rng.standard_normal((2 * nvar, 2 * nvar, ng)) * 0.25
             f = 0.5 * (f + f.transpose(1, 0, 2))
@@ -135,20 +151,20 @@ def make_problem(nao: int, nc: int, no: int, nv: int, naux: int, ng: int, *, xct
             f[idx, idx, :] = -np.abs(rng.standard_normal((2 * nvar, ng)))
             gradscale = np.ones(2 * nvar)
             if nvar == 4:
-                gradscale[[1, 2, 3, 5, 6, 7]] = 0.3
+                gradscale[[1, 2, 3, 5, 6, 7]] = 0.15
             f = f * gradscale[:, None, None] * gradscale[None, :, None]
             fxc_uks = (f * fscale).reshape(2, nvar, 2, nvar, ng)
         if "alda0" in fxc_kinds:
-            fxc_alda0 = -np.abs(rng.standard_normal(ng)) * 1.5 * fscale * weights
+            fxc_alda0 = -np.abs(rng.standard_normal(ng)) * fscale * weights
         if "mcol" in fxc_kinds:
             f = rng.standard_normal((nvar, nvar, ng)) * 0.25
             f = 0.5 * (f + f.transpose(1, 0, 2))
             idx = np.arange(nvar)
             f[idx, idx, :] = -np.abs(rng.standard_normal((nvar, ng)))
             if nvar == 4:
-                gs = np.array([1.0, 0.3, 0.3, 0.3])
+                gs = np.array([1.0, 0.15, 0.15, 0.15])
                 f = f * gs[:, None, None] * gs[None, :, None]
-            fxc_mcol = f * (0.75 * fscale)
+            fxc_mcol = f * (0.5 * fscale)
 
     p = ProblemData(nao=nao, nc=nc, no=no, nv=nv, restricted=restricted, mo_coeff=mo_coeff,
                     mo_energy=mo_energy, fock_ks=fock_ks, fock_hf=fock_hf, cderi=cderi, cderi_lr=cderi_lr,

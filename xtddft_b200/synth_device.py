@@ -141,7 +141,7 @@ def make_device_problem(cfg: int, scale: float = 1.0, seed: Optional[int] = None
                     fock_ks=np.stack([fa, fb]), fock_hf=fock_hf, hyb=c["hyb"], xctype=XC_GGA if nvar == 4 else XC_LDA,
                     df_external=True, grid_external=True, meta=dict(config=cfg, name=c["name"], method=method, scale=scale))
     nocc, nvir = nc + no, no + nv
-    coupling = 0.15
+    coupling = 0.5
     cc = math.sqrt(coupling / 4.0 / max(1.0, math.sqrt(nocc * nvir / naux)))
     ao_amp = 0.2
     f_scale = 0.1 / (500.0 * ao_amp ** 4 * (1.0 + math.sqrt(nocc * nvir / ng)) ** 2)
