@@ -187,7 +187,7 @@ def main():
     from xtddft_b200 import _lib
     from xtddft_b200.dist import SigmaReducer, init_process_group_from_env
     from xtddft_b200.synth_device import make_device_problem
-    from xtddft_b200.workloads import engine_for_device_problem
+    from xtddft_b200.workloads import default_workspace_bytes, engine_for_device_problem
 
     rank, local_rank, world = init_process_group_from_env()
     if not torch.cuda.is_available():
@@ -197,16 +197,7 @@ def main():
     reducer = SigmaReducer() if world > 1 else None
     dp = make_device_problem(args.config, args.scale)
     nvec = args.nvec or dp.nroots
-    free, total_mem = torch.cuda.mem_get_info()
-    # workspace: what is left after the resident tensors, capped
-    if args.workspace_gb > 0:
-        ws = int(args.workspace_gb * (1 << 30))
-    else:
-        p = dp.p
-        nv_i, no_i = p.nvir_b + 2, p.nocc_a + 2
-        resident = (dp.naux // world + 1) * (nv_i * ((nv_i + 15) // 16 * 16) + no_i * ((no_i + 15) // 16 * 16)) * 8 * (2 if dp.method == "xtda" else 1)
-        resident += (dp.ng // world + 1) * ((p.nao + 15) // 16 * 16) * dp.nvar * 8 * 1.25
-        ws = int(min(24 << 30, max(1 << 30, (free - resident) * 0.55)))
+    ws = int(args.workspace_gb * (1 << 30)) if args.workspace_gb > 0 else default_workspace_bytes(dp, world)
     t_setup0 = time.perf_counter()
     eng = engine_for_device_problem(dp, max_nvec=max(nvec, 16), workspace_bytes=ws, rank=rank, world=world, reducer=reducer)
     torch.cuda.synchronize()

