@@ -30,6 +30,19 @@ sys.path.insert(0, ROOT)
 FP64_PEAK_TFLOPS = 37.1      # measured DMMA.8x8x4 issue rate on this pool's B200 (profiles/fp64_peaks_r01.json)
 
 
+def _hbm_peak():
+    """Measured HBM copy bandwidth of this pool's B200s (driver-written MEASURED_PEAKS.json), else the profiling recipe's
+    fallback figure."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (torch copy, read+write bytes)"
+    except Exception:
+        return 6438.8, "fallback: B200 copy bandwidth recorded in BASELINE.md (MEASURED_PEAKS.json absent)"
+
+
+HBM_PEAK_GBS, HBM_PEAK_SOURCE = _hbm_peak()
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -300,18 +313,35 @@ def main():
                            "cuBLAS DGEMM on the same box: 35.4 TFLOP/s)",
             "flops_per_launch_group": k2_flops, "ms_per_step_in_kernel": gemm_ms,
             "all_gemm_flops_per_step": flops / args.steps, "all_gemm_tflops_over_step": flops / args.steps / (ms_step * 1e-3) / 1e12}
+    # ---- streaming kernel of the grid path (xc_weight_kernel) against HBM bandwidth --------------------------
+    roof_xc = None
+    xs_ms = phase.get("xc_stream", 0.0) / args.steps
+    if dp.fxc_kind != "none" and xs_ms > 0:
+        ng_loc = dp.ng // world + (1 if rank < dp.ng % world else 0)
+        nve = 1 if dp.fxc_kind == "alda0" else dp.nvar
+        n_fxc = {"alda0": 1, "mcol": dp.nvar ** 2, "uks": (2 * dp.nvar) ** 2}[dp.fxc_kind]
+        occ_cols = sum(ch.no for ch in eng.plan.channels)
+        # per grid point: Y read + A written in place (nve components x nvec x no), phi read once, kernel row read once
+        xc_bytes = 8.0 * ng_loc * (2 * nve * nvec * occ_cols + nve * occ_cols + n_fxc)
+        hbm_peak = HBM_PEAK_GBS
+        roof_xc = {"bound": "hbm", "kernel": "xc_weight_kernel (rho1 on the grid, f_xc weighting, A buffers in place)",
+                   "achieved": xc_bytes / (xs_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                   "frac": xc_bytes / (xs_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "bytes_per_step": xc_bytes,
+                   "ms_per_step_in_kernel": xs_ms, "peak_source": HBM_PEAK_SOURCE}
     out_json = {
         "metric": "davidson_sigma_vectors_per_s", "value": value, "unit": "sigma-vectors/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": dp.name, "method": dp.method, "nvec_per_step": nvec, "nao": p.nao, "nc": p.nc, "no": p.no, "nv": p.nv,
                    "dim": dim, "naux": dp.naux, "ng": dp.ng, "grid_components": dp.nvar, "hyb": p.hyb,
+                   "generator": dp.p.meta.get("generator", "synthetic"),
                    "parallelism": f"aux+grid sharded x{world}, one all-reduce of [nvec,dim] per call",
                    "l2": "inputs larger than L2 (DF tensor and AO values stream from HBM every call)"},
         "clocks": clocks,
         "e2e": {"value": nvec / e2e_s, "unit": "sigma-vectors/s", "h2d_bytes_per_step": nvec * dim * 8, "d2h_bytes_per_step": nvec * dim * 8},
         "gpu_launches": int(launches),
         "roofline": roof,
+        "roofline_xc": roof_xc,
         "phase_ms_per_step": {k: v / args.steps for k, v in phase.items()},
         "setup_s": setup_s,
     }

@@ -1,7 +1,6 @@
 """BASELINE-size checks of the CUDA sigma path through size-independent properties (the oracle cannot finish these
 sizes): A is real symmetric (<y, A x> = <x, A y>), sigma is linear, the host and device entry points agree bit for
-bit, aux / grid shards sum to the unsharded result, and a sampled set of sigma elements equals an independent
-per-element evaluation from the resident tensors.  Needs one B200 with ~150 GB free for the config-5 case."""
+bit and aux / grid shards sum to the unsharded result.  Needs one B200 with ~160 GB free for the config-5 case."""
 import numpy as np
 import pytest
 
@@ -52,8 +51,9 @@ def _properties(torch, eng):
     # nvec-independence (1 vector alone == the same vector inside a batch) and host entry == device entry
     h1 = eng.sigma(z[2:3].contiguous())
     assert (h1[0] - hz[2]).abs().max().item() <= 1e-12 * max(1.0, hz[2].abs().max().item())
-    hh = eng.sigma_host(z[:2].cpu().numpy())
-    assert np.array_equal(hh, hz[:2].cpu().numpy())
+    z2 = z[:2].contiguous()
+    hh = eng.sigma_host(z2.cpu().numpy())
+    assert np.array_equal(hh, eng.sigma(z2).cpu().numpy())          # same nvec -> same split-K schedule -> same bits
     return hz
 
 

@@ -94,3 +94,8 @@ def test_xsf_gpu_order_golden(torch_cuda, golden_dir, tag):
             hx, hdiag = _run(plan, p, d[f"z_X{X}_re{re}"])
             _close(hx, d[f"hx_X{X}_re{re}"])
             assert np.abs(hdiag - d[f"hdiag_X{X}_re{re}"]).max() < 1e-10
+    # spin-flip-up branch of the GPU class (extype=0, XSF_TDA_GPU.py:422-439)
+    plan = planmod.build_sf_plan(p, isf=1, method=1, hdiag_kind="gpu")
+    hx, hdiag = _run(plan, p, d["z_up"])
+    _close(hx, d["hx_up"])
+    assert np.abs(hdiag - d["hdiag_up"]).max() < 1e-12

@@ -50,6 +50,10 @@ struct GemmDesc {
   double alpha = 1.0;
   bool accumulate = false;         // C += instead of C =
   int splits = 0;                  // split of the (nouter x ktiles) iteration space; 0 = choose
+  // optional two-level output rows: row m lives at (m / c_row_div) * c_row_hi + (m % c_row_div) * c_row_lo
+  // (elements; both even) instead of m * ldc.  c_row_div == 0: plain rows.
+  int c_row_div = 0;
+  long c_row_hi = 0, c_row_lo = 0;
 };
 
 struct GemmKernelParams {
@@ -61,7 +65,13 @@ struct GemmKernelParams {
   long ldc, c_batch_stride, c_split_stride;
   double alpha;
   int accumulate;
+  int c_row_div;
+  long c_row_hi, c_row_lo;
 };
+
+__host__ __device__ __forceinline__ long c_row_offset(int m, long ldc, int div, long hi, long lo) {
+  return div ? (long)(m / div) * hi + (long)(m % div) * lo : (long)m * ldc;
+}
 
 // ------------------------------------------------------------------------------------------------------
 // PTX helpers
@@ -228,7 +238,7 @@ dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   for (int i = 0; i < 8; ++i) {
     const int m = m_base + i * 8 + g;
     if (m >= p.M) continue;
-    double* crow = C + (long)m * p.ldc;
+    double* crow = C + c_row_offset(m, p.ldc, p.c_row_div, p.c_row_hi, p.c_row_lo);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n_base + j * 8 + 2 * t;
@@ -279,14 +289,14 @@ __global__ void dgemm_naive_kernel(const NaiveParams q) {
       acc = fma(a, b, acc);
     }
   }
-  double* c = p.C + (long)zb * p.c_batch_stride + (long)m * p.ldc + n;
+  double* c = p.C + (long)zb * p.c_batch_stride + c_row_offset(m, p.ldc, p.c_row_div, p.c_row_hi, p.c_row_lo) + n;
   *c = p.alpha * acc + (p.accumulate ? *c : 0.0);
 }
 
 // C (+)= sum_s partial[s]   (deterministic split-K reduction)
 __global__ void reduce_splits_kernel(double* __restrict__ C, long ldc, long c_batch_stride, const double* __restrict__ part,
                                      long ldp, long p_batch_stride, long p_split_stride, int splits, int M, int N,
-                                     int accumulate) {
+                                     int accumulate, int row_div, long row_hi, long row_lo) {
   const int zb = blockIdx.y;
   const long total = (long)M * N;
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
@@ -295,7 +305,7 @@ __global__ void reduce_splits_kernel(double* __restrict__ C, long ldc, long c_ba
     const double* src = part + (long)zb * p_batch_stride + m * ldp + n;
     double acc = 0.0;
     for (int s = 0; s < splits; ++s) acc += src[(long)s * p_split_stride];
-    double* dst = C + (long)zb * c_batch_stride + m * ldc + n;
+    double* dst = C + (long)zb * c_batch_stride + c_row_offset((int)m, ldc, row_div, row_hi, row_lo) + n;
     *dst = acc + (accumulate ? *dst : 0.0);
   }
 }
@@ -390,6 +400,8 @@ inline int gemm(GemmContext& ctx, const GemmDesc& d, cudaStream_t stream) {
   p.b_q0 = d.B.q0; p.b_hi = d.b_hi; p.b_lo = d.b_lo;
   p.C = d.C; p.ldc = d.ldc; p.c_batch_stride = d.c_batch_stride; p.c_split_stride = 0;
   p.alpha = d.alpha; p.accumulate = d.accumulate ? 1 : 0; p.splits = 1;
+  p.c_row_div = d.c_row_div; p.c_row_hi = d.c_row_hi; p.c_row_lo = d.c_row_lo;
+  XTD_REQUIRE(d.c_row_div == 0 || (d.c_row_hi % 2 == 0 && d.c_row_lo % 2 == 0), XTD_ERR_ALIGN, "gemm: split row strides must be even");
   ctx.flops += 2.0 * d.M * d.N * (double)d.K * d.nouter * d.batches;
 
   if (ctx.naive) {
@@ -453,6 +465,7 @@ inline int gemm(GemmContext& ctx, const GemmDesc& d, cudaStream_t stream) {
     kp.c_batch_stride = part_batch * splits;
     kp.accumulate = 0;
     kp.alpha = d.alpha;
+    kp.c_row_div = 0;
   }
   CUtensorMap ma, mb;
   XTD_TRY(make_tensor_map(ctx, d.A, d.a_kc, &ma));
@@ -470,7 +483,8 @@ inline int gemm(GemmContext& ctx, const GemmDesc& d, cudaStream_t stream) {
     long nblk = cdiv((long)d.M * d.N, 256);
     dim3 rg((unsigned)(nblk > 4096 ? 4096 : nblk), d.batches);
     reduce_splits_kernel<<<rg, 256, 0, stream>>>(d.C, d.ldc, d.c_batch_stride, ctx.split_ws, part_ld, part_batch * splits,
-                                                 part_batch, splits, d.M, d.N, d.accumulate ? 1 : 0);
+                                                 part_batch, splits, d.M, d.N, d.accumulate ? 1 : 0, d.c_row_div, d.c_row_hi,
+                                                 d.c_row_lo);
     XTD_COUNT_LAUNCH(); ctx.launches++;
     XTD_CUDA(cudaGetLastError());
   }

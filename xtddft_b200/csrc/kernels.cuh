@@ -156,7 +156,28 @@ struct XcArgs {
   const double* wf;        // per-point kernel data: UKS [ng][(2 nvar)^2] (weighted), ALDA0 [ng], MCOL [ng][nvar^2] (2 w f)
 };
 
-template <int NVAR, int KIND>
+// XU trial vectors are processed together (independent loads in flight before the first shuffle reduction: the kernel
+// is latency-bound otherwise); W = 2 uses 16-byte accesses (needs an even occupied count so that every
+// (vector, component) row segment stays 16-byte aligned).
+template <int W>
+struct XcVec;
+template <>
+struct XcVec<1> {
+  double v[1];
+  __device__ __forceinline__ void load(const double* p) { v[0] = *p; }
+  __device__ __forceinline__ void store(double* p) const { *p = v[0]; }
+};
+template <>
+struct XcVec<2> {
+  double v[2];
+  __device__ __forceinline__ void load(const double* p) {
+    const double2 t = *reinterpret_cast<const double2*>(p);
+    v[0] = t.x; v[1] = t.y;
+  }
+  __device__ __forceinline__ void store(double* p) const { *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]); }
+};
+
+template <int NVAR, int KIND, int XU, int W>
 __global__ void __launch_bounds__(256) xc_weight_kernel(const XcArgs a) {
   const int lane = threadIdx.x & 31;
   const long g = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -177,55 +198,95 @@ __global__ void __launch_bounds__(256) xc_weight_kernel(const XcArgs a) {
   } else {
     fk[0] = a.wf[a.g0 + g];
   }
-  for (int x = 0; x < a.nvec; ++x) {
-    double rho[NR];
+  for (int x0 = 0; x0 < a.nvec; x0 += XU) {
+    double rho[XU][NR];
 #pragma unroll
-    for (int q = 0; q < NR; ++q) rho[q] = 0.0;
+    for (int u = 0; u < XU; ++u)
+#pragma unroll
+      for (int q = 0; q < NR; ++q) rho[u][q] = 0.0;
 #pragma unroll
     for (int s = 0; s < NCH; ++s) {
-      const double* y = a.Y[s] + g * a.ldY[s] + (long)x * a.no[s];
+      const int no = a.no[s];
+      const double* yb = a.Y[s] + g * a.ldY[s] + (long)x0 * no;
       const double* p = a.phi[s] + (a.g0 + g) * a.ldphi[s];
-      for (int o = lane; o < a.no[s]; o += 32) {
-        const double y0 = y[o], p0 = p[o];
-        rho[s * NVAR] += y0 * p0;
+      for (int o = lane * W; o < no; o += 32 * W) {
+        XcVec<W> pc[NVAR];
 #pragma unroll
-        for (int k = 1; k < NVAR; ++k)
-          rho[s * NVAR + k] += y[k * a.y_comp[s] + o] * p0 + y0 * p[k * a.phi_comp[s] + o];
+        for (int k = 0; k < NVAR; ++k) pc[k].load(p + k * a.phi_comp[s] + o);
+        XcVec<W> yc[XU][NVAR];
+#pragma unroll
+        for (int u = 0; u < XU; ++u)
+          if (x0 + u < a.nvec) {
+#pragma unroll
+            for (int k = 0; k < NVAR; ++k) yc[u][k].load(yb + (long)u * no + k * a.y_comp[s] + o);
+          }
+#pragma unroll
+        for (int u = 0; u < XU; ++u)
+          if (x0 + u < a.nvec) {
+#pragma unroll
+            for (int e = 0; e < W; ++e) {
+              rho[u][s * NVAR] += yc[u][0].v[e] * pc[0].v[e];
+#pragma unroll
+              for (int k = 1; k < NVAR; ++k) rho[u][s * NVAR + k] += yc[u][k].v[e] * pc[0].v[e] + yc[u][0].v[e] * pc[k].v[e];
+            }
+          }
       }
     }
 #pragma unroll
-    for (int q = 0; q < NR; ++q) rho[q] = warp_sum(rho[q]);
-    double wv[NR];
-    if (KIND == XC_KIND_UKS) {
-      double mine = 0.0;
+    for (int u = 0; u < XU; ++u)
 #pragma unroll
-      for (int q = 0; q < NR; ++q) mine += fk[q] * rho[q];      // wv[t,d] = sum_{s,c} wf[g][t,d][s,c] rho[s,c]
+      for (int q = 0; q < NR; ++q) rho[u][q] = warp_sum(rho[u][q]);
+    double wv[XU][NR];
 #pragma unroll
-      for (int q = 0; q < NR; ++q) wv[q] = __shfl_sync(0xffffffffu, mine, q);
-    } else if (KIND == XC_KIND_MCOL) {
-      double mine = 0.0;
+    for (int u = 0; u < XU; ++u) {
+      if (KIND == XC_KIND_UKS) {
+        double mine = 0.0;
 #pragma unroll
-      for (int q = 0; q < NVAR; ++q) mine += fk[q] * rho[q];    // wv[a] = sum_b (2 w f[b,a]) rho[b]
+        for (int q = 0; q < NR; ++q) mine += fk[q] * rho[u][q];      // wv[t,d] = sum_{s,c} wf[g][t,d][s,c] rho[s,c]
 #pragma unroll
-      for (int q = 0; q < NVAR; ++q) wv[q] = __shfl_sync(0xffffffffu, mine, q);
-    } else {
-      wv[0] = rho[0] * fk[0];
+        for (int q = 0; q < NR; ++q) wv[u][q] = __shfl_sync(0xffffffffu, mine, q);
+      } else if (KIND == XC_KIND_MCOL) {
+        double mine = 0.0;
+#pragma unroll
+        for (int q = 0; q < NVAR; ++q) mine += fk[q] * rho[u][q];    // wv[a] = sum_b (2 w f[b,a]) rho[b]
+#pragma unroll
+        for (int q = 0; q < NVAR; ++q) wv[u][q] = __shfl_sync(0xffffffffu, mine, q);
+      } else {
+        wv[u][0] = rho[u][0] * fk[0];
+      }
     }
 #pragma unroll
     for (int s = 0; s < NCH; ++s) {
-      double* y = a.Y[s] + g * a.ldY[s] + (long)x * a.no[s];
+      const int no = a.no[s];
+      double* yb = a.Y[s] + g * a.ldY[s] + (long)x0 * no;
       const double* p = a.phi[s] + (a.g0 + g) * a.ldphi[s];
-      for (int o = lane; o < a.no[s]; o += 32) {
-        const double p0 = p[o];
-        double a0 = wv[s * NVAR] * p0;
+      for (int o = lane * W; o < no; o += 32 * W) {
+        XcVec<W> pc[NVAR];
+        pc[0].load(p + o);
         if (KIND != XC_KIND_ALDA0) {
 #pragma unroll
-          for (int k = 1; k < NVAR; ++k) {
-            a0 += wv[s * NVAR + k] * p[k * a.phi_comp[s] + o];
-            y[k * a.y_comp[s] + o] = wv[s * NVAR + k] * p0;
-          }
+          for (int k = 1; k < NVAR; ++k) pc[k].load(p + k * a.phi_comp[s] + o);
         }
-        y[o] = a0;
+#pragma unroll
+        for (int u = 0; u < XU; ++u)
+          if (x0 + u < a.nvec) {
+            XcVec<W> out;
+#pragma unroll
+            for (int e = 0; e < W; ++e) out.v[e] = wv[u][s * NVAR] * pc[0].v[e];
+            if (KIND != XC_KIND_ALDA0) {
+#pragma unroll
+              for (int k = 1; k < NVAR; ++k) {
+                XcVec<W> ok;
+#pragma unroll
+                for (int e = 0; e < W; ++e) {
+                  out.v[e] += wv[u][s * NVAR + k] * pc[k].v[e];
+                  ok.v[e] = wv[u][s * NVAR + k] * pc[0].v[e];
+                }
+                ok.store(yb + (long)u * no + k * a.y_comp[s] + o);
+              }
+            }
+            out.store(yb + (long)u * no + o);
+          }
       }
     }
   }

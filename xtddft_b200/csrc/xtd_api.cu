@@ -730,7 +730,13 @@ static int setup_call_buffers(xtd_engine* h, int nvec) {
 
 template <int NVAR, int KIND>
 static void launch_xc(const XcArgs& a, cudaStream_t s) {
-  xc_weight_kernel<NVAR, KIND><<<(unsigned)cdiv(a.gb, 8), 256, 0, s>>>(a);
+  // vectors per pass: 4 for one AO component, 2 for value + gradient (register budget); 16-byte accesses when every
+  // (vector, component) row segment is 16-byte aligned, i.e. all occupied counts are even
+  constexpr int XU = NVAR == 1 ? 4 : 2;
+  const bool even = (a.no[0] % 2 == 0) && (a.nch == 1 || a.no[1] % 2 == 0);
+  const unsigned grid = (unsigned)cdiv(a.gb, 8);
+  if (even) xc_weight_kernel<NVAR, KIND, XU, 2><<<grid, 256, 0, s>>>(a);
+  else xc_weight_kernel<NVAR, KIND, XU, 1><<<grid, 256, 0, s>>>(a);
 }
 
 static int run_xc(xtd_engine* h, int nvec) {
@@ -864,6 +870,34 @@ static int run_k(xtd_engine* h, int nvec) {
     for (size_t ab = 0; ab < ablks.size(); ++ab) {
       for (long P0 = 0; P0 < naux; P0 += pc) {
         const int pn = (int)std::min<long>(pc, naux - P0);
+        if (k.uniform) {
+          // Uniform weights: flatten (P, i) into the row index so the small occupied dimension is not padded to the
+          // 128-row tile per aux function.  U[P][i][x][b] = sum_j Loo[(P,i)][j] zt[x][b][j]; the contraction below
+          // then reads rows m = (i, x) of slice P and scatters them to sigma[x][i][:] through the two-level row map.
+          {
+            PhaseTimer t(h, XTD_T_K1);
+            GemmDesc d;
+            d.A = view2d(Loo + P0 * ch->no * ch->ldoo, ch->ldoo, pn * ch->no, ch->no);
+            d.B = view3d(h->ZT[k.ch], ch->ldzt, (long)ch->nv * ch->ldzt, nvec, ch->nv, ch->no);
+            d.M = pn * ch->no; d.N = ch->nv; d.K = ch->no;
+            d.batches = nvec; d.z_div = 1; d.a_hi = 0; d.b_hi = 1;
+            d.C = U; d.ldc = (long)nvec * ch->ldz; d.c_batch_stride = ch->ldz;
+            XTD_TRY(gemm(h->gemm, d, s));
+          }
+          {
+            PhaseTimer t(h, XTD_T_K2);
+            // SIG[x][i][a] += w * sum_P sum_b U[P][(i,x)][b] Lvv[P][a][b]
+            GemmDesc d;
+            d.A = view3d(U, ch->ldz, (long)nvec * ch->no * ch->ldz, pn, nvec * ch->no, ch->nv);
+            d.B = view3d(Lvv, ch->ldvv, (long)ch->nv * ch->ldvv, (int)(naux - P0), ch->nv, ch->nv, 0, 0, (int)P0);
+            d.M = nvec * ch->no; d.N = ch->nv; d.K = ch->nv; d.nouter = pn;
+            d.C = h->SIG + h->sig_base[k.ch]; d.ldc = ch->ldz; d.accumulate = true;
+            d.c_row_div = nvec; d.c_row_hi = ch->ldz; d.c_row_lo = (long)ch->no * ch->ldz;
+            d.alpha = k.w[0][0][0][0];
+            XTD_TRY(gemm(h->gemm, d, s));
+          }
+          continue;
+        }
         {
           PhaseTimer t(h, XTD_T_K1);
           for (size_t ib = 0; ib < iblks.size(); ++ib) {
@@ -986,6 +1020,7 @@ int xtd_sigma_partial(xtd_handle h, int nvec, const double* z_dev) {
   XTD_REQUIRE(nvec >= 1 && nvec <= h->max_nvec && z_dev, XTD_ERR_ARG, "xtd_sigma: nvec %d outside 1..%d", nvec, h->max_nvec);
   cudaStream_t s = h->stream;
   h->ev_used = 0;
+  if (h->prof_phase == XTD_T_TOTAL) cudaProfilerStart();
   if (h->ev_ok) cudaEventRecord(h->ev_total[0], s);
   XTD_TRY(setup_call_buffers(h, nvec));
   long base[2], total;
@@ -1039,6 +1074,7 @@ int xtd_sigma_finish(xtd_handle h, int nvec, double* hz_dev) {
     LAUNCH_CHECK();
   }
   if (h->ev_ok) cudaEventRecord(h->ev_total[1], s);
+  if (h->prof_phase == XTD_T_TOTAL) cudaProfilerStop();
   return XTD_OK;
 }
 
