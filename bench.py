@@ -165,6 +165,15 @@ def cpu_reference_rate(dp, nvec_sample: int = 1, target_s: float = 12.0):
             "seconds_per_vector_full_size": t_full}
 
 
+def config_dict(dp, nvec: int, dim: int, world: int) -> dict:
+    p = dp.p
+    return {"workload": dp.name, "method": dp.method, "nvec_per_step": nvec, "nao": p.nao, "nc": p.nc, "no": p.no, "nv": p.nv,
+            "dim": dim, "naux": dp.naux, "ng": dp.ng, "grid_components": dp.nvar, "hyb": p.hyb,
+            "generator": p.meta.get("generator", "synthetic"),
+            "parallelism": f"aux+grid sharded x{world}, one all-reduce of [nvec,dim] per call",
+            "l2": "inputs larger than L2 (DF tensor and AO values stream from HBM every call)"}
+
+
 def run_reference(args):
     """`--impl reference`: the reference's CPU implementation of the path.  PySCF is not installable here (no wheel,
     no network) and the reference tree does not import without it, so this arm times the oracle port (kind "port")."""
@@ -172,6 +181,7 @@ def run_reference(args):
     if rank != 0:
         return
     from xtddft_b200.synth_device import make_device_problem
+    from xtddft_b200.workloads import plan_for
     dp = make_device_problem(args.config, args.scale)
     nvec = args.nvec or dp.nroots
     vals = []
@@ -184,16 +194,36 @@ def run_reference(args):
     out = {"impl": "reference", "metric": "davidson_sigma_vectors_per_s", "value": v, "unit": "sigma-vectors/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * nvec / v, "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": dp.name, "method": dp.method, "nvec_per_step": nvec, "nao": dp.p.nao, "naux": dp.naux, "ng": dp.ng},
+           "config": config_dict(dp, nvec, int(plan_for(dp.p, dp.method).ext_dim), 1),
            "cpu_baseline": cb, "e2e": {"value": v, "unit": "sigma-vectors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit(out)
 
 
 # ---------------------------------------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------------------------------------
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: everything else any library prints on fd 1 (e.g. NCCL's version banner) is
+    sent to stderr for the rest of the run."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, line)
+
+
 def main():
     args = parse()
+    _claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
     import torch
@@ -332,11 +362,7 @@ def main():
         "metric": "davidson_sigma_vectors_per_s", "value": value, "unit": "sigma-vectors/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": dp.name, "method": dp.method, "nvec_per_step": nvec, "nao": p.nao, "nc": p.nc, "no": p.no, "nv": p.nv,
-                   "dim": dim, "naux": dp.naux, "ng": dp.ng, "grid_components": dp.nvar, "hyb": p.hyb,
-                   "generator": dp.p.meta.get("generator", "synthetic"),
-                   "parallelism": f"aux+grid sharded x{world}, one all-reduce of [nvec,dim] per call",
-                   "l2": "inputs larger than L2 (DF tensor and AO values stream from HBM every call)"},
+        "config": config_dict(dp, nvec, dim, world),
         "clocks": clocks,
         "e2e": {"value": nvec / e2e_s, "unit": "sigma-vectors/s", "h2d_bytes_per_step": nvec * dim * 8, "d2h_bytes_per_step": nvec * dim * 8},
         "gpu_launches": int(launches),
@@ -349,7 +375,7 @@ def main():
         out_json["davidson"] = dav
     if world == 1 and not args.no_cpu_baseline:
         out_json["cpu_baseline"] = cpu_reference_rate(dp)
-    print(json.dumps(out_json))
+    emit(out_json)
     if world > 1:
         torch.distributed.destroy_process_group()
 
