@@ -73,6 +73,11 @@ int xtd_jblock_diag(xtd_handle h, int jb, double* out_dev);   /* out[nr*nc] = su
  *   XTD_FXC_MCOL  fxc[nvar,nvar,ng] unweighted       (cache_xc_kernel_sf_mc) */
 int xtd_set_grid(xtd_handle h, const double* ao_dev, int nvar, long ng, long ld_row, long stride_comp, const double* w_dev);
 int xtd_set_fxc(xtd_handle h, int kind, const double* fxc_dev);
+/* Transform the AO values once to the occupied / virtual MO values of every declared channel (phi = ao.Co, phiv = ao.Cv)
+ * and build the per-point kernel tables.  Needs the channels, xtd_set_grid and xtd_set_fxc; implied by xtd_finalize.
+ * After it returns the ao, weights and (UKS / MCOL) fxc buffers are no longer referenced and may be freed -- call it
+ * before streaming the 3-centre tensor when memory is tight.  The ALDA0 kernel f[ng] stays referenced. */
+int xtd_grid_commit(xtd_handle h);
 
 /* local terms (Fock blocks, Delta-A couplings; XTDA.py:628-687, XSF_TDA.py:1146-1274):
  *   RIGHT: dst[r,c] += alpha * sum_b src[r,b] M[b,c]   M[mrows=k, mcols=nc]

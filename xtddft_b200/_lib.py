@@ -41,6 +41,7 @@ SIGNATURES = {
     "xtd_jblock_diag": (_I, [_P, _I, _P]),
     "xtd_set_grid": (_I, [_P, _P, _I, _L, _L, _L, _P]),
     "xtd_set_fxc": (_I, [_P, _I, _P]),
+    "xtd_grid_commit": (_I, [_P]),
     "xtd_add_local_gemm": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _D]),
     "xtd_add_rank1": (_I, [_P, _I, _P, _I, _P]),
     "xtd_add_diag": (_I, [_P, _I, _P]),

@@ -5,8 +5,9 @@
 //   per (tensor, channel) with an exchange term
 //                 Loo [naux_loc][no][ld_oo], Lvv [naux_loc][nv][ld_vv]   MO-resident 3-centre blocks
 //   per Coulomb block  Ljb [naux_loc][nr][ld]
-//   grid          ao (caller's buffer, [nvar][ng][ld]), phi [ch][nvar][ng][ld_o] = ao . Co, per-point kernel table wf
-//   per call (workspace arena)  Z, ZT, ZTs, SIG, mo1T, RT, Y/U chunk, split-K partials
+//   grid          phi [ch][nvar][ng][ld_o] = ao . Co and phiv [ch][nvar][ng][ld_v] = ao . Cv (the caller's ao buffer is
+//                 only read by xtd_grid_commit), per-point kernel table wf
+//   per call (workspace arena)  Z, ZT, ZTs, SIG, Y/U chunk, split-K partials
 #include "../../include/xtd_sigma.h"
 #include "gemm.cuh"
 #include "kernels.cuh"
@@ -45,10 +46,14 @@ struct Channel {
   long ldz, ldzt, ldco, ldcv, ldN;
   DevBuf Co, Cv, CoT, CvT;          // [nao][ldco], [nao][ldcv], [no][ldN], [nv][ldN]
   DevBuf Loo[2], Lvv[2];            // per DF tensor
+  DevBuf Loob[2][2];                // per DF tensor and occupied row block: [naux_loc][rows of the block][ldoo], so that
+  bool need_split[2] = {false, false};   // (aux, row) flattens into one uniformly strided row index for block weights
   long ldoo, ldvv;
   bool need_k[2] = {false, false};
-  DevBuf phi;                       // [nvar_eff][ng][ldphi]
+  DevBuf phi;                       // occupied values on the grid  [nvar_eff][ng][ldphi]
   long ldphi = 0;
+  DevBuf phiv;                      // virtual values on the grid   [nvar_eff][ng][ldphiv]
+  long ldphiv = 0;
   // gather CSR
   long *g_indptr = nullptr, *g_cols = nullptr;
   double* g_vals = nullptr;
@@ -123,6 +128,7 @@ struct xtd_engine {
   int fxc_kind = XTD_FXC_NONE;
   const double* fxc = nullptr;
   DevBuf wf;
+  bool grid_committed = false;
   // local terms
   std::vector<LocalGemmRec*> lgemms;
   std::vector<Rank1Rec*> rank1s;
@@ -140,7 +146,6 @@ struct xtd_engine {
   double *Z[2] = {nullptr, nullptr}, *ZT[2] = {nullptr, nullptr}, *ZTs[2] = {nullptr, nullptr};
   double* SIG = nullptr;
   long sig_base[2] = {0, 0};
-  double *mo1T[2] = {nullptr, nullptr}, *RT[2] = {nullptr, nullptr};
   double* scratch = nullptr;      // Y / U chunk region
   size_t scratch_doubles = 0;
   double *jR = nullptr, *jRm = nullptr, *r1d = nullptr;
@@ -264,6 +269,58 @@ MatView view3d(const double* base, long ld, long sq, int nq, int rows, int cols,
   return v;
 }
 
+// AO values -> MO values on the grid, once per solve (the MO<->AO transforms of the reference's vind applied to the
+// grid basis instead of to every trial vector):
+//   phi [c][g][o] = sum_mu ao[c][g][mu] Co[mu][o]      phiv[c][g][v] = sum_mu ao[c][g][mu] Cv[mu][v]
+// plus the per-point kernel tables.  Afterwards the caller's ao / weights buffers are no longer referenced.
+int grid_commit(xtd_engine* h) {
+  XTD_REQUIRE(h->ao && h->fxc_kind != XTD_FXC_NONE, XTD_ERR_STATE, "grid commit: xtd_set_grid and xtd_set_fxc come first");
+  XTD_REQUIRE(!h->ch.empty(), XTD_ERR_STATE, "grid commit: channels must be declared first");
+  if (h->fxc_kind == XTD_FXC_UKS) XTD_REQUIRE(h->ch.size() == 2, XTD_ERR_ARG, "UKS kernel needs two channels");
+  else XTD_REQUIRE(h->ch.size() == 1, XTD_ERR_ARG, "spin-flip kernels need one channel");
+  cudaStream_t s = h->stream;
+  h->nvar_eff = (h->fxc_kind == XTD_FXC_ALDA0) ? 1 : h->nvar;
+  if (h->ng > 0) {
+    h->arena.used = 0;
+    size_t split_bytes = std::min<size_t>(h->arena.cap / 4, (size_t)1 << 30);
+    h->gemm.split_ws = h->arena.take(split_bytes / 8);
+    h->gemm.split_ws_bytes = split_bytes;
+    for (auto* c : h->ch) {
+      c->ldphi = pad_ld(c->no);
+      c->ldphiv = pad_ld(c->nv);
+      XTD_TRY(c->phi.alloc((size_t)h->nvar_eff * h->ng * c->ldphi));
+      XTD_TRY(c->phiv.alloc((size_t)h->nvar_eff * h->ng * c->ldphiv));
+      GemmDesc d;
+      d.A = view3d(h->ao, h->ao_ld, h->ao_comp, h->nvar_eff, (int)h->ng, h->nao);
+      d.B = view2d(c->CoT.p, h->ldN, c->no, h->nao);
+      d.M = (int)h->ng; d.N = c->no; d.K = h->nao; d.batches = h->nvar_eff; d.a_hi = 1; d.b_hi = 0;
+      d.C = c->phi.p; d.ldc = c->ldphi; d.c_batch_stride = h->ng * c->ldphi;
+      XTD_TRY(gemm(h->gemm, d, s));
+      GemmDesc e = d;
+      e.B = view2d(c->CvT.p, h->ldN, c->nv, h->nao);
+      e.N = c->nv;
+      e.C = c->phiv.p; e.ldc = c->ldphiv; e.c_batch_stride = h->ng * c->ldphiv;
+      XTD_TRY(gemm(h->gemm, e, s));
+    }
+    if (h->fxc_kind == XTD_FXC_UKS) {
+      const int nr = 2 * h->nvar;
+      XTD_TRY(h->wf.alloc((size_t)h->ng * nr * nr));
+      build_wf_uks_kernel<<<grid1d(h->ng, 128), 128, 0, s>>>(h->wf.p, h->fxc, h->wgrid, h->ng, h->nvar);
+      LAUNCH_CHECK();
+    } else if (h->fxc_kind == XTD_FXC_MCOL) {
+      XTD_TRY(h->wf.alloc((size_t)h->ng * h->nvar * h->nvar));
+      build_wf_mcol_kernel<<<grid1d(h->ng, 128), 128, 0, s>>>(h->wf.p, h->fxc, h->wgrid, h->ng, h->nvar);
+      LAUNCH_CHECK();
+    }
+    XTD_CUDA(cudaStreamSynchronize(s));
+  }
+  h->grid_committed = true;
+  h->ao = nullptr;
+  h->wgrid = nullptr;
+  if (h->fxc_kind != XTD_FXC_ALDA0) h->fxc = nullptr;   // ALDA0 reads the caller's weighted kernel f[ng] on every call
+  return XTD_OK;
+}
+
 }  // namespace
 
 // =========================================================================================================
@@ -305,8 +362,8 @@ int xtd_destroy(xtd_handle h) {
   if (!h) return XTD_OK;
   cudaDeviceSynchronize();
   for (auto* c : h->ch) {
-    c->Co.release(); c->Cv.release(); c->CoT.release(); c->CvT.release(); c->phi.release();
-    for (int t = 0; t < 2; ++t) { c->Loo[t].release(); c->Lvv[t].release(); }
+    c->Co.release(); c->Cv.release(); c->CoT.release(); c->CvT.release(); c->phi.release(); c->phiv.release();
+    for (int t = 0; t < 2; ++t) { c->Loo[t].release(); c->Lvv[t].release(); c->Loob[t][0].release(); c->Loob[t][1].release(); }
     if (c->g_indptr) cudaFree(c->g_indptr);
     if (c->g_cols) cudaFree(c->g_cols);
     if (c->g_vals) cudaFree(c->g_vals);
@@ -405,6 +462,7 @@ int xtd_add_kterm(xtd_handle h, int tensor, int chn, const double* w, int nob, i
         }
   h->kterms.push_back(k);
   c->need_k[tensor] = true;
+  if (!k.uniform && c->o_blocks.size() > 1) c->need_split[tensor] = true;
   return XTD_OK;
 }
 
@@ -435,6 +493,11 @@ int xtd_df_begin(xtd_handle h, int tensor, long naux_local) {
     if (!c->need_k[tensor]) continue;
     XTD_TRY(c->Loo[tensor].alloc((size_t)naux_local * c->no * c->ldoo));
     XTD_TRY(c->Lvv[tensor].alloc((size_t)naux_local * c->nv * c->ldvv));
+    if (c->need_split[tensor]) {
+      const int o2 = c->o_blocks[1].first;
+      XTD_TRY(c->Loob[tensor][0].alloc((size_t)naux_local * o2 * c->ldoo));
+      XTD_TRY(c->Loob[tensor][1].alloc((size_t)naux_local * (c->no - o2) * c->ldoo));
+    }
   }
   if (tensor == 0)
     for (auto* j : h->jblocks) XTD_TRY(j->L.alloc((size_t)naux_local * j->nr * j->ld));
@@ -507,6 +570,17 @@ int xtd_df_add(xtd_handle h, int tensor, const double* l_dev, long np, long ld_r
           e.batches = pn; e.a_hi = 1; e.b_hi = 0;
           e.C = c->Loo[tensor].p + P0 * c->no * c->ldoo; e.ldc = c->ldoo; e.c_batch_stride = (long)c->no * c->ldoo;
           XTD_TRY(gemm(h->gemm, e, s));
+          if (c->need_split[tensor]) {
+            const int o2 = c->o_blocks[1].first;
+            const int r0s[2] = {0, o2}, nrs[2] = {o2, c->no - o2};
+            for (int ib = 0; ib < 2; ++ib) {
+              GemmDesc f = e;
+              f.A = view3d(half, ldN, (long)c->no * ldN, pn, nrs[ib], N, r0s[ib], 0);
+              f.M = nrs[ib];
+              f.C = c->Loob[tensor][ib].p + P0 * nrs[ib] * c->ldoo; f.c_batch_stride = (long)nrs[ib] * c->ldoo;
+              XTD_TRY(gemm(h->gemm, f, s));
+            }
+          }
         }
         if (tensor == 0)
           for (auto* j : h->jblocks) {
@@ -550,7 +624,7 @@ int xtd_jblock_diag(xtd_handle h, int jb, double* out_dev) {
 }
 
 int xtd_set_grid(xtd_handle h, const double* ao_dev, int nvar, long ng, long ld_row, long stride_comp, const double* w_dev) {
-  XTD_REQUIRE(h && !h->finalized, XTD_ERR_STATE, "xtd_set_grid after finalize");
+  XTD_REQUIRE(h && !h->finalized && !h->grid_committed, XTD_ERR_STATE, "xtd_set_grid after commit / finalize");
   XTD_REQUIRE(ao_dev && w_dev && (nvar == 1 || nvar == 4) && ng >= 0 && ld_row >= h->nao, XTD_ERR_ARG, "xtd_set_grid: bad arguments");
   XTD_REQUIRE(ld_row % 2 == 0 && stride_comp % 2 == 0 && ((uintptr_t)ao_dev & 15) == 0, XTD_ERR_ALIGN,
               "xtd_set_grid: ao needs even ld_row / stride_comp and a 16-byte aligned base (pad with xtd helpers)");
@@ -559,10 +633,16 @@ int xtd_set_grid(xtd_handle h, const double* ao_dev, int nvar, long ng, long ld_
 }
 
 int xtd_set_fxc(xtd_handle h, int kind, const double* fxc_dev) {
-  XTD_REQUIRE(h && !h->finalized, XTD_ERR_STATE, "xtd_set_fxc after finalize");
+  XTD_REQUIRE(h && !h->finalized && !h->grid_committed, XTD_ERR_STATE, "xtd_set_fxc after commit / finalize");
   XTD_REQUIRE(kind >= XTD_FXC_NONE && kind <= XTD_FXC_MCOL && (kind == XTD_FXC_NONE || fxc_dev), XTD_ERR_ARG, "xtd_set_fxc: bad arguments");
   h->fxc_kind = kind; h->fxc = fxc_dev;
   return XTD_OK;
+}
+
+int xtd_grid_commit(xtd_handle h) {
+  XTD_REQUIRE(h && !h->finalized, XTD_ERR_STATE, "xtd_grid_commit after finalize");
+  if (h->fxc_kind == XTD_FXC_NONE || h->grid_committed) return XTD_OK;
+  return grid_commit(h);
 }
 
 int xtd_add_local_gemm(xtd_handle h, int side, int dch, int r0, int nr, int c0, int nc, int sch, int sr0, int sc0, const double* mat,
@@ -640,44 +720,14 @@ int xtd_finalize(xtd_handle h, int max_nvec) {
   cudaStream_t s = h->stream;
   h->max_nvec = max_nvec;
   const bool xc = (h->fxc_kind != XTD_FXC_NONE) && h->ng > 0;
-  if (h->fxc_kind != XTD_FXC_NONE) XTD_REQUIRE(h->ao, XTD_ERR_STATE, "xtd_finalize: kernel set but no grid");
-  if (xc) {
-    if (h->fxc_kind == XTD_FXC_UKS) XTD_REQUIRE(h->ch.size() == 2, XTD_ERR_ARG, "UKS kernel needs two channels");
-    else XTD_REQUIRE(h->ch.size() == 1, XTD_ERR_ARG, "spin-flip kernels need one channel");
-    h->nvar_eff = (h->fxc_kind == XTD_FXC_ALDA0) ? 1 : h->nvar;
-    // occupied values on the grid  phi[c][g][o] = sum_mu ao[c][g][mu] Co[mu][o]
-    h->arena.used = 0;
-    size_t split_bytes = std::min<size_t>(h->arena.cap / 4, (size_t)1 << 30);
-    h->gemm.split_ws = h->arena.take(split_bytes / 8);
-    h->gemm.split_ws_bytes = split_bytes;
-    for (auto* c : h->ch) {
-      c->ldphi = pad_ld(c->no);
-      XTD_TRY(c->phi.alloc((size_t)h->nvar_eff * h->ng * c->ldphi));
-      GemmDesc d;
-      d.A = view3d(h->ao, h->ao_ld, h->ao_comp, h->nvar_eff, (int)h->ng, h->nao);
-      d.B = view2d(c->CoT.p, h->ldN, c->no, h->nao);
-      d.M = (int)h->ng; d.N = c->no; d.K = h->nao; d.batches = h->nvar_eff; d.a_hi = 1; d.b_hi = 0;
-      d.C = c->phi.p; d.ldc = c->ldphi; d.c_batch_stride = h->ng * c->ldphi;
-      XTD_TRY(gemm(h->gemm, d, s));
-    }
-    if (h->fxc_kind == XTD_FXC_UKS) {
-      const int nr = 2 * h->nvar;
-      XTD_TRY(h->wf.alloc((size_t)h->ng * nr * nr));
-      build_wf_uks_kernel<<<grid1d(h->ng, 128), 128, 0, s>>>(h->wf.p, h->fxc, h->wgrid, h->ng, h->nvar);
-      LAUNCH_CHECK();
-    } else if (h->fxc_kind == XTD_FXC_MCOL) {
-      XTD_TRY(h->wf.alloc((size_t)h->ng * h->nvar * h->nvar));
-      build_wf_mcol_kernel<<<grid1d(h->ng, 128), 128, 0, s>>>(h->wf.p, h->fxc, h->wgrid, h->ng, h->nvar);
-      LAUNCH_CHECK();
-    }
-  }
+  if (h->fxc_kind != XTD_FXC_NONE) XTD_REQUIRE(h->ao || h->grid_committed, XTD_ERR_STATE, "xtd_finalize: kernel set but no grid");
+  if (xc && !h->grid_committed) XTD_TRY(grid_commit(h));
   XTD_CUDA(cudaStreamSynchronize(s));
   // check that the fixed per-call buffers for max_nvec fit in the arena with room for a work chunk
   size_t fixed = 0;
   for (auto* c : h->ch) {
     fixed += (size_t)max_nvec * c->no * c->ldz * 2;              // Z, SIG
     fixed += (size_t)max_nvec * c->nv * c->ldzt * 2;             // ZT, ZTs
-    if (xc) fixed += (size_t)max_nvec * c->no * h->ldN * 2;      // mo1T, RT
   }
   XTD_REQUIRE(fixed * 8 + (32u << 20) < h->arena.cap, XTD_ERR_NOMEM, "xtd_finalize: workspace of %zu bytes too small for %d vectors (%zu fixed)",
               h->arena.cap, max_nvec, fixed * 8);
@@ -705,11 +755,6 @@ static int setup_call_buffers(xtd_engine* h, int nvec) {
     h->ZT[c] = h->arena.take((size_t)nvec * ch->nv * ch->ldzt);
     h->ZTs[c] = h->arena.take((size_t)nvec * ch->nv * ch->ldzt);
     XTD_REQUIRE(h->ZT[c] && h->ZTs[c], XTD_ERR_NOMEM, "workspace exhausted (transposed trial vectors)");
-    if (xc) {
-      h->mo1T[c] = h->arena.take((size_t)nvec * ch->no * h->ldN);
-      h->RT[c] = h->arena.take((size_t)nvec * ch->no * h->ldN);
-      XTD_REQUIRE(h->mo1T[c] && h->RT[c], XTD_ERR_NOMEM, "workspace exhausted (half-transformed densities)");
-    }
   }
   const size_t njb = h->jblocks.size();
   if (njb) {
@@ -742,22 +787,7 @@ static void launch_xc(const XcArgs& a, cudaStream_t s) {
 static int run_xc(xtd_engine* h, int nvec) {
   cudaStream_t s = h->stream;
   const int nch = (int)h->ch.size();
-  const int N = h->nao;
   const int nve = h->nvar_eff;
-  {
-    PhaseTimer t(h, XTD_T_XC_GEMM);
-    for (int c = 0; c < nch; ++c) {
-      Channel* ch = h->ch[c];
-      // mo1T[(x,o)][mu] = sum_v Z[(x,o)][v] Cv[mu][v]      (MO -> AO back-transformation of the trial vectors)
-      GemmDesc d;
-      d.A = view2d(h->Z[c], ch->ldz, nvec * ch->no, ch->nv);
-      d.B = view2d(ch->Cv.p, ch->ldcv, N, ch->nv);
-      d.M = nvec * ch->no; d.N = N; d.K = ch->nv;
-      d.C = h->mo1T[c]; d.ldc = h->ldN;
-      XTD_TRY(gemm(h->gemm, d, s));
-      XTD_CUDA(cudaMemsetAsync(h->RT[c], 0, (size_t)nvec * ch->no * h->ldN * 8, s));
-    }
-  }
   // grid chunk: Y buffers for all channels must fit the scratch region
   size_t per_g = 0;
   long ldY[2] = {0, 0};
@@ -781,11 +811,11 @@ static int run_xc(xtd_engine* h, int nvec) {
       PhaseTimer t(h, XTD_T_XC_GEMM);
       for (int c = 0; c < nch; ++c) {
         Channel* ch = h->ch[c];
-        // Y[cmp][g][(x,o)] = sum_mu ao[cmp][g0+g][mu] mo1T[(x,o)][mu]
+        // Y[cmp][g][(x,o)] = sum_v phiv[cmp][g0+g][v] Z[(x,o)][v]     (trial vectors evaluated on the grid, virtual side)
         GemmDesc d;
-        d.A = view3d(h->ao, h->ao_ld, h->ao_comp, nve, gb, N, (int)g0, 0);
-        d.B = view2d(h->mo1T[c], h->ldN, nvec * ch->no, N);
-        d.M = gb; d.N = nvec * ch->no; d.K = N; d.batches = nve; d.a_hi = 1; d.b_hi = 0;
+        d.A = view3d(ch->phiv.p, ch->ldphiv, h->ng * ch->ldphiv, nve, gb, ch->nv, (int)g0, 0);
+        d.B = view2d(h->Z[c], ch->ldz, nvec * ch->no, ch->nv);
+        d.M = gb; d.N = nvec * ch->no; d.K = ch->nv; d.batches = nve; d.a_hi = 1; d.b_hi = 0;
         d.C = Y[c]; d.ldc = ldY[c]; d.c_batch_stride = (long)gb * ldY[c];
         XTD_TRY(gemm(h->gemm, d, s));
       }
@@ -814,28 +844,15 @@ static int run_xc(xtd_engine* h, int nvec) {
       PhaseTimer t(h, XTD_T_XC_GEMM);
       for (int c = 0; c < nch; ++c) {
         Channel* ch = h->ch[c];
-        // RT[(x,o)][mu] += sum_cmp sum_g A[cmp][g][(x,o)] ao[cmp][g0+g][mu]      (integration back to AO)
+        // SIG[(x,o)][v] += sum_cmp sum_g A[cmp][g][(x,o)] phiv[cmp][g0+g][v]      (integration straight into the MO block)
         GemmDesc d;
         d.a_kc = false; d.b_kc = false;
         d.A = view3d(Y[c], ldY[c], (long)gb * ldY[c], nve, gb, nvec * ch->no);
-        d.B = view3d(h->ao, h->ao_ld, h->ao_comp, nve, gb, N, (int)g0, 0);
-        d.M = nvec * ch->no; d.N = N; d.K = gb; d.nouter = nve;
-        d.C = h->RT[c]; d.ldc = h->ldN; d.accumulate = true;
+        d.B = view3d(ch->phiv.p, ch->ldphiv, h->ng * ch->ldphiv, nve, gb, ch->nv, (int)g0, 0);
+        d.M = nvec * ch->no; d.N = ch->nv; d.K = gb; d.nouter = nve;
+        d.C = h->SIG + h->sig_base[c]; d.ldc = ch->ldz; d.accumulate = true;
         XTD_TRY(gemm(h->gemm, d, s));
       }
-    }
-  }
-  {
-    PhaseTimer t(h, XTD_T_XC_GEMM);
-    for (int c = 0; c < nch; ++c) {
-      Channel* ch = h->ch[c];
-      // SIG[(x,o)][v] += sum_mu RT[(x,o)][mu] CvT[v][mu]      (AO -> MO projection)
-      GemmDesc d;
-      d.A = view2d(h->RT[c], h->ldN, nvec * ch->no, N);
-      d.B = view2d(ch->CvT.p, h->ldN, ch->nv, N);
-      d.M = nvec * ch->no; d.N = ch->nv; d.K = N;
-      d.C = h->SIG + h->sig_base[c]; d.ldc = ch->ldz; d.accumulate = true;
-      XTD_TRY(gemm(h->gemm, d, s));
     }
   }
   return XTD_OK;
@@ -898,39 +915,39 @@ static int run_k(xtd_engine* h, int nvec) {
           }
           continue;
         }
+        // Block weights: one half-transform per (row block, column block) pair with the trial vectors scaled by
+        // w(iblk, ablk, :, :); rows (P, i in block) are flattened as in the uniform case and land in U[P][i][x][b].
         {
           PhaseTimer t(h, XTD_T_K1);
           for (size_t ib = 0; ib < iblks.size(); ++ib) {
-            const double* zt = h->ZT[k.ch];
-            if (!k.uniform) {
-              BlockSplit bs;
-              bs.o2off = o2off; bs.v2off = v2off;
-              for (int j = 0; j < 2; ++j)
-                for (int b = 0; b < 2; ++b) bs.w[j][b] = k.w[ib][ab][j < k.nob ? j : 0][b < k.nvb ? b : 0];
-              scale_blocks_kernel<<<dim3((unsigned)cdiv(ch->no, 128), ch->nv, nvec), 128, 0, s>>>(h->ZTs[k.ch], h->ZT[k.ch], ch->ldzt,
-                                                                                                (long)ch->nv * ch->ldzt, ch->nv, ch->no, bs);
-              LAUNCH_CHECK();
-              zt = h->ZTs[k.ch];
-            }
-            // U[P][x][i][b] = sum_j Loo[P][i][j] zt[x][b][j]        (exchange half-transform of the trial vectors)
+            BlockSplit bs;
+            bs.o2off = o2off; bs.v2off = v2off;
+            for (int j = 0; j < 2; ++j)
+              for (int b = 0; b < 2; ++b) bs.w[j][b] = k.w[ib][ab][j < k.nob ? j : 0][b < k.nvb ? b : 0];
+            scale_blocks_kernel<<<dim3((unsigned)cdiv(ch->no, 128), ch->nv, nvec), 128, 0, s>>>(h->ZTs[k.ch], h->ZT[k.ch], ch->ldzt,
+                                                                                              (long)ch->nv * ch->ldzt, ch->nv, ch->no, bs);
+            LAUNCH_CHECK();
+            const int i0 = iblks[ib].first, nr = iblks[ib].second;
+            const double* lrows = ch->need_split[k.tensor] ? ch->Loob[k.tensor][ib].p : Loo;   // single row block: Loo itself
             GemmDesc d;
-            d.A = view3d(Loo, ch->ldoo, (long)ch->no * ch->ldoo, (int)(naux - P0), iblks[ib].second, ch->no, iblks[ib].first, 0, (int)P0);
-            d.B = view3d(zt, ch->ldzt, (long)ch->nv * ch->ldzt, nvec, ch->nv, ch->no);
-            d.M = iblks[ib].second; d.N = ch->nv; d.K = ch->no;
-            d.batches = pn * nvec; d.z_div = nvec; d.a_hi = 1; d.a_lo = 0; d.b_hi = 0; d.b_lo = 1;
-            d.C = U + (long)iblks[ib].first * ch->ldz; d.ldc = ch->ldz; d.c_batch_stride = (long)ch->no * ch->ldz;
+            d.A = view2d(lrows + P0 * nr * ch->ldoo, ch->ldoo, pn * nr, ch->no);
+            d.B = view3d(h->ZTs[k.ch], ch->ldzt, (long)ch->nv * ch->ldzt, nvec, ch->nv, ch->no);
+            d.M = pn * nr; d.N = ch->nv; d.K = ch->no;
+            d.batches = nvec; d.z_div = 1; d.a_hi = 0; d.b_hi = 1;
+            d.C = U + (long)i0 * nvec * ch->ldz; d.ldc = (long)nvec * ch->ldz; d.c_batch_stride = ch->ldz;
+            d.c_row_div = nr; d.c_row_hi = (long)ch->no * nvec * ch->ldz; d.c_row_lo = (long)nvec * ch->ldz;
             XTD_TRY(gemm(h->gemm, d, s));
           }
         }
         {
           PhaseTimer t(h, XTD_T_K2);
-          // SIG[(x,i)][a] += w * sum_P sum_b U[P][(x,i)][b] Lvv[P][a][b]
+          // SIG[x][i][a in block] += sum_P sum_b U[P][(i,x)][b] Lvv[P][a][b]
           GemmDesc d;
           d.A = view3d(U, ch->ldz, (long)nvec * ch->no * ch->ldz, pn, nvec * ch->no, ch->nv);
           d.B = view3d(Lvv, ch->ldvv, (long)ch->nv * ch->ldvv, (int)(naux - P0), ablks[ab].second, ch->nv, ablks[ab].first, 0, (int)P0);
           d.M = nvec * ch->no; d.N = ablks[ab].second; d.K = ch->nv; d.nouter = pn;
           d.C = h->SIG + h->sig_base[k.ch] + ablks[ab].first; d.ldc = ch->ldz; d.accumulate = true;
-          d.alpha = k.uniform ? k.w[0][0][0][0] : 1.0;
+          d.c_row_div = nvec; d.c_row_hi = ch->ldz; d.c_row_lo = (long)ch->no * ch->ldz;
           XTD_TRY(gemm(h->gemm, d, s));
         }
       }

@@ -49,6 +49,7 @@ class SigmaEngine:
         torch.cuda.set_device(self.device)
         self.reducer = reducer
         self._keep: List[object] = []          # device tensors the engine holds raw pointers to
+        self._grid_keep: List[object] = []     # ... only until grid_commit
         self._h = C.c_void_p()
         _lib.check(self.lib.xtd_create(C.byref(self._h), self.nao, int(workspace_bytes)), "xtd_create")
         self._set_stream()
@@ -132,18 +133,27 @@ class SigmaEngine:
             buf = torch.zeros((nvar, ng, ld), dtype=torch.float64, device=self.device)
             buf[:, :, :self.nao] = ao[:, :, :self.nao]
             ao = buf
-        self._keep += [ao, weights]
+        self._grid_keep = [ao, weights]
         _lib.check(self.lib.xtd_set_grid(self._h, _ptr(ao), nvar, ng, ao.stride(1), ao.stride(0), _ptr(weights)), "xtd_set_grid")
 
     def set_fxc(self, kind: str, fxc):
         if kind != "none":
             assert fxc.is_contiguous()
-            self._keep.append(fxc)
+            # the ALDA0 kernel f[ng] is read on every call; the UKS / multicollinear tensors only by grid_commit
+            (self._keep if kind == "alda0" else self._grid_keep).append(fxc)
         _lib.check(self.lib.xtd_set_fxc(self._h, _KIND[kind], _ptr(fxc) if kind != "none" else None), "xtd_set_fxc")
+
+    def grid_commit(self):
+        """AO values -> occupied / virtual MO values on the grid (once per solve).  Afterwards the AO array, the weights
+        and the UKS / multicollinear kernel tensor are released: the engine keeps only MO values and its kernel table."""
+        self._set_stream()
+        _lib.check(self.lib.xtd_grid_commit(self._h), "xtd_grid_commit")
+        self._grid_keep = []
 
     # ---- finalize -----------------------------------------------------------------------------------
     def finalize(self, max_nvec: int = 40):
         plan = self.plan
+        self._set_stream()
         for lg in plan.local_gemms:
             m = np.ascontiguousarray(lg.mat, dtype=np.float64)
             dc, r0, nr, c0, ncol = lg.dst
@@ -175,6 +185,7 @@ class SigmaEngine:
         _lib.check(self.lib.xtd_set_scatter(self._h, plan.ext_dim, _np_ptr(sm.indptr), _np_ptr(sm.cols), _np_ptr(chans), _np_ptr(sm.vals),
                                             len(sm.cols)), "xtd_set_scatter")
         _lib.check(self.lib.xtd_finalize(self._h, int(max_nvec)), "xtd_finalize")
+        self._grid_keep = []                    # xtd_finalize implies the grid commit
         self.max_nvec = int(max_nvec)
         self.finalized = True
 
@@ -184,10 +195,6 @@ class SigmaEngine:
         """Upload a host ProblemData; with world > 1 this rank keeps only its aux block and grid batch."""
         import torch
         eng = cls(plan, p.nao, p.mo_coeff, workspace_bytes=workspace_bytes, device=device, reducer=reducer)
-        for t in eng.tensors_used:
-            full = p.cderi if t == 0 else p.cderi_lr
-            p0, p1 = split_range(full.shape[0], rank, world)
-            eng.load_cderi(t, full[p0:p1], chunk=df_chunk)
         if plan.xc_kind != "none":
             g0, g1 = split_range(p.ng, rank, world)
             ld = _pad16(p.nao)
@@ -202,6 +209,13 @@ class SigmaEngine:
             else:
                 f = torch.from_numpy(np.ascontiguousarray(p.fxc_mcol[..., g0:g1])).to(eng.device)
             eng.set_fxc(plan.xc_kind, f)
+            del ao, w, f
+            eng.grid_commit()                   # AO values are dropped before the tensor streams in
+            torch.cuda.empty_cache()
+        for t in eng.tensors_used:
+            full = p.cderi if t == 0 else p.cderi_lr
+            p0, p1 = split_range(full.shape[0], rank, world)
+            eng.load_cderi(t, full[p0:p1], chunk=df_chunk)
         eng.finalize(max_nvec)
         return eng
 

@@ -42,7 +42,9 @@ def default_workspace_bytes(dp: DeviceProblem, world: int = 1) -> int:
     nv_i, no_i = p.nvir_b + 2, p.nocc_a + 2
     resident = (dp.naux // world + 1) * (nv_i * pad(nv_i) + no_i * pad(no_i)) * 8 * (2 if dp.method == "xtda" else 1)
     if dp.fxc_kind != "none":
-        resident += (dp.ng // world + 1) * pad(p.nao) * dp.nvar * 8 * 1.25
+        nve = 1 if dp.fxc_kind == "alda0" else dp.nvar
+        nch = 2 if dp.method == "xtda" else 1
+        resident += (dp.ng // world + 1) * (pad(nv_i) + pad(no_i)) * nve * nch * 8          # MO values on the grid
     return int(min(24 << 30, max(1 << 30, (free - resident) * 0.55)))
 
 
@@ -50,8 +52,10 @@ def engine_for_device_problem(dp: DeviceProblem, *, max_nvec: int, workspace_byt
                               reducer=None) -> SigmaEngine:
     plan = plan_for(dp.p, dp.method)
     eng = SigmaEngine(plan, dp.p.nao, dp.p.mo_coeff, workspace_bytes=workspace_bytes, reducer=reducer)
+    dp.make_grid(eng, rank, world)
+    eng.grid_commit()                   # MO values on the grid; the AO array is released before the tensor streams in
+    eng.torch.cuda.empty_cache()
     if eng.tensors_used:
         dp.stream_cderi(eng, 0, rank, world)
-    dp.make_grid(eng, rank, world)
     eng.finalize(max_nvec)
     return eng
