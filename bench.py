@@ -317,10 +317,12 @@ def main():
             from xtddft_b200.davidson import davidson_for_engine
             barrier()
             t0 = time.perf_counter()
-            conv, e, x, info = davidson_for_engine(eng, dp.nroots, dp.method)
+            tm = {}
+            conv, e, x, info = davidson_for_engine(eng, dp.nroots, dp.method, timing=tm)
             torch.cuda.synchronize()
             dav = {"time_to_roots_s": time.perf_counter() - t0, "nroots": dp.nroots, "converged": bool(np.all(conv)),
-                   "cycles": int(info[0]), "sigma_vectors": int(info[1]), "lowest_root_ha": float(e[0])}
+                   "cycles": int(info[0]), "sigma_vectors": int(info[1]), "lowest_root_ha": float(e[0]),
+                   "seconds_in_sigma": tm.get("sigma_s"), "tolerances": "reference SF_TDA.py:392-395 / XTDA.py:775-777 / XSF_TDA.py:1467-1470"}
         except ImportError:
             dav = None
 

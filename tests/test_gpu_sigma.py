@@ -107,3 +107,63 @@ def test_medium_size_tiles(torch_cuda):
     eng = _engine(planmod.build_xtda_plan(p), p, max_nvec=4)
     _check(torch_cuda, eng, vind, hd.size, nvec=3)
     eng.close()
+
+
+@pytest.mark.parametrize("naux,ng", [(1, 1), (3, 129), (17, 5)])
+def test_ragged_sizes(torch_cuda, naux, ng):
+    """One auxiliary function / one grid point / sizes off every tile and chunk boundary; 1 and 7 vectors."""
+    p = make_problem(21, 5, 2, 14, naux, ng, xctype="GGA", hyb=0.5, seed=160 + naux)
+    vind, hd = osig.sf_gen_vind(p, -1, 1)
+    eng = _engine(planmod.build_sf_plan(p, isf=-1, method=1), p, max_nvec=8)
+    _check(torch_cuda, eng, vind, hd.size, nvec=1)
+    _check(torch_cuda, eng, vind, hd.size, nvec=7, seed=2)
+    eng.close()
+    vind, hd = osig.xtda_gen_vind(p)
+    eng = _engine(planmod.build_xtda_plan(p), p, max_nvec=8)
+    _check(torch_cuda, eng, vind, hd.size, nvec=2)
+    eng.close()
+
+
+def test_zero_vector_and_bad_arguments(torch_cuda):
+    torch = torch_cuda
+    from xtddft_b200 import _lib
+    p = make_problem(16, 4, 2, 10, 9, 40, xctype="LDA", hyb=0.3, seed=170)
+    vind, hd = osig.sf_gen_vind(p, -1, 0)
+    eng = _engine(planmod.build_sf_plan(p, isf=-1, method=0), p, max_nvec=4)
+    z = torch.zeros((2, hd.size), dtype=torch.float64, device="cuda")
+    assert eng.sigma(z).abs().max().item() == 0.0                       # A.0 = 0 exactly
+    with pytest.raises(AssertionError):
+        eng.sigma(torch.zeros((2, hd.size + 1), dtype=torch.float64, device="cuda"))
+    with pytest.raises(_lib.XtdError):                                   # the C-ABI rejects nvec outside 1..max_nvec
+        _lib.check(eng.lib.xtd_sigma(eng._h, 9, z.data_ptr(), z.data_ptr()), "xtd_sigma")
+    assert b"nvec" in eng.lib.xtd_last_error()
+    eng.close()
+
+
+def test_empty_shards(torch_cuda):
+    """world=4 with 2 auxiliary functions and 3 grid points: ranks 2 and 3 own no tensor slice, rank 3 no grid point; the
+    partial buffers still add up to the unsharded result."""
+    import ctypes as C
+    from xtddft_b200 import _lib
+    from xtddft_b200.engine import SigmaEngine, _as_tensor
+    torch = torch_cuda
+    p = make_problem(14, 3, 2, 9, 2, 3, xctype="LDA", hyb=0.5, seed=180)
+    plan = planmod.build_sf_plan(p, isf=-1, method=0)
+    vind, hd = osig.sf_gen_vind(p, -1, 0)
+    z = torch.from_numpy(np.random.default_rng(1).standard_normal((2, hd.size))).cuda()
+    acc = None
+    for r in range(4):
+        eng = SigmaEngine.from_problem(plan, p, workspace_bytes=256 << 20, max_nvec=4, rank=r, world=4)
+        _lib.check(eng.lib.xtd_sigma_partial(eng._h, 2, C.c_void_p(z.data_ptr())), "partial")
+        ptr, n = C.c_void_p(), C.c_long()
+        _lib.check(eng.lib.xtd_partial_buffer(eng._h, 2, C.byref(ptr), C.byref(n)), "buffer")
+        part = _as_tensor(torch, ptr.value, n.value, eng.device).clone()
+        acc = part if acc is None else acc + part
+        if r == 3:
+            # finish on the last engine with the summed partials: must equal the oracle
+            _as_tensor(torch, ptr.value, n.value, eng.device).copy_(acc)
+            out = torch.empty_like(z)
+            _lib.check(eng.lib.xtd_sigma_finish(eng._h, 2, C.c_void_p(out.data_ptr())), "finish")
+            ref = vind(z.cpu().numpy())
+            assert np.abs(out.cpu().numpy() - ref).max() < RTOL * max(1.0, np.abs(ref).max())
+        eng.close()

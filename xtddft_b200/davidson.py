@@ -14,6 +14,7 @@ that every caller unpacks is returned as [cycles, sigma_vectors].
 from __future__ import annotations
 
 import ctypes as C
+import time
 from typing import Callable, Optional
 
 import numpy as np
@@ -43,6 +44,9 @@ class CudaVectors:
 
     def _stream(self):
         return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def sync(self):
+        self.torch.cuda.synchronize(self.device)
 
     def alloc(self, rows: int):
         return self.torch.zeros((rows, self.dim), dtype=self.torch.float64, device=self.device)
@@ -141,7 +145,7 @@ def _sort_elast(elast, conv_last, vlast, v):
 
 def davidson1(aop: Callable, x0, precond, tol: float = 1e-12, max_cycle: int = 50, max_space: int = 12, lindep: float = 1e-14,
               nroots: int = 1, pick: Optional[Callable] = None, tol_residual: Optional[float] = None, callback: Optional[Callable] = None,
-              level_shift: float = 1e-3, backend=None, verbose: int = 0):
+              level_shift: float = 1e-3, backend=None, verbose: int = 0, timing: Optional[dict] = None):
     """Solve A c = e c for the lowest `nroots` roots.
 
     aop(X[k, dim] device matrix) -> [k, dim] device matrix;  x0: [n0, dim] host or device;  precond: diagonal (host or
@@ -186,7 +190,11 @@ def davidson1(aop: Callable, x0, precond, tol: float = 1e-12, max_cycle: int = 5
             nt = min(nt, 40)
         if nt == 0:
             raise LinearDependencyError("No linearly independent basis found by the diagonalization solver.")
+        if timing is not None:
+            vb.sync(); _t0 = time.perf_counter()
         axt = aop(xt[:nt])
+        if timing is not None:
+            vb.sync(); timing["sigma_s"] = timing.get("sigma_s", 0.0) + time.perf_counter() - _t0
         nsigma += nt
         head, space = space, space + nt
         vb.copy(xs[head:space], xt[:nt])
@@ -306,7 +314,8 @@ def pick_positive(w, v, nroots, envs):
     return w[idx], v[:, idx], idx
 
 
-def davidson_for_engine(eng, nroots: int, method: str, guess_gaps: Optional[np.ndarray] = None, verbose: int = 0, **over):
+def davidson_for_engine(eng, nroots: int, method: str, guess_gaps: Optional[np.ndarray] = None, verbose: int = 0,
+                        timing: Optional[dict] = None, **over):
     """Run the reference's Davidson settings for `method` on a SigmaEngine (vectors stay on the device)."""
     cfg = dict(SOLVER[method])
     cfg.update(over)
@@ -315,4 +324,4 @@ def davidson_for_engine(eng, nroots: int, method: str, guess_gaps: Optional[np.n
     x0 = init_guess(gaps, nroots, cfg["window"])
     return davidson1(eng.sigma, x0, hdiag, tol=cfg["tol"], tol_residual=cfg["tol_residual"], lindep=cfg["lindep"],
                      max_cycle=cfg["max_cycle"], nroots=min(nroots, hdiag.size), level_shift=cfg["level_shift"],
-                     pick=pick_positive if cfg["pick_positive"] else None, verbose=verbose)
+                     pick=pick_positive if cfg["pick_positive"] else None, verbose=verbose, timing=timing)

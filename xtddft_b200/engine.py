@@ -195,8 +195,8 @@ class SigmaEngine:
         """Upload a host ProblemData; with world > 1 this rank keeps only its aux block and grid batch."""
         import torch
         eng = cls(plan, p.nao, p.mo_coeff, workspace_bytes=workspace_bytes, device=device, reducer=reducer)
-        if plan.xc_kind != "none":
-            g0, g1 = split_range(p.ng, rank, world)
+        g0, g1 = split_range(p.ng, rank, world) if plan.xc_kind != "none" else (0, 0)
+        if g1 > g0:                             # a rank whose grid batch is empty simply has no grid term
             ld = _pad16(p.nao)
             ao = torch.zeros((p.nvar, g1 - g0, ld), dtype=torch.float64, device=eng.device)
             ao[:, :, :p.nao] = torch.from_numpy(np.ascontiguousarray(p.ao[:, g0:g1])).to(eng.device)

@@ -76,6 +76,8 @@ class DeviceProblem:
         if self.fxc_kind == "none":
             return
         g0, g1 = split_range(self.ng, rank, world)
+        if g1 == g0:
+            return
         n = self.p.nao
         ld = (n + 15) // 16 * 16
         ao = torch.zeros((self.nvar, g1 - g0, ld), dtype=torch.float64, device=eng.device)
