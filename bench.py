@@ -43,6 +43,16 @@ def _hbm_peak():
 HBM_PEAK_GBS, HBM_PEAK_SOURCE = _hbm_peak()
 
 
+def _ncu_traffic(workload: str, key: str):
+    """DRAM bytes per launch of the named kernel from the committed `ncu --set full` capture of this workload
+    (profiles/ncu_traffic_r01.json), or None when no capture of this workload exists."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")) as f:
+            return float(json.load(f)[workload][key]["traffic_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -340,7 +350,8 @@ def main():
         k2_flops += 2.0 * naux_loc * nvec * ch.no * ch.nv * ch.nv
     roof = {"bound": "tensor", "kernel": "dgemm_dmma_tma_kernel (exchange contraction sigma += U . Lvv)",
             "achieved": (k2_flops / (gemm_ms * 1e-3) / 1e12) if gemm_ms > 0 else None, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-            "frac": (k2_flops / (gemm_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS) if gemm_ms > 0 else None, "traffic": None,
+            "frac": (k2_flops / (gemm_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS) if gemm_ms > 0 else None,
+            "traffic": _ncu_traffic(dp.name, "k2") if world == 1 and args.scale == 1.0 else None,
             "peak_source": "measured DMMA.8x8x4 issue rate, profiles/fp64_peaks_r01.json (MEASURED_PEAKS.json has no FP64 entry; "
                            "cuBLAS DGEMM on the same box: 35.4 TFLOP/s)",
             "flops_per_launch_group": k2_flops, "ms_per_step_in_kernel": gemm_ms,
@@ -358,7 +369,8 @@ def main():
         hbm_peak = HBM_PEAK_GBS
         roof_xc = {"bound": "hbm", "kernel": "xc_weight_kernel (rho1 on the grid, f_xc weighting, A buffers in place)",
                    "achieved": xc_bytes / (xs_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                   "frac": xc_bytes / (xs_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "bytes_per_step": xc_bytes,
+                   "frac": xc_bytes / (xs_ms * 1e-3) / 1e9 / hbm_peak,
+                   "traffic": _ncu_traffic(dp.name, "xc_stream") if world == 1 and args.scale == 1.0 else None, "bytes_per_step": xc_bytes,
                    "ms_per_step_in_kernel": xs_ms, "peak_source": HBM_PEAK_SOURCE}
     out_json = {
         "metric": "davidson_sigma_vectors_per_s", "value": value, "unit": "sigma-vectors/s", "n_gpus": world, "steps": args.steps,
