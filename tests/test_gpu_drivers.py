@@ -132,3 +132,34 @@ def test_device_vector_kernels(torch_cuda):
     n2 = vb.precond(X, vb.from_host(hd[None]), sh)
     d = hd[None] - sh[:, None]; d[abs(d) < 1e-8] = 1e-8
     assert np.abs(vb.to_host(X) - a / d).max() < 1e-7 * np.abs(a / d).max()
+
+
+def test_driver_property_pass(torch_cuda):
+    """kernel() leaves the reference's strengths on the object: XTDA.os / .rs (XTDA.py:816-821) and the state-to-state
+    oscillator matrix XSF_TDA_GPU.os (XSF_TDA_GPU.py:1263), evaluated on the device and checked against the oracle."""
+    from golden.make_golden_properties import one_electron
+    from oracle import properties as oprop
+    from xtddft_b200.XSF_TDA import XSF_TDA
+    from xtddft_b200.XSF_TDA_GPU import XSF_TDA_GPU
+    from xtddft_b200.XTDA import XTDA
+    p = make_problem(30, 6, 2, 22, 26, 420, xctype="GGA", hyb=0.5, seed=205)
+    dip, ipo, rxp, _ = one_electron(p.nao, 206)
+    p.meta["one_electron"] = {"int1e_r": dip, "int1e_ipovlp": ipo, "int1e_cg_irxp": rxp}
+    p.meta["chiral"] = True
+    mf = SynthMF(p)
+    td = XTDA(mf.mol, mf, nstates=4)
+    td.kernel()
+    x_rows = td._x_rows
+    assert np.abs(td.os - oprop.xtda_osc_str(p, td.e, x_rows, dip)).max() < 1e-9 * max(1.0, np.abs(td.os).max())
+    assert np.abs(td.rs - oprop.xtda_rot_str(p, td.e, x_rows, ipo, rxp)).max() < 1e-9 * max(1.0, np.abs(td.rs).max())
+    c = p.mo_coeff[0]
+    ints_mo = np.einsum("xpq,pi,qj->xij", dip, c, c)
+    g = XSF_TDA_GPU(mf, X=3, collinear="alda0", nstates=4, extype=1)
+    g.kernel()
+    ref = oprop.osc_matrix(g.e, oprop.tdm_r(np.asarray(g.v), ints_mo, p.nc, p.no, p.nv, 3, olay.get_vect(p.no)))
+    assert g.os.shape == (4, 4) and np.abs(g.os - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())
+    x = XSF_TDA(mf, SA=2)
+    x.kernel(nstates=3, remove=False)
+    tdm, osc = x.calculate_TDM(verbose=False)
+    ref = oprop.tdm_r(np.asarray(x.v), ints_mo, p.nc, p.no, p.nv, 2, None)
+    assert np.abs(tdm - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())

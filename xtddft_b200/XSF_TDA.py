@@ -10,7 +10,7 @@ import numpy as np
 
 from . import plan as planmod
 from . import utils
-from .adapters import problem_from_mf
+from .adapters import one_electron_ints, problem_from_mf
 from .drivers_common import TimeCounter, make_engine, solve
 
 au2ev = utils.au2ev_xsf
@@ -71,3 +71,58 @@ class XSF_TDA:
 
     def deltaS2(self):
         return utils.delta_s2_sf_roks(self.v, self.nc, self.no, self.nv, self.vects if self.re else None)
+
+    # ---- property pass (XSF_TDA.py:429-592, 613-649, 729-790) on the device ---------------------------------
+    def _property_pass(self):
+        from .properties import PropertyPass
+        if getattr(self, "_pp", None) is None:
+            self._pp = PropertyPass(self.problem)
+        return self._pp
+
+    def calculate_TDM(self, verbose=True):
+        """Excited-state to excited-state transition dipoles and oscillator strengths; returns (tdm[3,n,n], osc[n,n]) and
+        prints the reference's table."""
+        dip = one_electron_ints(self.mf, self.problem, "int1e_r")
+        if dip is None:
+            raise ValueError("calculate_TDM needs the dipole integrals (a PySCF molecule, or problem.meta['one_electron'])")
+        pp = self._property_pass()
+        rows = np.ascontiguousarray(np.asarray(self.v).T)
+        if self.type_u:
+            tdm = pp.tdm_u(rows, dip, planmod.LAYOUT_BLOCK)
+        else:
+            tdm = pp.tdm_r(rows, dip, self.SA, planmod.LAYOUT_BLOCK, bool(self.re))
+        osc = pp.osc_matrix(self.e, tdm)
+        if verbose:
+            print("Excited state to Excited state transition dipole moments(Au)")
+            print("State State    X     Y     Z     OSC.")
+            for i in range(len(self.e)):
+                for j in range(len(self.e)):
+                    print(f"{i+1:2d} {j+1:2d} {tdm[0, i, j]:>8.4f} {tdm[1, i, j]:>8.4f} {tdm[2, i, j]:>8.4f}  {osc[i, j]:>8.4f} ")
+        return tdm, osc
+
+    def calculate_TDM_R(self, verbose=True):
+        assert not self.type_u
+        return self.calculate_TDM(verbose)
+
+    def calculate_TDM_U(self, verbose=True):
+        assert self.type_u, "Must be UHF/UKS reference !!!"
+        return self.calculate_TDM(verbose)
+
+    def deltaS2_U(self, nstate=None):
+        """P_ab of XSF_TDA.py:613-649 for state `nstate` (all states if None); D<S^2> = P_ab - no + 1."""
+        ovlp = one_electron_ints(self.mf, self.problem, "int1e_ovlp")
+        if ovlp is None:
+            ovlp = np.eye(self.nao)
+        rows = np.ascontiguousarray(np.asarray(self.v).T)
+        pab = self._property_pass().delta_s2_u(rows, ovlp, planmod.LAYOUT_BLOCK) + self.no - 1
+        return pab if nstate is None else pab[nstate]
+
+    def analyse(self):
+        """D<S^2> labels of XSF_TDA.py:771-787 (symmetry labels need PySCF's symm module and are reported as 'A')."""
+        if self.SA == 0 and not self.type_u:
+            ds = list(self.deltaS2())
+        elif self.type_u:
+            ds = list(self.deltaS2_U() - self.no + 1)
+        else:
+            ds = []
+        return ds, ["A"] * self.nstates

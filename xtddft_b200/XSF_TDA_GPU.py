@@ -8,7 +8,7 @@ import numpy as np
 
 from . import plan as planmod
 from . import utils
-from .adapters import problem_from_mf
+from .adapters import one_electron_ints, problem_from_mf
 from .drivers_common import TimeCounter, make_engine, solve
 
 
@@ -76,5 +76,31 @@ class XSF_TDA_GPU:
         over = dict(tol_residual=self.conv_tol, lindep=self.lindep, max_cycle=self.max_cycle)
         self.converged, self.e, self.v, self.Davidcyc, _ = solve(eng, self.nstates, "gpu_class", x0=self.init_guess(), tc=self.tc, **over)
         self.v = self.deal_v_davidson()
-        self.os = None      # needs dipole integrals
+        self.os = self.osc_str()      # state-to-state oscillator matrix; None without dipole integrals
         return self.e * utils.ha2eV, self.v
+
+    # ---- property pass (XSF_TDA_GPU.py:936-1116) on the device ------------------------------------------
+    def _tdm(self):
+        from .properties import PropertyPass
+        dip = one_electron_ints(self.mf, self.problem, "int1e_r")
+        if dip is None or self.extype == 0:
+            return None
+        pp = PropertyPass(self.problem)
+        rows = np.ascontiguousarray(np.asarray(self.v).T)
+        if self.problem.restricted:
+            return pp.tdm_r(rows, dip, self.X, planmod.LAYOUT_BLOCK, bool(self.re))
+        return pp.tdm_u(rows, dip, planmod.LAYOUT_BLOCK)
+
+    def calculate_TDM_R(self):
+        assert self.problem.restricted, "Must be ROHF/ROKS reference !!!"
+        return self.osc_str()
+
+    def calculate_TDM_U(self):
+        assert not self.problem.restricted, "Must be UHF/UKS reference !!!"
+        return self.osc_str()
+
+    def osc_str(self):
+        from .properties import PropertyPass
+        tdm = self._tdm()
+        self.tdm = tdm
+        return None if tdm is None else PropertyPass.osc_matrix(self.e, tdm)

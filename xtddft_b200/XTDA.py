@@ -2,9 +2,9 @@
 
 Same constructor, `kernel()` / `Davidson()` entry points, options and result attributes as the reference classes
 `XTDA` in xtddft/XTDA.py:21-54,694-829 (CPU) and xtddft/XTDA_GPU.py:24-53,368-500 (GPU); the sigma build
-`vind` (XTDA.py:615-690) runs in libxtdsigma.so.  Post-processing that needs one-electron integrals (oscillator /
-rotatory strengths) and the dense debug paths (`full_diag`, `X_TDA` tensor basis) are outside the hot path
-and raise NotImplementedError.
+`vind` (XTDA.py:615-690) runs in libxtdsigma.so, and so does the property pass after the solve (oscillator and
+rotatory strengths, XTDA.py:838-890 -> xtddft_b200/properties.py).  The dense debug paths (`full_diag`, `X_TDA` tensor
+basis) are outside the hot path and raise NotImplementedError.
 """
 from __future__ import annotations
 
@@ -12,7 +12,7 @@ import numpy as np
 
 from . import plan as planmod
 from . import utils
-from .adapters import problem_from_mf
+from .adapters import is_chiral, one_electron_ints, problem_from_mf
 from .drivers_common import TimeCounter, make_engine, solve
 
 
@@ -86,8 +86,9 @@ class XTDA:
         self.xyco_b = self.v.T[:, nocca * nvira:nocca * nvira + noccb * no]
         self.xycv_b = self.v.T[:, nocca * nvira + noccb * no:]
         self.dS2 = self.deltaS2()
-        self.os = None          # oscillator / rotatory strengths need dipole integrals
-        self.rs = None
+        self._x_rows = np.ascontiguousarray(x1.T)          # PySCF-order amplitude rows for the property pass
+        self.os = self.osc_str()                           # None when no dipole integrals are available
+        self.rs = self.rot_str() if is_chiral(self.mf, p) else np.zeros(self.nstates)     # XTDA.py:818-821
         if self.so2st:
             self.v = utils.so2st(self.v, nc, no, nv)
         return self.e
@@ -96,6 +97,27 @@ class XTDA:
         """XTDA.py:831-836: |X_cv(aa) - X_cv(bb)|^2."""
         d = self.xycv_a - self.xycv_b
         return np.einsum("ij,ij->i", d, d)
+
+    def _property_pass(self):
+        from .properties import PropertyPass
+        if getattr(self, "_pp", None) is None:
+            self._pp = PropertyPass(self.problem)
+        return self._pp
+
+    def osc_str(self):
+        """Length-form oscillator strengths f = 2/3 w |<0|r|n>|^2 (XTDA.py:838-858), on the device."""
+        dip = one_electron_ints(self.mf, self.problem, "int1e_r")
+        if dip is None:
+            return None
+        return self._property_pass().xtda_osc_str(self.e[:self.nstates], self._x_rows, dip)
+
+    def rot_str(self):
+        """Rotatory strengths in cgs units (XTDA.py:860-890), on the device."""
+        ipo = one_electron_ints(self.mf, self.problem, "int1e_ipovlp")
+        rxp = one_electron_ints(self.mf, self.problem, "int1e_cg_irxp")
+        if ipo is None or rxp is None:
+            return None
+        return self._property_pass().xtda_rot_str(self.e[:self.nstates], self._x_rows, ipo, rxp)
 
     def full_diag(self):
         raise NotImplementedError("full_diag is a dense O(dim^2) debug path, outside the sigma hot path")

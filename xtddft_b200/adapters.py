@@ -52,6 +52,36 @@ class _SynthMol:
         return self._nao
 
 
+def one_electron_ints(mf, problem: ProblemData, name: str):
+    """One-electron AO integrals the property pass needs (`int1e_r`, `int1e_ipovlp`, `int1e_cg_irxp`, `int1e_ovlp`):
+    from `problem.meta["one_electron"][name]` when the caller supplied them (synthetic inputs), else from libcint through
+    the PySCF molecule with the reference's own calls (XTDA.py:847,869,872; XSF_TDA_GPU.py:956,1001; XSF_TDA.py:628).
+    Returns None when neither source exists (the strengths are then left as None)."""
+    given = problem.meta.get("one_electron") if isinstance(problem.meta, dict) else None
+    if given is not None and name in given:
+        return np.asarray(given[name], dtype=np.float64)
+    mol = getattr(mf, "mol", None)
+    if mol is None or not hasattr(mol, "intor"):
+        return None
+    if name == "int1e_r":                                  # pragma: no cover  (needs PySCF)
+        return np.asarray(mol.intor_symmetric("int1e_r", comp=3))
+    if name == "int1e_ovlp":                               # pragma: no cover
+        return np.asarray(mf.get_ovlp())
+    return np.asarray(mol.intor(name, comp=3, hermi=2))    # pragma: no cover
+
+
+def is_chiral(mf, problem: ProblemData) -> bool:
+    """XTDA.py:818-821 computes rotatory strengths only for chiral molecules (`gto.mole.chiral_mol`)."""
+    flag = problem.meta.get("chiral") if isinstance(problem.meta, dict) else None
+    if flag is not None:
+        return bool(flag)
+    try:                                                   # pragma: no cover  (needs PySCF)
+        from pyscf import gto
+        return bool(gto.mole.chiral_mol(mf.mol))
+    except Exception:
+        return False
+
+
 def problem_from_mf(mf, **kw) -> ProblemData:
     if isinstance(mf, ProblemData):
         return mf
