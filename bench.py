@@ -364,10 +364,19 @@ def main():
         nve = 1 if dp.fxc_kind == "alda0" else dp.nvar
         n_fxc = {"alda0": 1, "mcol": dp.nvar ** 2, "uks": (2 * dp.nvar) ** 2}[dp.fxc_kind]
         occ_cols = sum(ch.no for ch in eng.plan.channels)
-        # per grid point: Y read + A written in place (nve components x nvec x no), phi read once, kernel row read once
-        xc_bytes = 8.0 * ng_loc * (2 * nve * nvec * occ_cols + nve * occ_cols + n_fxc)
+        split_form = bool(_lib.check(eng.lib.xtd_xc_split_form(eng._h, nvec), "xtd_xc_split_form"))
+        if split_form:
+            # per grid point: Y0 read + A written (nvec x no), T read + B written (nvec x nv), 4 occupied and 3 virtual
+            # gradient components of the MO values read once, kernel row read once
+            vir_cols = sum(ch.nv for ch in eng.plan.channels)
+            xc_bytes = 8.0 * ng_loc * (2 * nvec * (occ_cols + vir_cols) + 4 * occ_cols + 3 * vir_cols + n_fxc)
+            xc_kernel = "xc_weight_split_kernel (split-gradient form: CTA per grid point, warp per trial vector, MO values staged in smem)"
+        else:
+            # per grid point: Y read + A written in place (nve components x nvec x no), phi read once, kernel row read once
+            xc_bytes = 8.0 * ng_loc * (2 * nve * nvec * occ_cols + nve * occ_cols + n_fxc)
+            xc_kernel = "xc_weight_kernel (rho1 on the grid, f_xc weighting, A buffers in place)"
         hbm_peak = HBM_PEAK_GBS
-        roof_xc = {"bound": "hbm", "kernel": "xc_weight_kernel (rho1 on the grid, f_xc weighting, A buffers in place)",
+        roof_xc = {"bound": "hbm", "kernel": xc_kernel,
                    "achieved": xc_bytes / (xs_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                    "frac": xc_bytes / (xs_ms * 1e-3) / 1e9 / hbm_peak,
                    "traffic": _ncu_traffic(dp.name, "xc_stream") if world == 1 and args.scale == 1.0 else None, "bytes_per_step": xc_bytes,

@@ -108,6 +108,9 @@ int xtd_sigma_host(xtd_handle h, int nvec, const double* z_host, double* hz_host
 
 int xtd_get_stats(xtd_handle h, xtd_stats* out);
 int xtd_reset_stats(xtd_handle h);
+/* which GEMM arrangement the grid path uses for nvec vectors: 1 = split-gradient form (value GEMM on either side of the
+ * orbital product, gradient halves streamed), 0 = one GEMM per AO component.  Used by the bench to count streamed bytes. */
+int xtd_xc_split_form(xtd_handle h, int nvec);
 
 /* Davidson subspace algebra on device vectors (Davidson.py:152-271): all row vectors of length n */
 int xtd_vec_dots(void* stream, double* g_dev, int ldg, const double* a_dev, long lda, int m, const double* b_dev, long ldb, int k, long n);

@@ -167,3 +167,22 @@ def test_empty_shards(torch_cuda):
             ref = vind(z.cpu().numpy())
             assert np.abs(out.cpu().numpy() - ref).max() < RTOL * max(1.0, np.abs(ref).max())
         eng.close()
+
+
+@pytest.mark.parametrize("split", ["1", "0"])
+@pytest.mark.parametrize("nc,no,nv", [(5, 1, 15), (6, 2, 17), (130, 3, 140)])
+def test_gga_split_gradient_form(torch_cuda, monkeypatch, split, nc, no, nv):
+    """Value + gradient kernels in both GEMM arrangements (XTD_XC_SPLIT forces one): four components on the virtual side,
+    or value on the virtual side + value on the occupied side with the gradient halves streamed (run_xc).  UKS kernel on
+    two channels (X-TDA) and the multicollinear kernel on one (spin flip); odd / even orbital counts, > 1 tile."""
+    monkeypatch.setenv("XTD_XC_SPLIT", split)
+    p = make_problem(nc + no + nv, nc, no, nv, 7, 300, xctype="GGA", hyb=0.2, seed=190 + no)
+    vind, hd = osig.xtda_gen_vind(p)
+    eng = _engine(planmod.build_xtda_plan(p), p, max_nvec=8)
+    _check(torch_cuda, eng, vind, hd.size, nvec=3)
+    _check(torch_cuda, eng, vind, hd.size, nvec=1, seed=5)
+    eng.close()
+    vind, hd = osig.sf_gen_vind(p, -1, 1)
+    eng = _engine(planmod.build_sf_plan(p, isf=-1, method=1), p, max_nvec=8)
+    _check(torch_cuda, eng, vind, hd.size, nvec=4)
+    eng.close()

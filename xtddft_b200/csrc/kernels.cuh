@@ -292,6 +292,157 @@ __global__ void __launch_bounds__(256) xc_weight_kernel(const XcArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Value + gradient kernels with two GEMMs per direction instead of four ("split gradient" form):
+//   Y0[g,x,o] = sum_v phiv_0[g,v] z[x,o,v]      T[g,x,v] = sum_o phi_0[g,o] z[x,o,v]          (the two forward GEMMs)
+//   rho_0 = sum_o Y0 phi_0      rho_k = sum_o Y0 phi_k + sum_v T phiv_k                        (k = x, y, z)
+//   wv = f_xc . rho
+//   A[g,x,o] = wv_0 phi_0 + sum_k wv_k phi_k   (over Y0)       B[g,x,v] = sum_k wv_k phiv_k    (over T)
+//   sigma[x,o,v] += sum_g A[g,x,o] phiv_0[g,v] + sum_g phi_0[g,o] B[g,x,v]                     (the two backward GEMMs)
+// The gradient of the orbital product is split as (grad phi_o) phi_v + phi_o (grad phi_v); the second half is carried
+// by the virtual-side buffers T / B, which this kernel streams once (read T, write B in place).  One warp per grid
+// point, lanes over the orbital index, XU trial vectors in flight.
+// ------------------------------------------------------------------------------------------------------
+struct XcArgs2 {
+  int nch, nvec, gb;
+  long g0;
+  double* Y[2];            // [gb][ldY]          Y0 in, A out
+  long ldY[2];
+  double* T[2];            // [nvec][gb][ldT]    T in, B out
+  long ldT[2];
+  const double* phi[2];    // [4][ng][ldphi]
+  long ldphi[2], phi_comp[2];
+  const double* phiv[2];   // [4][ng][ldphiv]
+  long ldphiv[2], phiv_comp[2];
+  int no[2], nv[2];
+  const double* wf;        // UKS [ng][64] (weighted), MCOL [ng][16] (2 w f)
+};
+
+// One CTA per grid point, one warp per trial vector: the orbital values of the point (4 occupied components, 3 virtual
+// gradient components per channel) are staged in shared memory once and shared by all vectors, so every byte of Y0 / T
+// and of the MO values is read from HBM exactly once.
+__host__ __device__ inline long xc_split_smem_doubles(int nch, const int* no, const int* nv) {
+  long n = 0;
+  for (int s = 0; s < nch; ++s) n += 4L * ((no[s] + 1) & ~1) + 3L * ((nv[s] + 1) & ~1);
+  return n;
+}
+
+template <int KIND, int W>
+__global__ void __launch_bounds__(512, 2) xc_weight_split_kernel(const XcArgs2 a) {
+  constexpr int NVAR = 4;
+  constexpr int NCH = (KIND == XC_KIND_UKS) ? 2 : 1;
+  constexpr int NR = NCH * NVAR;
+  extern __shared__ __align__(16) double xc_sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const long g = blockIdx.x;
+  // ---- stage the MO values of this point ----------------------------------------------------------------
+  double* sphi[NCH];
+  double* sphiv[NCH];
+  int nop[NCH], nvp[NCH];
+  {
+    double* cur = xc_sm;
+#pragma unroll
+    for (int s = 0; s < NCH; ++s) {
+      nop[s] = (a.no[s] + 1) & ~1;
+      nvp[s] = (a.nv[s] + 1) & ~1;
+      sphi[s] = cur; cur += 4 * nop[s];
+      sphiv[s] = cur; cur += 3 * nvp[s];
+      const double* p = a.phi[s] + (a.g0 + g) * a.ldphi[s];
+      const double* pv = a.phiv[s] + (a.g0 + g) * a.ldphiv[s];
+      for (int i = threadIdx.x; i < 4 * nop[s]; i += blockDim.x) {
+        const int k = i / nop[s], o = i - k * nop[s];
+        sphi[s][i] = o < a.no[s] ? p[k * a.phi_comp[s] + o] : 0.0;
+      }
+      for (int i = threadIdx.x; i < 3 * nvp[s]; i += blockDim.x) {
+        const int k = i / nvp[s], v = i - k * nvp[s];
+        sphiv[s][i] = v < a.nv[s] ? pv[(k + 1) * a.phiv_comp[s] + v] : 0.0;
+      }
+    }
+  }
+  double fk[(KIND == XC_KIND_UKS) ? NR : NVAR];
+  if (KIND == XC_KIND_UKS) {
+    const double* row = a.wf + (a.g0 + g) * (long)(NR * NR);
+#pragma unroll
+    for (int q = 0; q < NR; ++q) fk[q] = (lane < NR) ? row[lane * NR + q] : 0.0;
+  } else {
+    const double* row = a.wf + (a.g0 + g) * (long)(NVAR * NVAR);
+#pragma unroll
+    for (int q = 0; q < NVAR; ++q) fk[q] = (lane < NVAR) ? row[lane * NVAR + q] : 0.0;
+  }
+  __syncthreads();
+  for (int x = warp; x < a.nvec; x += nwarps) {
+    double rho[NR];
+#pragma unroll
+    for (int q = 0; q < NR; ++q) rho[q] = 0.0;
+#pragma unroll
+    for (int s = 0; s < NCH; ++s) {
+      const int no = a.no[s], nv = a.nv[s];
+      const double* yb = a.Y[s] + g * a.ldY[s] + (long)x * no;
+#pragma unroll 2
+      for (int o = lane * W; o < no; o += 32 * W) {
+        XcVec<W> y;
+        y.load(yb + o);
+#pragma unroll
+        for (int e = 0; e < W; ++e)
+#pragma unroll
+          for (int k = 0; k < NVAR; ++k) rho[s * NVAR + k] += y.v[e] * sphi[s][k * nop[s] + o + e];
+      }
+      const double* tb = a.T[s] + ((long)x * a.gb + g) * a.ldT[s];
+#pragma unroll 2
+      for (int v = lane * 2; v < nv; v += 64) {
+        XcVec<2> t;
+        t.load(tb + v);
+        const double t1 = (v + 1 < nv) ? t.v[1] : 0.0;       // past an odd nv the buffer holds no data
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double2 pv = *reinterpret_cast<const double2*>(sphiv[s] + k * nvp[s] + v);
+          rho[s * NVAR + 1 + k] += t.v[0] * pv.x + t1 * pv.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NR; ++q) rho[q] = warp_sum(rho[q]);
+    double wv[NR];
+    {
+      double mine = 0.0;
+      constexpr int NQ = (KIND == XC_KIND_UKS) ? NR : NVAR;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) mine += fk[q] * rho[q];
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) wv[q] = __shfl_sync(0xffffffffu, mine, q);
+    }
+#pragma unroll
+    for (int s = 0; s < NCH; ++s) {
+      const int no = a.no[s], nv = a.nv[s];
+      double* yb = a.Y[s] + g * a.ldY[s] + (long)x * no;
+#pragma unroll 2
+      for (int o = lane * W; o < no; o += 32 * W) {
+        XcVec<W> out;
+#pragma unroll
+        for (int e = 0; e < W; ++e) {
+          double acc = 0.0;
+#pragma unroll
+          for (int k = 0; k < NVAR; ++k) acc += wv[s * NVAR + k] * sphi[s][k * nop[s] + o + e];
+          out.v[e] = acc;
+        }
+        out.store(yb + o);
+      }
+      double* tb = a.T[s] + ((long)x * a.gb + g) * a.ldT[s];
+#pragma unroll 2
+      for (int v = lane * 2; v < nv; v += 64) {
+        double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double2 pv = *reinterpret_cast<const double2*>(sphiv[s] + k * nvp[s] + v);
+          acc.x += wv[s * NVAR + 1 + k] * pv.x;
+          acc.y += wv[s * NVAR + 1 + k] * pv.y;
+        }
+        *reinterpret_cast<double2*>(tb + v) = acc;           // the staged value past an odd nv is 0
+      }
+    }
+  }
+}
+
 // per-point kernel tables (once per solve)
 // UKS: wf[g][t*nvar+d][s*nvar+c] = w[g] * fxc[s,c,t,d,g]
 __global__ void build_wf_uks_kernel(double* __restrict__ wf, const double* __restrict__ fxc, const double* __restrict__ w, long ng,

@@ -784,16 +784,59 @@ static void launch_xc(const XcArgs& a, cudaStream_t s) {
   else xc_weight_kernel<NVAR, KIND, XU, 1><<<grid, 256, 0, s>>>(a);
 }
 
+constexpr long XC_SPLIT_SMEM_MAX = 200 * 1024;
+
+template <int KIND>
+static int launch_xc_split(const XcArgs2& a, cudaStream_t s) {
+  const bool even = (a.no[0] % 2 == 0) && (a.nch == 1 || a.no[1] % 2 == 0);
+  const size_t smem = (size_t)xc_split_smem_doubles(a.nch, a.no, a.nv) * 8;
+  // warps = trial vectors, in as few equal rounds as 16 warps allow
+  const int rounds = (int)cdiv(a.nvec, 16);
+  const int nwarps = (int)cdiv(a.nvec, rounds);
+  static bool attr_set = false;
+  if (!attr_set) {
+    XTD_CUDA(cudaFuncSetAttribute(xc_weight_split_kernel<XC_KIND_UKS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XC_SPLIT_SMEM_MAX));
+    XTD_CUDA(cudaFuncSetAttribute(xc_weight_split_kernel<XC_KIND_UKS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XC_SPLIT_SMEM_MAX));
+    XTD_CUDA(cudaFuncSetAttribute(xc_weight_split_kernel<XC_KIND_MCOL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XC_SPLIT_SMEM_MAX));
+    XTD_CUDA(cudaFuncSetAttribute(xc_weight_split_kernel<XC_KIND_MCOL, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XC_SPLIT_SMEM_MAX));
+    attr_set = true;
+  }
+  if (even) xc_weight_split_kernel<KIND, 2><<<(unsigned)a.gb, 32 * nwarps, smem, s>>>(a);
+  else xc_weight_split_kernel<KIND, 1><<<(unsigned)a.gb, 32 * nwarps, smem, s>>>(a);
+  return XTD_OK;
+}
+
+// Value + gradient kernels: GEMM work (in padded 128-row tiles x contraction length, per grid point) of the
+// four-component form against the split-gradient form; the latter halves it unless an orbital block barely exceeds
+// a tile or the problem is tiny.
+static bool xc_use_split(const xtd_engine* h, int nvec) {
+  if (h->nvar_eff != 4) return false;
+  {
+    int no[2] = {0, 0}, nv[2] = {0, 0};
+    for (size_t c = 0; c < h->ch.size(); ++c) { no[c] = h->ch[c]->no; nv[c] = h->ch[c]->nv; }
+    if (xc_split_smem_doubles((int)h->ch.size(), no, nv) * 8 > XC_SPLIT_SMEM_MAX) return false;   // MO values of a point must fit shared memory
+  }
+  if (const char* e = getenv("XTD_XC_SPLIT")) return atoi(e) != 0;
+  auto tile = [](long n) { return (double)(cdiv(n, 128) * 128); };
+  double four = 0.0, split = 0.0;
+  for (auto* c : h->ch) {
+    four += 8.0 * tile((long)nvec * c->no) * c->nv;
+    split += 2.0 * tile((long)nvec * c->no) * c->nv + (double)nvec * (tile(c->nv) * pad_ld(c->no) + tile(c->no) * c->nv);
+  }
+  return split < 0.9 * four;
+}
+
 static int run_xc(xtd_engine* h, int nvec) {
   cudaStream_t s = h->stream;
   const int nch = (int)h->ch.size();
   const int nve = h->nvar_eff;
-  // grid chunk: Y buffers for all channels must fit the scratch region
+  const bool split = xc_use_split(h, nvec);
+  // grid chunk: the per-point buffers of all channels must fit the scratch region
   size_t per_g = 0;
   long ldY[2] = {0, 0};
   for (int c = 0; c < nch; ++c) {
     ldY[c] = pad_ld((long)nvec * h->ch[c]->no);
-    per_g += (size_t)nve * ldY[c];
+    per_g += split ? (size_t)ldY[c] + (size_t)nvec * h->ch[c]->ldphiv : (size_t)nve * ldY[c];
   }
   long GB = (long)(h->scratch_doubles / per_g);
   GB = std::min<long>(GB, 1 << 16);
@@ -801,42 +844,74 @@ static int run_xc(xtd_engine* h, int nvec) {
   XTD_REQUIRE(GB >= 128, XTD_ERR_NOMEM, "workspace too small for a 128-point grid chunk");
   for (long g0 = 0; g0 < h->ng; g0 += GB) {
     const int gb = (int)std::min<long>(GB, h->ng - g0);
-    double* Y[2];
+    double *Y[2] = {nullptr, nullptr}, *T[2] = {nullptr, nullptr};
     double* cur = h->scratch;
     for (int c = 0; c < nch; ++c) {
       Y[c] = cur;
-      cur += (size_t)nve * gb * ldY[c];
+      cur += (size_t)(split ? 1 : nve) * gb * ldY[c];
+      if (split) {
+        T[c] = cur;
+        cur += (size_t)nvec * gb * h->ch[c]->ldphiv;
+      }
     }
     {
       PhaseTimer t(h, XTD_T_XC_GEMM);
       for (int c = 0; c < nch; ++c) {
         Channel* ch = h->ch[c];
-        // Y[cmp][g][(x,o)] = sum_v phiv[cmp][g0+g][v] Z[(x,o)][v]     (trial vectors evaluated on the grid, virtual side)
+        // Y[cmp][g][(x,o)] = sum_v phiv[cmp][g0+g][v] Z[(x,o)][v]     (trial vectors evaluated on the grid, virtual side;
+        // only the value component in the split-gradient form)
         GemmDesc d;
         d.A = view3d(ch->phiv.p, ch->ldphiv, h->ng * ch->ldphiv, nve, gb, ch->nv, (int)g0, 0);
         d.B = view2d(h->Z[c], ch->ldz, nvec * ch->no, ch->nv);
-        d.M = gb; d.N = nvec * ch->no; d.K = ch->nv; d.batches = nve; d.a_hi = 1; d.b_hi = 0;
+        d.M = gb; d.N = nvec * ch->no; d.K = ch->nv; d.batches = split ? 1 : nve; d.a_hi = 1; d.b_hi = 0;
         d.C = Y[c]; d.ldc = ldY[c]; d.c_batch_stride = (long)gb * ldY[c];
         XTD_TRY(gemm(h->gemm, d, s));
+        if (split) {
+          // T[x][g][v] = sum_o phi_0[g0+g][o] Z[x][o][v]              (occupied side)
+          GemmDesc e;
+          e.b_kc = false;
+          e.A = view2d(ch->phi.p, ch->ldphi, gb, ch->no, (int)g0, 0);
+          e.B = view3d(h->Z[c], ch->ldz, (long)ch->no * ch->ldz, nvec, ch->no, ch->nv);
+          e.M = gb; e.N = ch->nv; e.K = ch->no; e.batches = nvec; e.z_div = 1; e.a_hi = 0; e.b_hi = 1;
+          e.C = T[c]; e.ldc = ch->ldphiv; e.c_batch_stride = (long)gb * ch->ldphiv;
+          XTD_TRY(gemm(h->gemm, e, s));
+        }
       }
     }
     {
       PhaseTimer t(h, XTD_T_XC_STREAM);
-      XcArgs a;
-      a.nch = nch; a.nvec = nvec; a.gb = gb; a.g0 = g0;
-      for (int c = 0; c < nch; ++c) {
-        a.Y[c] = Y[c]; a.ldY[c] = ldY[c]; a.y_comp[c] = (long)gb * ldY[c];
-        a.phi[c] = h->ch[c]->phi.p; a.ldphi[c] = h->ch[c]->ldphi; a.phi_comp[c] = h->ng * h->ch[c]->ldphi;
-        a.no[c] = h->ch[c]->no;
-      }
-      if (nch == 1) { a.Y[1] = nullptr; a.phi[1] = nullptr; a.no[1] = 0; a.ldY[1] = a.y_comp[1] = a.ldphi[1] = a.phi_comp[1] = 0; }
-      a.wf = (h->fxc_kind == XTD_FXC_ALDA0) ? h->fxc : h->wf.p;
-      if (h->fxc_kind == XTD_FXC_UKS) {
-        if (nve == 1) launch_xc<1, XC_KIND_UKS>(a, s); else launch_xc<4, XC_KIND_UKS>(a, s);
-      } else if (h->fxc_kind == XTD_FXC_ALDA0) {
-        launch_xc<1, XC_KIND_ALDA0>(a, s);
+      if (split) {
+        XcArgs2 a;
+        a.nch = nch; a.nvec = nvec; a.gb = gb; a.g0 = g0;
+        for (int c = 0; c < 2; ++c) {
+          const bool on = c < nch;
+          Channel* ch = on ? h->ch[c] : nullptr;
+          a.Y[c] = on ? Y[c] : nullptr; a.ldY[c] = on ? ldY[c] : 0;
+          a.T[c] = on ? T[c] : nullptr; a.ldT[c] = on ? ch->ldphiv : 0;
+          a.phi[c] = on ? ch->phi.p : nullptr; a.ldphi[c] = on ? ch->ldphi : 0; a.phi_comp[c] = on ? h->ng * ch->ldphi : 0;
+          a.phiv[c] = on ? ch->phiv.p : nullptr; a.ldphiv[c] = on ? ch->ldphiv : 0; a.phiv_comp[c] = on ? h->ng * ch->ldphiv : 0;
+          a.no[c] = on ? ch->no : 0; a.nv[c] = on ? ch->nv : 0;
+        }
+        a.wf = h->wf.p;
+        if (h->fxc_kind == XTD_FXC_UKS) XTD_TRY(launch_xc_split<XC_KIND_UKS>(a, s));
+        else XTD_TRY(launch_xc_split<XC_KIND_MCOL>(a, s));
       } else {
-        if (nve == 1) launch_xc<1, XC_KIND_MCOL>(a, s); else launch_xc<4, XC_KIND_MCOL>(a, s);
+        XcArgs a;
+        a.nch = nch; a.nvec = nvec; a.gb = gb; a.g0 = g0;
+        for (int c = 0; c < nch; ++c) {
+          a.Y[c] = Y[c]; a.ldY[c] = ldY[c]; a.y_comp[c] = (long)gb * ldY[c];
+          a.phi[c] = h->ch[c]->phi.p; a.ldphi[c] = h->ch[c]->ldphi; a.phi_comp[c] = h->ng * h->ch[c]->ldphi;
+          a.no[c] = h->ch[c]->no;
+        }
+        if (nch == 1) { a.Y[1] = nullptr; a.phi[1] = nullptr; a.no[1] = 0; a.ldY[1] = a.y_comp[1] = a.ldphi[1] = a.phi_comp[1] = 0; }
+        a.wf = (h->fxc_kind == XTD_FXC_ALDA0) ? h->fxc : h->wf.p;
+        if (h->fxc_kind == XTD_FXC_UKS) {
+          if (nve == 1) launch_xc<1, XC_KIND_UKS>(a, s); else launch_xc<4, XC_KIND_UKS>(a, s);
+        } else if (h->fxc_kind == XTD_FXC_ALDA0) {
+          launch_xc<1, XC_KIND_ALDA0>(a, s);
+        } else {
+          if (nve == 1) launch_xc<1, XC_KIND_MCOL>(a, s); else launch_xc<4, XC_KIND_MCOL>(a, s);
+        }
       }
       LAUNCH_CHECK();
     }
@@ -847,11 +922,21 @@ static int run_xc(xtd_engine* h, int nvec) {
         // SIG[(x,o)][v] += sum_cmp sum_g A[cmp][g][(x,o)] phiv[cmp][g0+g][v]      (integration straight into the MO block)
         GemmDesc d;
         d.a_kc = false; d.b_kc = false;
-        d.A = view3d(Y[c], ldY[c], (long)gb * ldY[c], nve, gb, nvec * ch->no);
+        d.A = view3d(Y[c], ldY[c], (long)gb * ldY[c], split ? 1 : nve, gb, nvec * ch->no);
         d.B = view3d(ch->phiv.p, ch->ldphiv, h->ng * ch->ldphiv, nve, gb, ch->nv, (int)g0, 0);
-        d.M = nvec * ch->no; d.N = ch->nv; d.K = gb; d.nouter = nve;
+        d.M = nvec * ch->no; d.N = ch->nv; d.K = gb; d.nouter = split ? 1 : nve;
         d.C = h->SIG + h->sig_base[c]; d.ldc = ch->ldz; d.accumulate = true;
         XTD_TRY(gemm(h->gemm, d, s));
+        if (split) {
+          // SIG[x][o][v] += sum_g phi_0[g0+g][o] B[x][g][v]
+          GemmDesc e;
+          e.a_kc = false; e.b_kc = false;
+          e.A = view2d(ch->phi.p, ch->ldphi, gb, ch->no, (int)g0, 0);
+          e.B = view3d(T[c], ch->ldphiv, (long)gb * ch->ldphiv, nvec, gb, ch->nv);
+          e.M = ch->no; e.N = ch->nv; e.K = gb; e.batches = nvec; e.z_div = 1; e.a_hi = 0; e.b_hi = 1;
+          e.C = h->SIG + h->sig_base[c]; e.ldc = ch->ldz; e.c_batch_stride = (long)ch->no * ch->ldz; e.accumulate = true;
+          XTD_TRY(gemm(h->gemm, e, s));
+        }
       }
     }
   }
@@ -1139,6 +1224,12 @@ int xtd_get_stats(xtd_handle h, xtd_stats* out) {
   if (cudaEventElapsedTime(&tot, h->ev_total[0], h->ev_total[1]) == cudaSuccess) out->ms[XTD_T_TOTAL] = tot;
   else cudaGetLastError();
   return XTD_OK;
+}
+
+int xtd_xc_split_form(xtd_handle h, int nvec) {
+  XTD_REQUIRE(h && h->finalized && nvec >= 1, XTD_ERR_STATE, "xtd_xc_split_form: finalize first");
+  if (h->fxc_kind == XTD_FXC_NONE || h->ng == 0) return 0;
+  return xc_use_split(h, nvec) ? 1 : 0;
 }
 
 int xtd_reset_stats(xtd_handle h) {
