@@ -186,3 +186,22 @@ def test_gga_split_gradient_form(torch_cuda, monkeypatch, split, nc, no, nv):
     eng = _engine(planmod.build_sf_plan(p, isf=-1, method=1), p, max_nvec=8)
     _check(torch_cuda, eng, vind, hd.size, nvec=4)
     eng.close()
+
+
+@pytest.mark.parametrize("narrow", ["on", "off"])
+@pytest.mark.parametrize("nc,no,nv", [(131, 3, 150), (40, 4, 33), (7, 2, 260)])
+def test_xsf_narrow_open_block(torch_cuda, monkeypatch, narrow, nc, no, nv):
+    """Block-weighted exchange of the XSF Delta A with the open-shell output columns taken by the narrow-output pass
+    (contract with the few open rows of Lvv first) or by the general pass (XTD_NO_NARROW); > 1 tile of closed orbitals,
+    odd / even open-shell counts, removed OO vector."""
+    if narrow == "off":
+        monkeypatch.setenv("XTD_NO_NARROW", "1")
+    p = make_problem(nc + no + nv, nc, no, nv, 9, 200, xctype="LDA", hyb=0.3, seed=210 + no)
+    for sa, remove in [(3, True), (2, False)]:
+        vind, hd = osig.xsf_gen_vind(p, sa=sa, method=0, remove=remove, foo=0.8, fglobal=0.7)
+        pl = planmod.build_sf_plan(p, isf=-1, method=0, sa=sa, layout=planmod.LAYOUT_BLOCK, remove=remove, foo=0.8, fglobal=0.7,
+                                   hdiag_kind="xsf")
+        eng = _engine(pl, p)
+        _check(torch_cuda, eng, vind, hd.size, nvec=3)
+        _check(torch_cuda, eng, vind, hd.size, nvec=1, seed=3)
+        eng.close()
