@@ -125,6 +125,9 @@ int xtd_vec_scale(void* stream, double* x_dev, long ld, const double* s_dev, int
 /* plain GEMM entry (tests / benchmarks of the DMMA kernel): C[M,N] = alpha * A[M,K] * B[N,K]^T */
 int xtd_dgemm_tn(void* stream, int m, int n, int k, double alpha, const double* a_dev, long lda, const double* b_dev, long ldb,
                  double* c_dev, long ldc, int accumulate);
+/* general form: A is [M,K] row-major when a_kc != 0, else [K,M]; B is [N,K] when b_kc != 0, else [K,N] */
+int xtd_dgemm(void* stream, int m, int n, int k, double alpha, const double* a_dev, long lda, int a_kc, const double* b_dev, long ldb,
+              int b_kc, double* c_dev, long ldc, int accumulate);
 unsigned long long xtd_launch_count(void);
 
 #ifdef __cplusplus

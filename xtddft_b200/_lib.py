@@ -62,6 +62,7 @@ SIGNATURES = {
     "xtd_vec_precond": (_I, [_P, _P, _L, _P, _P, _P, _I, _L]),
     "xtd_vec_scale": (_I, [_P, _P, _L, _P, _I, _L]),
     "xtd_dgemm_tn": (_I, [_P, _I, _I, _I, _D, _P, _L, _P, _L, _P, _L, _I]),
+    "xtd_dgemm": (_I, [_P, _I, _I, _I, _D, _P, _L, _I, _P, _L, _I, _P, _L, _I]),
     "xtd_launch_count": (C.c_ulonglong, []),
 }
 

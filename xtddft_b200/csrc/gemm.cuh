@@ -67,6 +67,7 @@ struct GemmKernelParams {
   int accumulate;
   int c_row_div;
   long c_row_hi, c_row_lo;
+  int m_tail_cfg, n_tail_cfg;      // warp layout of the last (partial) tile row / column: 0 = the main 128 x 128 layout
 };
 
 __host__ __device__ __forceinline__ long c_row_offset(int m, long ldc, int div, long hi, long lo) {
@@ -137,8 +138,77 @@ __device__ __forceinline__ uint32_t frag_off(int r, int k) {
 // ------------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------------
-template <bool A_KC, bool B_KC>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+// IT x JT DMMA tiles per warp (warp tile 8 IT x 8 JT), WM warps along M and 8 / WM along N.  The main layout <8, 4, 2>
+// covers the 128 x 128 CTA tile; the others cover a partial last tile with all eight warps instead of leaving most of them
+// multiplying zero padding:  <4,4,4> 128 x 64 and <2,4,8> 128 x 32 for a short N tail,  <8,2,1> 64 x 128 and <2,2,1> 16 x 128
+// for a short M tail.  TMA still fetches full boxes (rows past the view are zero-filled, no traffic); the CTAs of partial
+// tiles sit in the same grid as the full ones and fill the gaps of the last wave.
+template <bool A_KC, bool B_KC, int IT, int JT, int WM>
+__device__ __forceinline__ void dmma_consume(const GemmKernelParams& p, uint8_t* smem, uint64_t* full, uint64_t* empty, int warp, int lane,
+                                             int tile_m, int tile_n, int zb, int sp, long it0, long it1) {
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = (warp % WM) * (8 * IT), wn = (warp / WM) * (8 * JT);
+  double acc[IT][JT][2];
+#pragma unroll
+  for (int i = 0; i < IT; ++i)
+#pragma unroll
+    for (int j = 0; j < JT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const uint32_t smem_base = smem_u32(smem);
+  for (long it = it0; it < it1; ++it) {
+    const long rel = it - it0;
+    const int s = (int)(rel % STAGES);
+    const uint32_t ph = (uint32_t)((rel / STAGES) & 1);
+    mbar_wait(&full[s], ph);
+    const uint32_t sa = smem_base + s * STAGE_BYTES;
+    const uint32_t sb = sa + TILE_BYTES_A;
+#pragma unroll
+    for (int kk = 0; kk < BK / 4; ++kk) {
+      double a[IT], b[JT];
+#pragma unroll
+      for (int i = 0; i < IT; ++i) a[i] = lds_f64(sa + frag_off<A_KC>(wm + i * 8 + g, kk * 4 + t));
+#pragma unroll
+      for (int j = 0; j < JT; ++j) b[j] = lds_f64(sb + frag_off<B_KC>(wn + j * 8 + g, kk * 4 + t));
+#pragma unroll
+      for (int i = 0; i < IT; ++i)
+#pragma unroll
+        for (int j = 0; j < JT; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+
+  // ===================== epilogue: registers -> global (16-byte stores) =====================
+  double* C = p.C + (long)zb * p.c_batch_stride + (long)sp * p.c_split_stride;
+  const int m_base = tile_m * BM + wm, n_base = tile_n * BN + wn;
+#pragma unroll
+  for (int i = 0; i < IT; ++i) {
+    const int m = m_base + i * 8 + g;
+    if (m >= p.M) continue;
+    double* crow = C + c_row_offset(m, p.ldc, p.c_row_div, p.c_row_hi, p.c_row_lo);
+#pragma unroll
+    for (int j = 0; j < JT; ++j) {
+      const int n = n_base + j * 8 + 2 * t;
+      if (n >= p.N) continue;
+      double v0 = p.alpha * acc[i][j][0], v1 = p.alpha * acc[i][j][1];
+      if (n + 1 < p.N) {
+        double2* dst = reinterpret_cast<double2*>(crow + n);
+        if (p.accumulate) {
+          double2 old = *dst;
+          v0 += old.x;
+          v1 += old.y;
+        }
+        *dst = make_double2(v0, v1);
+      } else {
+        if (p.accumulate) v0 += crow[n];
+        crow[n] = v0;
+      }
+    }
+  }
+}
+
+template <bool A_KC, bool B_KC, bool TAILS>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)   // 9 warps are allocated as 12 (granularity 4): 168 registers per thread
 dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const GemmKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -198,66 +268,18 @@ dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     return;
   }
 
-  // ===================== DMMA consumers: warp tile 64 (m) x 32 (n) =====================
-  const int g = lane >> 2, t = lane & 3;
-  const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;
-  double acc[8][4][2];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-  const uint32_t smem_base = smem_u32(smem);
-  for (long it = it0; it < it1; ++it) {
-    const long rel = it - it0;
-    const int s = (int)(rel % STAGES);
-    const uint32_t ph = (uint32_t)((rel / STAGES) & 1);
-    mbar_wait(&full[s], ph);
-    const uint32_t sa = smem_base + s * STAGE_BYTES;
-    const uint32_t sb = sa + TILE_BYTES_A;
-#pragma unroll
-    for (int kk = 0; kk < BK / 4; ++kk) {
-      double a[8], b[4];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) a[i] = lds_f64(sa + frag_off<A_KC>(wm + i * 8 + g, kk * 4 + t));
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = lds_f64(sb + frag_off<B_KC>(wn + j * 8 + g, kk * 4 + t));
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);
+  // ===================== DMMA consumers: warp layout by tile position =====================
+  if (!TAILS) {   // no short last tile in this launch: the main layout only
+    dmma_consume<A_KC, B_KC, 8, 4, 2>(p, smem, full, empty, warp, lane, tile_m, tile_n, zb, sp, it0, it1);
+    return;
   }
-
-  // ===================== epilogue: registers -> global (16-byte stores) =====================
-  double* C = p.C + (long)zb * p.c_batch_stride + (long)sp * p.c_split_stride;
-  const int m_base = tile_m * BM + wm, n_base = tile_n * BN + wn;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int m = m_base + i * 8 + g;
-    if (m >= p.M) continue;
-    double* crow = C + c_row_offset(m, p.ldc, p.c_row_div, p.c_row_hi, p.c_row_lo);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n_base + j * 8 + 2 * t;
-      if (n >= p.N) continue;
-      double v0 = p.alpha * acc[i][j][0], v1 = p.alpha * acc[i][j][1];
-      if (n + 1 < p.N) {
-        double2* dst = reinterpret_cast<double2*>(crow + n);
-        if (p.accumulate) {
-          double2 old = *dst;
-          v0 += old.x;
-          v1 += old.y;
-        }
-        *dst = make_double2(v0, v1);
-      } else {
-        if (p.accumulate) v0 += crow[n];
-        crow[n] = v0;
-      }
-    }
-  }
+  const int mcfg = (tile_m == (int)gridDim.x - 1) ? p.m_tail_cfg : 0;
+  const int ncfg = (tile_n == (int)gridDim.y - 1) ? p.n_tail_cfg : 0;
+  if (mcfg == 3) dmma_consume<A_KC, B_KC, 8, 2, 1>(p, smem, full, empty, warp, lane, tile_m, tile_n, zb, sp, it0, it1);
+  else if (mcfg == 4) dmma_consume<A_KC, B_KC, 2, 2, 1>(p, smem, full, empty, warp, lane, tile_m, tile_n, zb, sp, it0, it1);
+  else if (ncfg == 1) dmma_consume<A_KC, B_KC, 4, 4, 4>(p, smem, full, empty, warp, lane, tile_m, tile_n, zb, sp, it0, it1);
+  else if (ncfg == 2) dmma_consume<A_KC, B_KC, 2, 4, 8>(p, smem, full, empty, warp, lane, tile_m, tile_n, zb, sp, it0, it1);
+  else dmma_consume<A_KC, B_KC, 8, 4, 2>(p, smem, full, empty, warp, lane, tile_m, tile_n, zb, sp, it0, it1);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -324,6 +346,7 @@ struct GemmContext {
   double* split_ws = nullptr;  // workspace for split-K partials
   size_t split_ws_bytes = 0;
   bool attr_set = false;
+  bool tails = true;         // partial last tiles get their own warp layout (XTD_GEMM_TAILS=0 disables)
   // statistics
   double flops = 0.0;        // executed useful flops (2*M*N*K*nouter*batches)
   unsigned long long launches = 0;
@@ -342,13 +365,20 @@ inline int gemm_context_init(GemmContext& ctx) {
   XTD_CUDA(cudaDeviceGetAttribute(&ctx.num_sms, cudaDevAttrMultiProcessorCount, dev));
   const char* e = getenv("XTD_GEMM");
   ctx.naive = (e && e[0] == 'n');
-  if (!ctx.attr_set) {
-    XTD_CUDA(cudaFuncSetAttribute(dgemm_dmma_tma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-    XTD_CUDA(cudaFuncSetAttribute(dgemm_dmma_tma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-    XTD_CUDA(cudaFuncSetAttribute(dgemm_dmma_tma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-    XTD_CUDA(cudaFuncSetAttribute(dgemm_dmma_tma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-    ctx.attr_set = true;
+  ctx.tails = !(getenv("XTD_GEMM_TAILS") && getenv("XTD_GEMM_TAILS")[0] == '0');
+  return XTD_OK;
+}
+
+template <bool A_KC, bool B_KC, bool TAILS>
+inline int launch_kernel(dim3 grd, cudaStream_t stream, const CUtensorMap& ma, const CUtensorMap& mb, const GemmKernelParams& kp) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    XTD_CUDA(cudaFuncSetAttribute(dgemm_dmma_tma_kernel<A_KC, B_KC, TAILS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    attr_set = true;
   }
+  dgemm_dmma_tma_kernel<A_KC, B_KC, TAILS><<<grd, GEMM_THREADS, GEMM_SMEM, stream>>>(ma, mb, kp);
+  XTD_COUNT_LAUNCH();
+  XTD_CUDA(cudaGetLastError());
   return XTD_OK;
 }
 
@@ -401,6 +431,7 @@ inline int gemm(GemmContext& ctx, const GemmDesc& d, cudaStream_t stream) {
   p.C = d.C; p.ldc = d.ldc; p.c_batch_stride = d.c_batch_stride; p.c_split_stride = 0;
   p.alpha = d.alpha; p.accumulate = d.accumulate ? 1 : 0; p.splits = 1;
   p.c_row_div = d.c_row_div; p.c_row_hi = d.c_row_hi; p.c_row_lo = d.c_row_lo;
+  p.m_tail_cfg = 0; p.n_tail_cfg = 0;
   XTD_REQUIRE(d.c_row_div == 0 || (d.c_row_hi % 2 == 0 && d.c_row_lo % 2 == 0), XTD_ERR_ALIGN, "gemm: split row strides must be even");
   ctx.flops += 2.0 * d.M * d.N * (double)d.K * d.nouter * d.batches;
 
@@ -472,13 +503,23 @@ inline int gemm(GemmContext& ctx, const GemmDesc& d, cudaStream_t stream) {
   XTD_TRY(make_tensor_map(ctx, d.B, d.b_kc, &mb));
   XTD_REQUIRE(((uintptr_t)kp.C & 15) == 0 && kp.ldc % 2 == 0 && kp.c_batch_stride % 2 == 0, XTD_ERR_ALIGN,
               "gemm: C must be 16-byte aligned with even ldc");
-  dim3 grd(tm, tn, d.batches * splits);
-  if (d.a_kc && d.b_kc) dgemm_dmma_tma_kernel<true, true><<<grd, GEMM_THREADS, GEMM_SMEM, stream>>>(ma, mb, kp);
-  else if (d.a_kc && !d.b_kc) dgemm_dmma_tma_kernel<true, false><<<grd, GEMM_THREADS, GEMM_SMEM, stream>>>(ma, mb, kp);
-  else if (!d.a_kc && d.b_kc) dgemm_dmma_tma_kernel<false, true><<<grd, GEMM_THREADS, GEMM_SMEM, stream>>>(ma, mb, kp);
-  else dgemm_dmma_tma_kernel<false, false><<<grd, GEMM_THREADS, GEMM_SMEM, stream>>>(ma, mb, kp);
-  XTD_COUNT_LAUNCH(); ctx.launches++;
-  XTD_CUDA(cudaGetLastError());
+  // A short last tile in M or N (<= 64 of 128) gets a warp layout that covers only its live part (dmma_consume).
+  const int m_tail = d.M % BM, n_tail = d.N % BN;
+  if (ctx.tails && m_tail > 0 && m_tail <= 64) kp.m_tail_cfg = m_tail <= 16 ? 4 : 3;
+  if (ctx.tails && n_tail > 0 && n_tail <= 64) kp.n_tail_cfg = n_tail <= 32 ? 2 : 1;
+  const dim3 grd(tm, tn, (unsigned)(d.batches * splits));
+  const bool tails = kp.m_tail_cfg || kp.n_tail_cfg;
+#define XTD_LAUNCH(AK, BK_)                                                        \
+  do {                                                                             \
+    if (tails) XTD_TRY((launch_kernel<AK, BK_, true>(grd, stream, ma, mb, kp)));   \
+    else XTD_TRY((launch_kernel<AK, BK_, false>(grd, stream, ma, mb, kp)));        \
+  } while (0)
+  if (d.a_kc && d.b_kc) XTD_LAUNCH(true, true);
+  else if (d.a_kc && !d.b_kc) XTD_LAUNCH(true, false);
+  else if (!d.a_kc && d.b_kc) XTD_LAUNCH(false, true);
+  else XTD_LAUNCH(false, false);
+#undef XTD_LAUNCH
+  ctx.launches++;
   if (splits > 1) {
     long nblk = cdiv((long)d.M * d.N, 256);
     dim3 rg((unsigned)(nblk > 4096 ? 4096 : nblk), d.batches);

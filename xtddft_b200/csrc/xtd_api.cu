@@ -1325,8 +1325,8 @@ int xtd_vec_scale(void* stream, double* x, long ld, const double* sc, int k, lon
   return XTD_OK;
 }
 
-int xtd_dgemm_tn(void* stream, int m, int n, int k, double alpha, const double* a, long lda, const double* b, long ldb, double* c,
-                 long ldc, int accumulate) {
+int xtd_dgemm(void* stream, int m, int n, int k, double alpha, const double* a, long lda, int a_kc, const double* b, long ldb, int b_kc,
+              double* c, long ldc, int accumulate) {
   static GemmContext ctx;
   static double* ws = nullptr;
   if (!ctx.encode) {
@@ -1335,9 +1335,16 @@ int xtd_dgemm_tn(void* stream, int m, int n, int k, double alpha, const double* 
     ctx.split_ws = ws; ctx.split_ws_bytes = (size_t)256 << 20;
   }
   GemmDesc d;
-  d.A = view2d(a, lda, m, k); d.B = view2d(b, ldb, n, k);
+  d.a_kc = a_kc != 0; d.b_kc = b_kc != 0;
+  d.A = d.a_kc ? view2d(a, lda, m, k) : view2d(a, lda, k, m);
+  d.B = d.b_kc ? view2d(b, ldb, n, k) : view2d(b, ldb, k, n);
   d.M = m; d.N = n; d.K = k; d.C = c; d.ldc = ldc; d.alpha = alpha; d.accumulate = accumulate != 0;
   return gemm(ctx, d, (cudaStream_t)stream);
+}
+
+int xtd_dgemm_tn(void* stream, int m, int n, int k, double alpha, const double* a, long lda, const double* b, long ldb, double* c,
+                 long ldc, int accumulate) {
+  return xtd_dgemm(stream, m, n, k, alpha, a, lda, 1, b, ldb, 1, c, ldc, accumulate);
 }
 
 }  // extern "C"
