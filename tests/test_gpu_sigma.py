@@ -205,3 +205,16 @@ def test_xsf_narrow_open_block(torch_cuda, monkeypatch, narrow, nc, no, nv):
         _check(torch_cuda, eng, vind, hd.size, nvec=3)
         _check(torch_cuda, eng, vind, hd.size, nvec=1, seed=3)
         eng.close()
+
+
+@pytest.mark.parametrize("route", ["gemm", "stream"])
+def test_xtda_coulomb_routes(torch_cuda, monkeypatch, route):
+    """Full-width Coulomb blocks (X-TDA J[Da] + J[Db]) as two GEMMs over the flattened pair index, or with the streaming
+    kernels (XTD_J_STREAM); odd auxiliary count, 9 vectors."""
+    if route == "stream":
+        monkeypatch.setenv("XTD_J_STREAM", "1")
+    p = make_problem(150, 20, 2, 128, 37, 100, xctype="LDA", hyb=0.0, seed=220)
+    vind, hd = osig.xtda_gen_vind(p)
+    eng = _engine(planmod.build_xtda_plan(p), p, max_nvec=16)
+    _check(torch_cuda, eng, vind, hd.size, nvec=9)
+    eng.close()

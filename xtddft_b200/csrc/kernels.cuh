@@ -494,14 +494,14 @@ __global__ void __launch_bounds__(256) j_rho_kernel(double* __restrict__ R, long
 
 // Rm[x][t][P] = sum_s mix[t][s] R[x][s][P]
 __global__ void j_mix_kernel(double* __restrict__ Rm, const double* __restrict__ R, const double* __restrict__ mix, int njb, long naux,
-                             int nvec) {
+                             long ldr, int nvec) {
   const long P = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const int x = blockIdx.y;
   if (P >= naux || x >= nvec) return;
   for (int t = 0; t < njb; ++t) {
     double acc = 0.0;
-    for (int s = 0; s < njb; ++s) acc += mix[t * njb + s] * R[((long)x * njb + s) * naux + P];
-    Rm[((long)x * njb + t) * naux + P] = acc;
+    for (int s = 0; s < njb; ++s) acc += mix[t * njb + s] * R[((long)x * njb + s) * ldr + P];
+    Rm[((long)x * njb + t) * ldr + P] = acc;
   }
 }
 

@@ -769,8 +769,8 @@ static int setup_call_buffers(xtd_engine* h, int nvec) {
   }
   const size_t njb = h->jblocks.size();
   if (njb) {
-    h->jR = h->arena.take((size_t)nvec * njb * std::max<long>(h->naux[0], 1));
-    h->jRm = h->arena.take((size_t)nvec * njb * std::max<long>(h->naux[0], 1));
+    h->jR = h->arena.take((size_t)nvec * njb * (std::max<long>(h->naux[0], 1) + 1));
+    h->jRm = h->arena.take((size_t)nvec * njb * (std::max<long>(h->naux[0], 1) + 1));
     XTD_REQUIRE(h->jR && h->jRm, XTD_ERR_NOMEM, "workspace exhausted (Coulomb vectors)");
   }
   h->r1d = h->arena.take((size_t)nvec + 8);
@@ -1097,24 +1097,50 @@ static int run_j(xtd_engine* h, int nvec) {
   const long naux = h->naux[0];
   if (!njb || naux == 0) return XTD_OK;
   PhaseTimer t(h, XTD_T_J);
+  const long nap = naux + (naux & 1);        // per-block row of the aux-space vectors, even for the GEMM route
+  // A block that spans the full width of its channel is contiguous in (i, a) for every aux function and vector, so both
+  // Coulomb steps are plain GEMMs over the flattened pair index (the streaming kernels re-read all trial vectors from L2
+  // once per aux function); sub-blocks (XSF Delta A) keep the streaming kernels.
+  const bool no_gemm = getenv("XTD_J_STREAM") != nullptr;
+  auto flat = [&](const JBlockRec* j) { return !no_gemm && j->c0 == 0 && j->ld == h->ch[j->ch]->ldz; };
   for (int b = 0; b < njb; ++b) {
     JBlockRec* j = h->jblocks[b];
     Channel* ch = h->ch[j->ch];
-    // R[x][b][P] = <L_b[P], z block>
-    j_rho_kernel<8><<<(unsigned)naux, 256, 0, s>>>(h->jR + (long)b * naux, (long)njb * naux, j->L.p, j->ld, (long)j->nr * j->ld,
-                                                  h->Z[j->ch] + (long)j->r0 * ch->ldz + j->c0, ch->ldz, (long)ch->no * ch->ldz, j->nr, j->nc,
-                                                  nvec);
-    LAUNCH_CHECK();
+    if (flat(j)) {
+      // R[x][b][P] = sum_(i,a) Z[x][(r0+i, a)] L_b[P][(i, a)]
+      GemmDesc d;
+      d.A = view2d(h->Z[j->ch] + (long)j->r0 * ch->ldz, (long)ch->no * ch->ldz, nvec, (int)(j->nr * ch->ldz));
+      d.B = view2d(j->L.p, (long)j->nr * j->ld, (int)naux, (int)(j->nr * j->ld));
+      d.M = nvec; d.N = (int)naux; d.K = (int)(j->nr * ch->ldz);
+      d.C = h->jR + (long)b * nap; d.ldc = (long)njb * nap;
+      XTD_TRY(gemm(h->gemm, d, s));
+    } else {
+      j_rho_kernel<8><<<(unsigned)naux, 256, 0, s>>>(h->jR + (long)b * nap, (long)njb * nap, j->L.p, j->ld, (long)j->nr * j->ld,
+                                                    h->Z[j->ch] + (long)j->r0 * ch->ldz + j->c0, ch->ldz, (long)ch->no * ch->ldz, j->nr, j->nc,
+                                                    nvec);
+      LAUNCH_CHECK();
+    }
   }
-  j_mix_kernel<<<dim3((unsigned)cdiv(naux, 128), nvec), 128, 0, s>>>(h->jRm, h->jR, h->jmix_dev.p, njb, naux, nvec);
+  j_mix_kernel<<<dim3((unsigned)cdiv(naux, 128), nvec), 128, 0, s>>>(h->jRm, h->jR, h->jmix_dev.p, njb, naux, nap, nvec);
   LAUNCH_CHECK();
   for (int b = 0; b < njb; ++b) {
     JBlockRec* j = h->jblocks[b];
     Channel* ch = h->ch[j->ch];
-    j_apply_kernel<8><<<dim3((unsigned)cdiv((long)j->nr * j->nc, 256), (unsigned)cdiv(nvec, 8)), 256, 0, s>>>(
-        h->SIG + h->sig_base[j->ch] + (long)j->r0 * ch->ldz + j->c0, ch->ldz, (long)ch->no * ch->ldz, j->L.p, j->ld, (long)j->nr * j->ld,
-        h->jRm + (long)b * naux, (long)njb * naux, naux, j->nr, j->nc, nvec);
-    LAUNCH_CHECK();
+    if (flat(j)) {
+      // SIG[x][(r0+i, a)] += sum_P Rm[x][b][P] L_b[P][(i, a)]
+      GemmDesc d;
+      d.b_kc = false;
+      d.A = view2d(h->jRm + (long)b * nap, (long)njb * nap, nvec, (int)naux);
+      d.B = view2d(j->L.p, (long)j->nr * j->ld, (int)naux, (int)(j->nr * j->ld));
+      d.M = nvec; d.N = (int)(j->nr * j->ld); d.K = (int)naux;
+      d.C = h->SIG + h->sig_base[j->ch] + (long)j->r0 * ch->ldz; d.ldc = (long)ch->no * ch->ldz; d.accumulate = true;
+      XTD_TRY(gemm(h->gemm, d, s));
+    } else {
+      j_apply_kernel<8><<<dim3((unsigned)cdiv((long)j->nr * j->nc, 256), (unsigned)cdiv(nvec, 8)), 256, 0, s>>>(
+          h->SIG + h->sig_base[j->ch] + (long)j->r0 * ch->ldz + j->c0, ch->ldz, (long)ch->no * ch->ldz, j->L.p, j->ld, (long)j->nr * j->ld,
+          h->jRm + (long)b * nap, (long)njb * nap, naux, j->nr, j->nc, nvec);
+      LAUNCH_CHECK();
+    }
   }
   return XTD_OK;
 }
