@@ -119,7 +119,7 @@ def cpu_reference_rate(dp, nvec_sample: int = 1, target_s: float = 12.0):
     sigma is linear in both, so the full-size time per vector is t_k*naux/naux_s + t_xc*ng/ng_s + t_rest."""
     from oracle import jk, numint
     from xtddft_b200.synth_device import host_sample
-    from xtddft_b200.workloads import oracle_vind_for
+    from oracle.workloads import oracle_vind_for
     try:
         from threadpoolctl import threadpool_info
         info = threadpool_info()

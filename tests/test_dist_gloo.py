@@ -28,7 +28,8 @@ def _worker(rank, world, port, method, out_dir):
     from plan_interp import PlanInterpreter
     from xtddft_b200.dist import SigmaReducer, split_range
     from xtddft_b200.synth import make_problem
-    from xtddft_b200.workloads import oracle_vind_for, plan_for
+    from oracle.workloads import oracle_vind_for
+    from xtddft_b200.workloads import plan_for
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)

@@ -18,20 +18,6 @@ def plan_for(p, method: str):
     raise ValueError(method)
 
 
-def oracle_vind_for(p, method: str):
-    """Oracle builder matching `plan_for` (imported lazily: tests / smoke / cpu baseline only)."""
-    from oracle import sigma as osig
-    if method == "xtda":
-        return osig.xtda_gen_vind(p)
-    if method == "sf_down":
-        return osig.sf_gen_vind(p, -1, 0)
-    if method == "sf_up":
-        return osig.sf_gen_vind(p, 1, 0)
-    if method == "xsf":
-        return osig.xsf_gen_vind(p, sa=3, method=0, remove=True)
-    raise ValueError(method)
-
-
 def default_workspace_bytes(dp: DeviceProblem, world: int = 1) -> int:
     """Workspace for the per-call buffers: what is left of HBM after the resident MO-basis tensor blocks and AO values
     of this rank's shard, capped at 24 GiB (more does not change the chunking noticeably)."""
