@@ -25,7 +25,7 @@ extern "C" {
 
 typedef struct xtd_engine* xtd_handle;
 
-enum { XTD_FXC_NONE = 0, XTD_FXC_UKS = 1, XTD_FXC_ALDA0 = 2, XTD_FXC_MCOL = 3 };
+enum { XTD_FXC_NONE = 0, XTD_FXC_UKS = 1, XTD_FXC_ALDA0 = 2, XTD_FXC_MCOL = 3, XTD_FXC_UKS_TAU = 4, XTD_FXC_MCOL_TAU = 5 };
 enum { XTD_SIDE_RIGHT = 0, XTD_SIDE_LEFT = 1 };
 
 typedef struct {
@@ -70,7 +70,9 @@ int xtd_jblock_diag(xtd_handle h, int jb, double* out_dev);   /* out[nr*nc] = su
  * ao[nvar, ng, nao] with row stride ld_row and component stride stride_comp, weights[ng], cached kernel:
  *   XTD_FXC_UKS   fxc[2,nvar,2,nvar,ng] unweighted   (numint.cache_xc_kernel)
  *   XTD_FXC_ALDA0 f[ng] weighted                     (SF_TDA.cache_xc_kernel_sf)
- *   XTD_FXC_MCOL  fxc[nvar,nvar,ng] unweighted       (cache_xc_kernel_sf_mc) */
+ *   XTD_FXC_MCOL  fxc[nvar,nvar,ng] unweighted       (cache_xc_kernel_sf_mc)
+ *   XTD_FXC_UKS_TAU / XTD_FXC_MCOL_TAU   meta-GGA: the same layouts with 5 kernel components (rho, grad rho, tau) over the
+ *                 4 AO components value + gradient (MGGA_DENSITY_LAPL off, SF_TDA.py:141-152, 1028-1040) */
 int xtd_set_grid(xtd_handle h, const double* ao_dev, int nvar, long ng, long ld_row, long stride_comp, const double* w_dev);
 int xtd_set_fxc(xtd_handle h, int kind, const double* fxc_dev);
 /* Transform the AO values once to the occupied / virtual MO values of every declared channel (phi = ao.Co, phiv = ao.Cv)

@@ -10,30 +10,38 @@ reference calls or forks.  Dense AO values (no screening): the sparse helpers `_
 import numpy as np
 
 
-def eval_rho1(ao, dm):
+def eval_rho1(ao, dm, mgga=False):
     """rho[c,g] of a (non-symmetric) density matrix, hermi=0.
     LDA (ao[1,g,n]): rho_0 = sum phi_mu D_mu,nu phi_nu.
-    GGA (ao[4,g,n]): rho_k = sum (d_k phi_mu) D phi_nu + phi_mu D (d_k phi_nu)."""
+    GGA (ao[4,g,n]): rho_k = sum (d_k phi_mu) D phi_nu + phi_mu D (d_k phi_nu).
+    meta-GGA (ao[4,g,n], MGGA_DENSITY_LAPL off): a fifth component tau = 1/2 sum_k (d_k phi_mu) D (d_k phi_nu)."""
     nvar = ao.shape[0]
     c0 = ao[0] @ dm                      # c0[g,nu] = sum_mu phi_mu D_mu,nu
-    rho = np.empty((nvar, ao.shape[1]))
+    rho = np.empty((5 if mgga else nvar, ao.shape[1]))
     rho[0] = np.einsum("gn,gn->g", c0, ao[0])
     if nvar > 1:
         c1 = ao[0] @ dm.T
         for k in range(1, 4):
             rho[k] = np.einsum("gn,gn->g", c0, ao[k]) + np.einsum("gn,gn->g", c1, ao[k])
+    if mgga:
+        rho[4] = 0.5 * sum(np.einsum("gn,gn->g", ao[k] @ dm, ao[k]) for k in range(1, 4))
     return rho
 
 
 def _integrate(ao, wv, lda):
-    """V = ao^T diag(wv) ao (LDA)  or  sym( ao_0^T sum_c ao_c wv_c ) with wv_0 halved (GGA)."""
+    """V = ao^T diag(wv) ao (LDA)  or  sym( ao_0^T sum_c ao_c wv_c ) with wv_0 halved (GGA); a fifth row of wv is the tau
+    potential: + 1/2 sum_k (d_k ao)^T wv_4 (d_k ao)  (SF_TDA.py:141-152: wv[4] *= .5, _tau_dot_sparse, added after the
+    symmetrisation)."""
     if lda:
         return (ao[0] * wv[0][:, None]).T @ ao[0]
-    w = wv.copy()
+    w = wv[:4].copy()
     w[0] *= 0.5
     aow = np.einsum("cgn,cg->gn", ao, w)
     v = ao[0].T @ aow
-    return v + v.T
+    v = v + v.T
+    if wv.shape[0] == 5:
+        v = v + sum(ao[k].T @ (ao[k] * (0.5 * wv[4])[:, None]) for k in range(1, 4))
+    return v
 
 
 def nr_uks_fxc(ao, weights, fxc, dms):
@@ -43,7 +51,8 @@ def nr_uks_fxc(ao, weights, fxc, dms):
     nset = dms.shape[1]
     out = np.zeros_like(dms)
     for i in range(nset):
-        rho1 = np.stack([eval_rho1(ao, dms[0, i]), eval_rho1(ao, dms[1, i])])      # [2,nvar,g]
+        mg = fxc.shape[1] == 5
+        rho1 = np.stack([eval_rho1(ao, dms[0, i], mg), eval_rho1(ao, dms[1, i], mg)])      # [2,nvar,g]
         wv = np.einsum("axg,axbyg->byg", rho1, fxc) * weights
         for s in range(2):
             out[s, i] = _integrate(ao, wv[s], lda=(nvar == 1))
@@ -70,7 +79,7 @@ def nr_uks_fxc_sf_mc(ao, weights, fxc_sf, dms):
     out = np.zeros_like(dms)
     nvar = ao.shape[0]
     for i in range(dms.shape[0]):
-        rho1 = eval_rho1(ao, dms[i])
+        rho1 = eval_rho1(ao, dms[i], fxc_sf.shape[0] == 5)
         if nvar == 1:
             wv = (rho1[0] * fxc_sf[0, 0] * 2.0 * weights)[None]
         else:

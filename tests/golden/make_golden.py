@@ -129,11 +129,13 @@ class FakeNumInt:
                 a0 = ao if ao.ndim == 2 else ao[0]
                 return np.array([a0[g] @ dm @ a0[g] for g in range(a0.shape[0])])
             ng = ao.shape[1]
-            rho = np.zeros((4, ng))
+            rho = np.zeros((5 if xctype == "MGGA" else 4, ng))
             for g in range(ng):
                 rho[0, g] = ao[0, g] @ dm @ ao[0, g]
                 for k in range(1, 4):
                     rho[k, g] = ao[k, g] @ dm @ ao[0, g] + ao[0, g] @ dm @ ao[k, g]
+                if xctype == "MGGA":          # tau = 1/2 sum_k (d_k phi) D (d_k phi)   (pyscf eval_rho, no Laplacian)
+                    rho[4, g] = 0.5 * sum(ao[k, g] @ dm @ ao[k, g] for k in range(1, 4))
             return rho
         return make_rho, ndms, self.p.nao
 
@@ -163,7 +165,7 @@ class FakeNumInt:
         """pyscf.dft.numint.nr_uks_fxc, grid-point loops."""
         p = self.p
         dms = np.asarray(dms)
-        nvar = p.ao.shape[0]
+        nvar = 5 if p.xctype == "MGGA" else p.ao.shape[0]
         out = np.zeros_like(dms)
         make_a = self._gen_rho_evaluator(mol, dms[0])[0]
         make_b = self._gen_rho_evaluator(mol, dms[1])[0]
@@ -187,6 +189,10 @@ class FakeNumInt:
                         aow = sum(wv[d, g] * p.ao[d, g] for d in range(4))
                         m += np.outer(p.ao[0, g], aow)
                     out[t, i] = m + m.T
+                    if nvar == 5:             # meta-GGA: wv_tau halved, tau-dot added after the symmetrisation
+                        for g in range(p.ng):
+                            for k in range(1, 4):
+                                out[t, i] += 0.5 * wv[4, g] * np.outer(p.ao[k, g], p.ao[k, g])
         return out
 
 
@@ -205,8 +211,13 @@ def _scale_ao_sparse(ao, wv, mask, ao_loc, out=None):
     return sum(ao[c] * wv[c][:, None] for c in range(wv.shape[0]))
 
 
-def _tau_dot_sparse(*a, **k):
-    raise NotImplementedError
+def _tau_dot_sparse(bra, ket, wv, nbins, mask, pair_mask, ao_loc, out=None):
+    """pyscf.dft.numint._tau_dot_sparse: sum over x, y, z of (d_k bra)^T diag(wv) (d_k ket)."""
+    r = sum(bra[k].T @ (ket[k] * wv[:, None]) for k in range(1, 4))
+    if out is None:
+        return r
+    out += r
+    return out
 
 
 def full_eri(cderi):
@@ -435,6 +446,9 @@ def load_reference_modules():
     mods["utils"] = ref_utils
     mods["XTDA"] = importlib.import_module("xtddft.XTDA")
     mods["SF_TDA"] = importlib.import_module("xtddft.SF_TDA")
+    # SF_TDA.py:142,1029 read a module-level MGGA_DENSITY_LAPL that the file never defines (it is a local of
+    # cache_xc_kernel_sf, :42): the meta-GGA branches raise NameError as shipped.  Define it with the value the file uses.
+    mods["SF_TDA"].MGGA_DENSITY_LAPL = False
     # XSF_TDA.py does not parse as shipped (full-width comma at line 1137): fix in memory
     path = os.path.join(REF, "xtddft", "XSF_TDA.py")
     src = open(path, encoding="utf-8").read().replace("，", ",")
@@ -480,6 +494,7 @@ def main():
         dict(tag="roks_lda_no3", nc=2, no=3, nv=4, naux=9, ng=30, xctype="LDA", hyb=0.0, restricted=True, seed=13),
         dict(tag="roks_hf_no1", nc=3, no=1, nv=4, naux=9, ng=0, xctype="HF", hyb=1.0, restricted=True, seed=14),
         dict(tag="uks_gga_no1", nc=3, no=1, nv=5, naux=11, ng=40, xctype="GGA", hyb=0.2, restricted=False, seed=15),
+        dict(tag="roks_mgga_no2", nc=3, no=2, nv=4, naux=10, ng=36, xctype="MGGA", hyb=0.1, restricted=True, seed=16),
     ]
     for c in xtda_cases:
         p = make_problem(c["nc"] + c["no"] + c["nv"], c["nc"], c["no"], c["nv"], c["naux"], c["ng"], xctype=c["xctype"],
@@ -505,6 +520,7 @@ def main():
         dict(tag="up_gga", isf=1, nc=3, no=2, nv=4, naux=10, ng=36, xctype="GGA", hyb=0.5, restricted=True, seed=22),
         dict(tag="down_lda", isf=-1, nc=2, no=3, nv=4, naux=9, ng=33, xctype="LDA", hyb=0.3, restricted=True, seed=23),
         dict(tag="down_uks", isf=-1, nc=3, no=2, nv=4, naux=10, ng=36, xctype="GGA", hyb=0.5, restricted=False, seed=24),
+        dict(tag="down_mgga", isf=-1, nc=3, no=2, nv=4, naux=10, ng=36, xctype="MGGA", hyb=0.4, restricted=True, seed=26),
     ]
     for c in sf_cases:
         p = make_problem(c["nc"] + c["no"] + c["nv"], c["nc"], c["no"], c["nv"], c["naux"], c["ng"], xctype=c["xctype"],
@@ -534,6 +550,14 @@ def main():
     dms = np.einsum("xov,qv,po->xpq", z, cv, co)
     v_mc = R["SF_TDA"].nr_uks_fxc_sf_tda_mc(mf._numint, mf.mol, mf.grids, mf.xc, None, dms, 0, 0, None, None, p.fxc_mcol)
     np.savez(os.path.join(HERE, "sf_mcol_contraction.npz"), dms=dms, v=v_mc, params=np.array([3, 2, 4, 10, 36, 25]))
+    # ... and its meta-GGA branch (tau component of the kernel, SF_TDA.py:1028-1040)
+    p = make_problem(9, 3, 2, 4, 10, 36, xctype="MGGA", hyb=0.5, seed=27)
+    mf = FakeROKS(p)
+    co, cv = p.mo_coeff[0][:, :p.nocc_a], p.mo_coeff[1][:, p.nocc_b:]
+    z = rand_vectors(127, 2, p.nocc_a * p.nvir_b).reshape(2, p.nocc_a, p.nvir_b)
+    dms = np.einsum("xov,qv,po->xpq", z, cv, co)
+    v_mc = R["SF_TDA"].nr_uks_fxc_sf_tda_mc(mf._numint, mf.mol, mf.grids, mf.xc, None, dms, 0, 0, None, None, p.fxc_mcol)
+    np.savez(os.path.join(HERE, "sf_mcol_contraction_mgga.npz"), dms=dms, v=v_mc, params=np.array([3, 2, 4, 10, 36, 27]))
 
     # ---- XSF-TDA (XSF_TDA.py, block layout) ----------------------------------------------------------
     for (tagname, nc, no, nv, xct, seed) in [("gga_no2", 3, 2, 4, "GGA", 31), ("lda_no3", 2, 3, 3, "LDA", 32)]:

@@ -100,25 +100,29 @@ class PlanInterpreter:
         # grid kernel, half-transformed: Y = ao . (Cv z^T), rho via phi_o, A-buffers, R = ao^T A, project with Cv
         if plan.xc_kind != "none":
             nvar = p.ao.shape[0]
+            tau = plan.xc_kind.endswith("_tau")                        # meta-GGA: fifth component of rho / wv
+            kind = plan.xc_kind.replace("_tau", "")
             ys = [es("cgm,mv,xov->cgxo", p.ao, self.cv[c], zs[c]) for c in range(len(zs))]
             rhos = []
             for c in range(len(zs)):
                 y, ph = ys[c], self.phi[c]
-                r = np.zeros((nvar,) + y.shape[1:3])                   # [c, g, x]
+                r = np.zeros((nvar + int(tau),) + y.shape[1:3])        # [c, g, x]
                 r[0] = es("gxo,go->gx", y[0], ph[0])
                 for k in range(1, nvar):
                     r[k] = es("gxo,go->gx", y[k], ph[0]) + es("gxo,go->gx", y[0], ph[k])
+                    if tau:
+                        r[4] += 0.5 * es("gxo,go->gx", y[k], ph[k])
                 rhos.append(r)
             wvs = []
-            if plan.xc_kind == "uks":
+            if kind == "uks":
                 rho1 = np.stack(rhos)                                  # [s, c, g, x]
                 wv = es("scgx,sctdg->tdgx", rho1, p.fxc_uks) * p.weights[None, None, :, None]
                 wvs = [wv[0], wv[1]]
-            elif plan.xc_kind == "alda0":
+            elif kind == "alda0":
                 wv = np.zeros_like(rhos[0])
                 wv[0] = rhos[0][0] * p.fxc_alda0[:, None]
                 wvs = [wv]
-            elif plan.xc_kind == "mcol":
+            elif kind == "mcol":
                 wvs = [es("bgx,bag->agx", rhos[0], 2.0 * p.fxc_mcol) * p.weights[None, :, None]]
             for c in range(len(zs)):
                 wv, ph = wvs[c], self.phi[c]
@@ -127,6 +131,8 @@ class PlanInterpreter:
                 for k in range(1, nvar):
                     a[0] += es("gx,go->gxo", wv[k], ph[k])
                     a[k] = es("gx,go->gxo", wv[k], ph[0])
+                    if tau:
+                        a[k] += 0.5 * es("gx,go->gxo", wv[4], ph[k])
                 rt = es("cgxo,cgm->xom", a, p.ao)
                 sig[c] += es("xom,mv->xov", rt, self.cv[c])
         return sig

@@ -49,7 +49,7 @@ def _close(a, b, tol=RTOL):
     assert err <= tol, err
 
 
-@pytest.mark.parametrize("tag", ["roks_gga_no1", "roks_gga_no2", "roks_lda_no3", "roks_hf_no1", "uks_gga_no1"])
+@pytest.mark.parametrize("tag", ["roks_gga_no1", "roks_gga_no2", "roks_lda_no3", "roks_hf_no1", "uks_gga_no1", "roks_mgga_no2"])
 def test_xtda_golden(torch_cuda, golden_dir, tag):
     d = _load(golden_dir, f"xtda_{tag}.npz")
     p = _problem(d)
@@ -58,7 +58,7 @@ def test_xtda_golden(torch_cuda, golden_dir, tag):
     assert np.abs(hdiag - d["hdiag"]).max() < 1e-12
 
 
-@pytest.mark.parametrize("tag", ["down_gga", "up_gga", "down_lda", "down_uks"])
+@pytest.mark.parametrize("tag", ["down_gga", "up_gga", "down_lda", "down_uks", "down_mgga"])
 def test_sf_golden(torch_cuda, golden_dir, tag):
     d = _load(golden_dir, f"sf_{tag}.npz")
     p = _problem(d)

@@ -218,3 +218,20 @@ def test_xtda_coulomb_routes(torch_cuda, monkeypatch, route):
     eng = _engine(planmod.build_xtda_plan(p), p, max_nvec=16)
     _check(torch_cuda, eng, vind, hd.size, nvec=9)
     eng.close()
+
+
+@pytest.mark.parametrize("nc,no,nv", [(5, 1, 15), (6, 2, 17), (130, 3, 140)])
+@pytest.mark.parametrize("restricted", [True, False])
+def test_meta_gga(torch_cuda, nc, no, nv, restricted):
+    """Kernel tables with a tau component (meta-GGA, no Laplacian): UKS kernel of X-TDA, multicollinear spin flip; the
+    ALDA0 kernel of a meta-GGA has no tau part.  Odd / even occupied counts (8- and 16-byte access variants)."""
+    p = make_problem(nc + no + nv, nc, no, nv, 7, 260, xctype="MGGA", hyb=0.2, restricted=restricted, seed=230 + no)
+    vind, hd = osig.xtda_gen_vind(p)
+    eng = _engine(planmod.build_xtda_plan(p), p, max_nvec=8)
+    _check(torch_cuda, eng, vind, hd.size, nvec=3)
+    eng.close()
+    for method in (1, 0):
+        vind, hd = osig.sf_gen_vind(p, -1, method)
+        eng = _engine(planmod.build_sf_plan(p, isf=-1, method=method), p, max_nvec=8)
+        _check(torch_cuda, eng, vind, hd.size, nvec=5)
+        eng.close()

@@ -41,7 +41,7 @@ def test_helpers(golden_dir):
         _close(layouts.get_vect(no), h[f"vects_{no}"], 1e-15)
 
 
-@pytest.mark.parametrize("tag", ["roks_gga_no1", "roks_gga_no2", "roks_lda_no3", "roks_hf_no1", "uks_gga_no1"])
+@pytest.mark.parametrize("tag", ["roks_gga_no1", "roks_gga_no2", "roks_lda_no3", "roks_hf_no1", "uks_gga_no1", "roks_mgga_no2"])
 def test_xtda_sigma(golden_dir, tag):
     d = _load(golden_dir, f"xtda_{tag}.npz")
     p = _problem(d)
@@ -50,7 +50,7 @@ def test_xtda_sigma(golden_dir, tag):
     _close(vind(d["z"]), d["hx"])
 
 
-@pytest.mark.parametrize("tag", ["down_gga", "up_gga", "down_lda", "down_uks"])
+@pytest.mark.parametrize("tag", ["down_gga", "up_gga", "down_lda", "down_uks", "down_mgga"])
 def test_sf_sigma(golden_dir, tag):
     d = _load(golden_dir, f"sf_{tag}.npz")
     p = _problem(d)
@@ -67,6 +67,14 @@ def test_sf_sigma(golden_dir, tag):
 def test_sf_mcol_contraction(golden_dir):
     d = _load(golden_dir, "sf_mcol_contraction.npz")
     p = make_problem(9, 3, 2, 4, 10, 36, xctype="GGA", hyb=0.5, seed=25)
+    _close(numint.nr_uks_fxc_sf_mc(p.ao, p.weights, p.fxc_mcol, d["dms"]), d["v"])
+
+
+def test_sf_mcol_contraction_mgga(golden_dir):
+    """tau component of the multicollinear kernel (SF_TDA.py:1028-1040; the shipped file needs MGGA_DENSITY_LAPL defined)"""
+    d = _load(golden_dir, "sf_mcol_contraction_mgga.npz")
+    p = make_problem(9, 3, 2, 4, 10, 36, xctype="MGGA", hyb=0.5, seed=27)
+    assert p.fxc_mcol.shape[0] == 5 and p.ao.shape[0] == 4
     _close(numint.nr_uks_fxc_sf_mc(p.ao, p.weights, p.fxc_mcol, d["dms"]), d["v"])
 
 

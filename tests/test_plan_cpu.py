@@ -93,3 +93,20 @@ def test_xsf_lda_hf():
         it = PlanInterpreter(pl, p)
         z = _z(6, 2, hd.size)
         _check(it.sigma(z), vind(z))
+
+
+@pytest.mark.parametrize("restricted", [True, False])
+def test_meta_gga_plans(restricted):
+    """tau component of the kernel tables: X-TDA (UKS kernel), spin-flip multicollinear; ALDA0 has no tau part."""
+    p = make_problem(11, 3, 2, 6, 9, 30, xctype="MGGA", hyb=0.2, restricted=restricted, seed=77)
+    vind, hd = sigma.xtda_gen_vind(p)
+    pl = planmod.build_xtda_plan(p)
+    assert pl.xc_kind == "uks_tau"
+    z = _z(3, 2, hd.size)
+    _check(PlanInterpreter(pl, p).sigma(z), vind(z))
+    for method, kind in [(1, "mcol_tau"), (0, "alda0")]:
+        vind, hd = sigma.sf_gen_vind(p, -1, method)
+        pl = planmod.build_sf_plan(p, isf=-1, method=method)
+        assert pl.xc_kind == kind
+        z = _z(4, 2, hd.size)
+        _check(PlanInterpreter(pl, p).sigma(z), vind(z))

@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .problem import ProblemData, XC_GGA, XC_LDA, XC_NONE
+from .problem import ProblemData, XC_GGA, XC_LDA, XC_MGGA, XC_NONE
 
 
 class SynthMF:
@@ -152,9 +152,10 @@ def from_pyscf(mf, kernel: str = "uks", collinear_samples: int = 60, auxbasis=No
     if is_dft and kernel != "none":
         ni = mf._numint
         xt = ni._xc_type(mf.xc)
-        if xt not in ("LDA", "GGA"):
-            raise NotImplementedError("meta-GGA kernels are not supported by the B200 path yet")
-        xctype = XC_LDA if xt == "LDA" else XC_GGA
+        if xt not in ("LDA", "GGA", "MGGA"):
+            raise NotImplementedError(f"kernel type {xt} is not supported by the B200 path")
+        # meta-GGA: value + gradient AO components and kernel tables with a tau component (no Laplacian, as in the reference)
+        xctype = {"LDA": XC_LDA, "GGA": XC_GGA, "MGGA": XC_MGGA}[xt]
         coords, weights = mf.grids.coords, np.asarray(mf.grids.weights)
         aov = ni.eval_ao(mol, coords, deriv=0 if xt == "LDA" else 1)
         ao = aov[None] if xt == "LDA" else aov[:4]

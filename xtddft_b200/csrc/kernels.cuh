@@ -177,24 +177,28 @@ struct XcVec<2> {
   __device__ __forceinline__ void store(double* p) const { *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]); }
 };
 
-template <int NVAR, int KIND, int XU, int W>
+// TAU (value + gradient AO components only): the kernel tables carry a fifth component, the kinetic-energy density
+//   tau(g,x) = 1/2 sum_k sum_o Y_k phi_k,   and its potential adds  A_k += 1/2 wv_tau phi_k   (meta-GGA, no Laplacian).
+template <int NVAR, int KIND, int XU, int W, bool TAU = false>
 __global__ void __launch_bounds__(256) xc_weight_kernel(const XcArgs a) {
+  static_assert(!TAU || NVAR == 4, "the tau component needs value + gradient AO components");
   const int lane = threadIdx.x & 31;
   const long g = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (g >= a.gb) return;
   constexpr int NCH = (KIND == XC_KIND_UKS) ? 2 : 1;
-  constexpr int NR = NCH * NVAR;
+  constexpr int NK = TAU ? 5 : NVAR;          // components of the response density / kernel tables
+  constexpr int NR = NCH * NK;
   // kernel row for this grid point (kept in registers across the vector loop)
-  double fk[(KIND == XC_KIND_UKS) ? NR : (KIND == XC_KIND_MCOL ? NVAR : 1)];
+  double fk[(KIND == XC_KIND_UKS) ? NR : (KIND == XC_KIND_MCOL ? NK : 1)];
   if (KIND == XC_KIND_UKS) {
-    // lane l < NR owns output component l = t*NVAR + d and needs wf[g][l][*]
+    // lane l < NR owns output component l = t*NK + d and needs wf[g][l][*]
     const double* row = a.wf + (a.g0 + g) * (long)(NR * NR);
 #pragma unroll
     for (int q = 0; q < NR; ++q) fk[q] = (lane < NR) ? row[lane * NR + q] : 0.0;
   } else if (KIND == XC_KIND_MCOL) {
-    const double* row = a.wf + (a.g0 + g) * (long)(NVAR * NVAR);
+    const double* row = a.wf + (a.g0 + g) * (long)(NK * NK);
 #pragma unroll
-    for (int q = 0; q < NVAR; ++q) fk[q] = (lane < NVAR) ? row[lane * NVAR + q] : 0.0;
+    for (int q = 0; q < NK; ++q) fk[q] = (lane < NK) ? row[lane * NK + q] : 0.0;
   } else {
     fk[0] = a.wf[a.g0 + g];
   }
@@ -225,9 +229,12 @@ __global__ void __launch_bounds__(256) xc_weight_kernel(const XcArgs a) {
           if (x0 + u < a.nvec) {
 #pragma unroll
             for (int e = 0; e < W; ++e) {
-              rho[u][s * NVAR] += yc[u][0].v[e] * pc[0].v[e];
+              rho[u][s * NK] += yc[u][0].v[e] * pc[0].v[e];
 #pragma unroll
-              for (int k = 1; k < NVAR; ++k) rho[u][s * NVAR + k] += yc[u][k].v[e] * pc[0].v[e] + yc[u][0].v[e] * pc[k].v[e];
+              for (int k = 1; k < NVAR; ++k) {
+                rho[u][s * NK + k] += yc[u][k].v[e] * pc[0].v[e] + yc[u][0].v[e] * pc[k].v[e];
+                if (TAU) rho[u][s * NK + 4] += 0.5 * yc[u][k].v[e] * pc[k].v[e];
+              }
             }
           }
       }
@@ -248,9 +255,9 @@ __global__ void __launch_bounds__(256) xc_weight_kernel(const XcArgs a) {
       } else if (KIND == XC_KIND_MCOL) {
         double mine = 0.0;
 #pragma unroll
-        for (int q = 0; q < NVAR; ++q) mine += fk[q] * rho[u][q];    // wv[a] = sum_b (2 w f[b,a]) rho[b]
+        for (int q = 0; q < NK; ++q) mine += fk[q] * rho[u][q];      // wv[a] = sum_b (2 w f[b,a]) rho[b]
 #pragma unroll
-        for (int q = 0; q < NVAR; ++q) wv[u][q] = __shfl_sync(0xffffffffu, mine, q);
+        for (int q = 0; q < NK; ++q) wv[u][q] = __shfl_sync(0xffffffffu, mine, q);
       } else {
         wv[u][0] = rho[u][0] * fk[0];
       }
@@ -272,15 +279,16 @@ __global__ void __launch_bounds__(256) xc_weight_kernel(const XcArgs a) {
           if (x0 + u < a.nvec) {
             XcVec<W> out;
 #pragma unroll
-            for (int e = 0; e < W; ++e) out.v[e] = wv[u][s * NVAR] * pc[0].v[e];
+            for (int e = 0; e < W; ++e) out.v[e] = wv[u][s * NK] * pc[0].v[e];
             if (KIND != XC_KIND_ALDA0) {
 #pragma unroll
               for (int k = 1; k < NVAR; ++k) {
                 XcVec<W> ok;
 #pragma unroll
                 for (int e = 0; e < W; ++e) {
-                  out.v[e] += wv[u][s * NVAR + k] * pc[k].v[e];
-                  ok.v[e] = wv[u][s * NVAR + k] * pc[0].v[e];
+                  out.v[e] += wv[u][s * NK + k] * pc[k].v[e];
+                  ok.v[e] = wv[u][s * NK + k] * pc[0].v[e];
+                  if (TAU) ok.v[e] += 0.5 * wv[u][s * NK + 4] * pc[k].v[e];
                 }
                 ok.store(yb + (long)u * no + k * a.y_comp[s] + o);
               }

@@ -130,6 +130,7 @@ struct xtd_engine {
   int nvar = 0, nvar_eff = 0;
   long ng = 0, ao_ld = 0, ao_comp = 0;
   int fxc_kind = XTD_FXC_NONE;
+  bool tau = false;            // meta-GGA: kernel tables with a fifth (tau) component
   const double* fxc = nullptr;
   DevBuf wf;
   bool grid_committed = false;
@@ -306,14 +307,16 @@ int grid_commit(xtd_engine* h) {
       e.C = c->phiv.p; e.ldc = c->ldphiv; e.c_batch_stride = h->ng * c->ldphiv;
       XTD_TRY(gemm(h->gemm, e, s));
     }
+    if (h->tau) XTD_REQUIRE(h->nvar == 4, XTD_ERR_ARG, "meta-GGA kernels need value + gradient AO components (nvar = 4)");
+    const int nk = h->tau ? 5 : h->nvar;        // kernel components
     if (h->fxc_kind == XTD_FXC_UKS) {
-      const int nr = 2 * h->nvar;
+      const int nr = 2 * nk;
       XTD_TRY(h->wf.alloc((size_t)h->ng * nr * nr));
-      build_wf_uks_kernel<<<grid1d(h->ng, 128), 128, 0, s>>>(h->wf.p, h->fxc, h->wgrid, h->ng, h->nvar);
+      build_wf_uks_kernel<<<grid1d(h->ng, 128), 128, 0, s>>>(h->wf.p, h->fxc, h->wgrid, h->ng, nk);
       LAUNCH_CHECK();
     } else if (h->fxc_kind == XTD_FXC_MCOL) {
-      XTD_TRY(h->wf.alloc((size_t)h->ng * h->nvar * h->nvar));
-      build_wf_mcol_kernel<<<grid1d(h->ng, 128), 128, 0, s>>>(h->wf.p, h->fxc, h->wgrid, h->ng, h->nvar);
+      XTD_TRY(h->wf.alloc((size_t)h->ng * nk * nk));
+      build_wf_mcol_kernel<<<grid1d(h->ng, 128), 128, 0, s>>>(h->wf.p, h->fxc, h->wgrid, h->ng, nk);
       LAUNCH_CHECK();
     }
     XTD_CUDA(cudaStreamSynchronize(s));
@@ -645,8 +648,11 @@ int xtd_set_grid(xtd_handle h, const double* ao_dev, int nvar, long ng, long ld_
 
 int xtd_set_fxc(xtd_handle h, int kind, const double* fxc_dev) {
   XTD_REQUIRE(h && !h->finalized && !h->grid_committed, XTD_ERR_STATE, "xtd_set_fxc after commit / finalize");
-  XTD_REQUIRE(kind >= XTD_FXC_NONE && kind <= XTD_FXC_MCOL && (kind == XTD_FXC_NONE || fxc_dev), XTD_ERR_ARG, "xtd_set_fxc: bad arguments");
-  h->fxc_kind = kind; h->fxc = fxc_dev;
+  XTD_REQUIRE(kind >= XTD_FXC_NONE && kind <= XTD_FXC_MCOL_TAU && (kind == XTD_FXC_NONE || fxc_dev), XTD_ERR_ARG, "xtd_set_fxc: bad arguments");
+  h->tau = (kind == XTD_FXC_UKS_TAU || kind == XTD_FXC_MCOL_TAU);
+  if (h->tau) XTD_REQUIRE(h->ao == nullptr || h->nvar == 4, XTD_ERR_ARG, "meta-GGA kernels need value + gradient AO components (nvar = 4)");
+  h->fxc_kind = kind == XTD_FXC_UKS_TAU ? XTD_FXC_UKS : (kind == XTD_FXC_MCOL_TAU ? XTD_FXC_MCOL : kind);
+  h->fxc = fxc_dev;
   return XTD_OK;
 }
 
@@ -784,15 +790,15 @@ static int setup_call_buffers(xtd_engine* h, int nvec) {
   return XTD_OK;
 }
 
-template <int NVAR, int KIND>
+template <int NVAR, int KIND, bool TAU = false>
 static void launch_xc(const XcArgs& a, cudaStream_t s) {
   // vectors per pass: 4 for one AO component, 2 for value + gradient (register budget); 16-byte accesses when every
   // (vector, component) row segment is 16-byte aligned, i.e. all occupied counts are even
   constexpr int XU = NVAR == 1 ? 4 : 2;
   const bool even = (a.no[0] % 2 == 0) && (a.nch == 1 || a.no[1] % 2 == 0);
   const unsigned grid = (unsigned)cdiv(a.gb, 8);
-  if (even) xc_weight_kernel<NVAR, KIND, XU, 2><<<grid, 256, 0, s>>>(a);
-  else xc_weight_kernel<NVAR, KIND, XU, 1><<<grid, 256, 0, s>>>(a);
+  if (even) xc_weight_kernel<NVAR, KIND, XU, 2, TAU><<<grid, 256, 0, s>>>(a);
+  else xc_weight_kernel<NVAR, KIND, XU, 1, TAU><<<grid, 256, 0, s>>>(a);
 }
 
 constexpr long XC_SPLIT_SMEM_MAX = 200 * 1024;
@@ -821,7 +827,7 @@ static int launch_xc_split(const XcArgs2& a, cudaStream_t s) {
 // four-component form against the split-gradient form; the latter halves it unless an orbital block barely exceeds
 // a tile or the problem is tiny.
 static bool xc_use_split(const xtd_engine* h, int nvec) {
-  if (h->nvar_eff != 4) return false;
+  if (h->nvar_eff != 4 || h->tau) return false;      // tau needs the gradient of both orbitals: four-component form
   {
     int no[2] = {0, 0}, nv[2] = {0, 0};
     for (size_t c = 0; c < h->ch.size(); ++c) { no[c] = h->ch[c]->no; nv[c] = h->ch[c]->nv; }
@@ -917,11 +923,15 @@ static int run_xc(xtd_engine* h, int nvec) {
         if (nch == 1) { a.Y[1] = nullptr; a.phi[1] = nullptr; a.no[1] = 0; a.ldY[1] = a.y_comp[1] = a.ldphi[1] = a.phi_comp[1] = 0; }
         a.wf = (h->fxc_kind == XTD_FXC_ALDA0) ? h->fxc : h->wf.p;
         if (h->fxc_kind == XTD_FXC_UKS) {
-          if (nve == 1) launch_xc<1, XC_KIND_UKS>(a, s); else launch_xc<4, XC_KIND_UKS>(a, s);
+          if (nve == 1) launch_xc<1, XC_KIND_UKS>(a, s);
+          else if (h->tau) launch_xc<4, XC_KIND_UKS, true>(a, s);
+          else launch_xc<4, XC_KIND_UKS>(a, s);
         } else if (h->fxc_kind == XTD_FXC_ALDA0) {
           launch_xc<1, XC_KIND_ALDA0>(a, s);
         } else {
-          if (nve == 1) launch_xc<1, XC_KIND_MCOL>(a, s); else launch_xc<4, XC_KIND_MCOL>(a, s);
+          if (nve == 1) launch_xc<1, XC_KIND_MCOL>(a, s);
+          else if (h->tau) launch_xc<4, XC_KIND_MCOL, true>(a, s);
+          else launch_xc<4, XC_KIND_MCOL>(a, s);
         }
       }
       LAUNCH_CHECK();

@@ -20,7 +20,8 @@ from .dist import SigmaReducer, split_range
 from .plan import Plan, finish_xsf_hdiag
 from .problem import ProblemData
 
-_KIND = {"none": _lib.XTD_FXC_NONE, "uks": _lib.XTD_FXC_UKS, "alda0": _lib.XTD_FXC_ALDA0, "mcol": _lib.XTD_FXC_MCOL}
+_KIND = {"none": _lib.XTD_FXC_NONE, "uks": _lib.XTD_FXC_UKS, "alda0": _lib.XTD_FXC_ALDA0, "mcol": _lib.XTD_FXC_MCOL,
+         "uks_tau": _lib.XTD_FXC_UKS_TAU, "mcol_tau": _lib.XTD_FXC_MCOL_TAU}      # *_tau: meta-GGA kernel tables (5 components)
 
 
 def _ptr(t) -> C.c_void_p:
@@ -202,7 +203,7 @@ class SigmaEngine:
             ao[:, :, :p.nao] = torch.from_numpy(np.ascontiguousarray(p.ao[:, g0:g1])).to(eng.device)
             w = torch.from_numpy(np.ascontiguousarray(p.weights[g0:g1])).to(eng.device)
             eng.set_grid(ao, w)
-            if plan.xc_kind == "uks":
+            if plan.xc_kind in ("uks", "uks_tau"):
                 f = torch.from_numpy(np.ascontiguousarray(p.fxc_uks[..., g0:g1])).to(eng.device)
             elif plan.xc_kind == "alda0":
                 f = torch.from_numpy(np.ascontiguousarray(p.fxc_alda0[g0:g1])).to(eng.device)

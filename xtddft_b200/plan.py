@@ -108,7 +108,7 @@ class Plan:
     k_terms: List[KTerm] = field(default_factory=list)
     j_blocks: List[JBlock] = field(default_factory=list)
     j_mix: Optional[np.ndarray] = None
-    xc_kind: str = "none"          # none | uks | alda0 | mcol
+    xc_kind: str = "none"          # none | uks | alda0 | mcol | uks_tau | mcol_tau (meta-GGA tables with a tau component)
     local_gemms: List[LocalGemm] = field(default_factory=list)
     rank1s: List[Rank1] = field(default_factory=list)
     diags: List[DiagTerm] = field(default_factory=list)
@@ -215,7 +215,7 @@ def build_xtda_plan(p: ProblemData) -> Plan:
             plan.k_terms += _k_weight_tables(p, ci, len(chs.o_blocks), len(chs.v_blocks), None)
         plan.j_blocks = [JBlock(0, 0, cha.no, 0, cha.nv), JBlock(1, 0, chb.no, 0, chb.nv)]
         plan.j_mix = np.ones((2, 2))
-    plan.xc_kind = "uks" if p.xctype != "HF" else "none"
+    plan.xc_kind = ("uks_tau" if p.xctype == "MGGA" else "uks") if p.xctype != "HF" else "none"
 
     fa, fb = p.fock_ks
     if p.restricted:
@@ -311,6 +311,8 @@ def build_sf_plan(p: ProblemData, isf: int = -1, method: int = 0, sa: int = 0, l
     na, nb = p.nocc_a, p.nocc_b
     fa, fb = p.fock_ks
     xc_kind = {0: "alda0", 1: "mcol", 2: "none"}[method] if p.xctype != "HF" else "none"
+    if xc_kind == "mcol" and p.xctype == "MGGA":
+        xc_kind = "mcol_tau"           # the ALDA0 kernel has no tau part (SF_TDA.py:110-116: only rho_0 enters)
     if isf == 1:
         occ = np.arange(nb, dtype=np.int32)
         vir = (na + np.arange(nv)).astype(np.int32)

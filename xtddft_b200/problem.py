@@ -23,6 +23,7 @@ import numpy as np
 XC_NONE = "HF"     # no grid term (Hartree-Fock / collinear spin-flip)
 XC_LDA = "LDA"     # nvar = 1
 XC_GGA = "GGA"     # nvar = 4
+XC_MGGA = "MGGA"   # AO components 4 (value + gradient, no Laplacian), kernel components 5 (rho, grad rho, tau)
 
 # kinds of cached kernel (xtd_set_fxc)
 FXC_NONE = 0
@@ -90,6 +91,11 @@ class ProblemData:
     @property
     def nvar(self) -> int:
         return 0 if self.ao is None else int(self.ao.shape[0])
+
+    @property
+    def nkern(self) -> int:
+        """components of the response density / kernel tables: 1, 4 or 5 (meta-GGA adds tau)"""
+        return 5 if self.xctype == XC_MGGA else self.nvar
 
     @property
     def spin_s(self) -> float:

@@ -15,7 +15,7 @@ from typing import Optional
 
 import numpy as np
 
-from .problem import ProblemData, XC_GGA, XC_LDA, XC_NONE
+from .problem import ProblemData, XC_GGA, XC_LDA, XC_MGGA, XC_NONE
 
 # BASELINE.json configs -> synthetic shapes.  "method": xtda | sf_down | xsf
 CONFIGS = {
@@ -138,8 +138,8 @@ def make_problem(nao: int, nc: int, no: int, nv: int, naux: int, ng: int, *, xct
 
     ao = weights = fxc_uks = fxc_alda0 = fxc_mcol = None
     if xctype != XC_NONE and ng > 0:
-        ao, weights = gaussian_ao(rng, ng, nao, deriv=(xctype == XC_GGA))
-        nvar = ao.shape[0]
+        ao, weights = gaussian_ao(rng, ng, nao, deriv=(xctype in (XC_GGA, XC_MGGA)))
+        nvar = 5 if xctype == XC_MGGA else ao.shape[0]      # kernel components (meta-GGA: rho, grad rho, tau)
         # scale the kernels so that the grid term of A has norm ~ xc_strength (a perturbation of the gaps):
         # power-iteration estimate for a unit kernel on the largest occ x vir block
         est = _xc_norm_estimate(ao[0], ca[:, :nc + no], cb[:, nc:], weights)
@@ -152,6 +152,9 @@ def make_problem(nao: int, nc: int, no: int, nv: int, naux: int, ng: int, *, xct
             gradscale = np.ones(2 * nvar)
             if nvar == 4:
                 gradscale[[1, 2, 3, 5, 6, 7]] = 0.15
+            if nvar == 5:
+                gradscale[[1, 2, 3, 6, 7, 8]] = 0.15
+                gradscale[[4, 9]] = 0.3
             f = f * gradscale[:, None, None] * gradscale[None, :, None]
             fxc_uks = (f * fscale).reshape(2, nvar, 2, nvar, ng)
         if "alda0" in fxc_kinds:
@@ -161,8 +164,8 @@ def make_problem(nao: int, nc: int, no: int, nv: int, naux: int, ng: int, *, xct
             f = 0.5 * (f + f.transpose(1, 0, 2))
             idx = np.arange(nvar)
             f[idx, idx, :] = -np.abs(rng.standard_normal((nvar, ng)))
-            if nvar == 4:
-                gs = np.array([1.0, 0.15, 0.15, 0.15])
+            if nvar >= 4:
+                gs = np.array([1.0, 0.15, 0.15, 0.15, 0.3])[:nvar]
                 f = f * gs[:, None, None] * gs[None, :, None]
             fxc_mcol = f * (0.5 * fscale)
 
