@@ -371,10 +371,12 @@ inline int gemm_context_init(GemmContext& ctx) {
 
 template <bool A_KC, bool B_KC, bool TAILS>
 inline int launch_kernel(dim3 grd, cudaStream_t stream, const CUtensorMap& ma, const CUtensorMap& mb, const GemmKernelParams& kp) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};      // the opt-in is per device
+  int dev = 0;
+  XTD_CUDA(cudaGetDevice(&dev));
+  if (!attr_set[dev & 63]) {
     XTD_CUDA(cudaFuncSetAttribute(dgemm_dmma_tma_kernel<A_KC, B_KC, TAILS>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-    attr_set = true;
+    attr_set[dev & 63] = true;
   }
   dgemm_dmma_tma_kernel<A_KC, B_KC, TAILS><<<grd, GEMM_THREADS, GEMM_SMEM, stream>>>(ma, mb, kp);
   XTD_COUNT_LAUNCH();

@@ -810,7 +810,10 @@ static int launch_xc_split(const XcArgs2& a, cudaStream_t s) {
   // warps = trial vectors, in as few equal rounds as 16 warps allow
   const int rounds = (int)cdiv(a.nvec, 16);
   const int nwarps = (int)cdiv(a.nvec, rounds);
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {false};      // the shared-memory opt-in is per device
+  int dev = 0;
+  XTD_CUDA(cudaGetDevice(&dev));
+  bool& attr_set = attr_set_dev[dev & 63];
   if (!attr_set) {
     XTD_CUDA(cudaFuncSetAttribute(xc_weight_split_kernel<XC_KIND_UKS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XC_SPLIT_SMEM_MAX));
     XTD_CUDA(cudaFuncSetAttribute(xc_weight_split_kernel<XC_KIND_UKS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XC_SPLIT_SMEM_MAX));
@@ -1363,9 +1366,12 @@ int xtd_vec_scale(void* stream, double* x, long ld, const double* sc, int k, lon
 
 int xtd_dgemm(void* stream, int m, int n, int k, double alpha, const double* a, long lda, int a_kc, const double* b, long ldb, int b_kc,
               double* c, long ldc, int accumulate) {
-  static GemmContext ctx;
-  static double* ws = nullptr;
+  static GemmContext ctxs[64];                 // one context + split-K workspace per device
+  int dev = 0;
+  XTD_CUDA(cudaGetDevice(&dev));
+  GemmContext& ctx = ctxs[dev & 63];
   if (!ctx.encode) {
+    double* ws = nullptr;
     XTD_TRY(gemm_context_init(ctx));
     XTD_CUDA(cudaMalloc((void**)&ws, (size_t)256 << 20));
     ctx.split_ws = ws; ctx.split_ws_bytes = (size_t)256 << 20;
