@@ -189,11 +189,12 @@ def test_gga_split_gradient_form(torch_cuda, monkeypatch, split, nc, no, nv):
 
 
 @pytest.mark.parametrize("narrow", ["on", "off"])
-@pytest.mark.parametrize("nc,no,nv", [(131, 3, 150), (40, 4, 33), (7, 2, 260)])
+@pytest.mark.parametrize("nc,no,nv", [(131, 3, 150), (40, 4, 33), (7, 2, 260), (20, 3, 141)])
 def test_xsf_narrow_open_block(torch_cuda, monkeypatch, narrow, nc, no, nv):
     """Block-weighted exchange of the XSF Delta A with the open-shell output columns taken by the narrow-output pass
     (contract with the few open rows of Lvv first) or by the general pass (XTD_NO_NARROW); > 1 tile of closed orbitals,
-    odd / even open-shell counts, removed OO vector."""
+    odd / even open-shell counts, removed OO vector.  nv = 260 and 141 leave 4 / 13 columns past the last full 128-column
+    tile of the virtual block: that tail takes the narrow pass too."""
     if narrow == "off":
         monkeypatch.setenv("XTD_NO_NARROW", "1")
     p = make_problem(nc + no + nv, nc, no, nv, 9, 200, xctype="LDA", hyb=0.3, seed=210 + no)

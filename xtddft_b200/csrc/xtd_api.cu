@@ -50,6 +50,8 @@ struct Channel {
   bool need_split[2] = {false, false};   // (aux, row) flattens into one uniformly strided row index for block weights
   DevBuf Lvo[2];                    // [naux_loc][v2off][ldvv]: rows of Lvv in the narrow first virtual block (open shells),
   bool need_narrow[2] = {false, false};   // gathered so (aux, row) flattens: narrow-output exchange pass (run_k)
+  DevBuf Lvt[2];                    // [naux_loc][tail_w][ldvv]: the last rows of Lvv past a multiple of 128 in the second block
+  int tail_start = 0, tail_w = 0;   // (a short column tail of the block-weighted output takes the same pass)
   long ldoo, ldvv;
   bool need_k[2] = {false, false};
   DevBuf phi;                       // occupied values on the grid  [nvar_eff][ng][ldphi]
@@ -370,7 +372,7 @@ int xtd_destroy(xtd_handle h) {
   cudaDeviceSynchronize();
   for (auto* c : h->ch) {
     c->Co.release(); c->Cv.release(); c->CoT.release(); c->CvT.release(); c->phi.release(); c->phiv.release();
-    for (int t = 0; t < 2; ++t) { c->Loo[t].release(); c->Lvv[t].release(); c->Lvo[t].release(); c->Loob[t][0].release(); c->Loob[t][1].release(); }
+    for (int t = 0; t < 2; ++t) { c->Loo[t].release(); c->Lvv[t].release(); c->Lvo[t].release(); c->Lvt[t].release(); c->Loob[t][0].release(); c->Loob[t][1].release(); }
     if (c->g_indptr) cudaFree(c->g_indptr);
     if (c->g_cols) cudaFree(c->g_cols);
     if (c->g_vals) cudaFree(c->g_vals);
@@ -470,7 +472,11 @@ int xtd_add_kterm(xtd_handle h, int tensor, int chn, const double* w, int nob, i
   h->kterms.push_back(k);
   c->need_k[tensor] = true;
   if (!k.uniform && c->o_blocks.size() > 1) c->need_split[tensor] = true;
-  if (!k.uniform && c->v_blocks.size() > 1 && c->v_blocks[1].first <= NARROW_MAX) c->need_narrow[tensor] = true;
+  if (!k.uniform && c->v_blocks.size() > 1 && c->v_blocks[1].first <= NARROW_MAX) {
+    c->need_narrow[tensor] = true;
+    const int v2 = c->v_blocks[1].first, wide = c->nv - v2, q = wide / 128, w = wide - 128 * q;
+    if (q >= 1 && w > 0 && w <= NARROW_MAX) { c->tail_start = v2 + 128 * q; c->tail_w = w; }
+  }
   return XTD_OK;
 }
 
@@ -502,6 +508,7 @@ int xtd_df_begin(xtd_handle h, int tensor, long naux_local) {
     XTD_TRY(c->Loo[tensor].alloc((size_t)naux_local * c->no * c->ldoo));
     XTD_TRY(c->Lvv[tensor].alloc((size_t)naux_local * c->nv * c->ldvv));
     if (c->need_narrow[tensor]) XTD_TRY(c->Lvo[tensor].alloc((size_t)naux_local * c->v_blocks[1].first * c->ldvv));
+    if (c->need_narrow[tensor] && c->tail_w > 0) XTD_TRY(c->Lvt[tensor].alloc((size_t)naux_local * c->tail_w * c->ldvv));
     if (c->need_split[tensor]) {
       const int o2 = c->o_blocks[1].first;
       XTD_TRY(c->Loob[tensor][0].alloc((size_t)naux_local * o2 * c->ldoo));
@@ -619,6 +626,12 @@ int xtd_df_add(xtd_handle h, int tensor, const double* l_dev, long np, long ld_r
           const size_t v2 = (size_t)c->v_blocks[1].first;
           XTD_CUDA(cudaMemcpy2DAsync(c->Lvo[tensor].p + P0 * v2 * c->ldvv, v2 * c->ldvv * 8, c->Lvv[tensor].p + P0 * c->nv * c->ldvv,
                                      (size_t)c->nv * c->ldvv * 8, v2 * c->ldvv * 8, pn, cudaMemcpyDeviceToDevice, s));
+          if (c->tail_w > 0) {
+            const size_t tw = (size_t)c->tail_w;
+            XTD_CUDA(cudaMemcpy2DAsync(c->Lvt[tensor].p + P0 * tw * c->ldvv, tw * c->ldvv * 8,
+                                       c->Lvv[tensor].p + (P0 * c->nv + c->tail_start) * c->ldvv, (size_t)c->nv * c->ldvv * 8,
+                                       tw * c->ldvv * 8, pn, cudaMemcpyDeviceToDevice, s));
+          }
         }
       }
     }
@@ -1001,36 +1014,43 @@ static int run_k(xtd_engine* h, int nvec) {
     size_t ab_first = 0;
     const long ldj = ch->ldzt;
     const size_t zs_doubles = (size_t)nvec * ch->no * ch->ldz;
+    const int wmax = std::max(v2off, ch->tail_w);
     if (!k.uniform && ch->need_narrow[k.tensor] && ablks.size() == 2 &&
-        zs_doubles + (size_t)nvec * naux * v2off * ldj <= h->scratch_doubles && (long)nvec * naux < (1L << 30) && !getenv("XTD_NO_NARROW")) {
+        zs_doubles + (size_t)nvec * naux * wmax * ldj <= h->scratch_doubles && (long)nvec * naux < (1L << 30) && !getenv("XTD_NO_NARROW")) {
       double* Zs = h->scratch;
       double* R = h->scratch + zs_doubles;
-      const double* Lvo = ch->Lvo[k.tensor].p;
-      for (size_t ib = 0; ib < iblks.size(); ++ib) {
-        PhaseTimer t(h, XTD_T_K1);
-        BlockSplit bs;                       // the kernel is written for the transposed layout: roles of rows / columns swap
-        bs.o2off = v2off; bs.v2off = o2off;
-        for (int j = 0; j < 2; ++j)
-          for (int b = 0; b < 2; ++b) bs.w[b][j] = k.w[ib][0][j < k.nob ? j : 0][b < k.nvb ? b : 0];
-        scale_blocks_kernel<<<dim3((unsigned)cdiv(ch->nv, 128), ch->no, nvec), 128, 0, s>>>(Zs, h->Z[k.ch], ch->ldz, (long)ch->no * ch->ldz,
-                                                                                          ch->no, ch->nv, bs);
-        LAUNCH_CHECK();
-        GemmDesc d;
-        d.A = view2d(Lvo, ch->ldvv, (int)(naux * v2off), ch->nv);
-        d.B = view3d(Zs, ch->ldz, (long)ch->no * ch->ldz, nvec, ch->no, ch->nv);
-        d.M = (int)(naux * v2off); d.N = ch->no; d.K = ch->nv; d.batches = nvec; d.z_div = 1; d.a_hi = 0; d.b_hi = 1;
-        d.C = R; d.ldc = ldj; d.c_batch_stride = naux * v2off * ldj;
-        XTD_TRY(gemm(h->gemm, d, s));
-        const int i0 = iblks[ib].first, nr = iblks[ib].second;
-        GemmDesc e;
-        e.A = view3d(Loo, ch->ldoo, (long)ch->no * ch->ldoo, (int)naux, nr, ch->no, i0, 0);
-        e.B = view3d(R, ldj, (long)v2off * ldj, (int)(nvec * naux), v2off, ch->no);
-        e.M = nr; e.N = v2off; e.K = ch->no; e.nouter = (int)naux; e.batches = nvec; e.z_div = 1; e.a_hi = 0; e.b_hi = (int)naux;
-        e.C = h->SIG + h->sig_base[k.ch] + (long)i0 * ch->ldz; e.ldc = ch->ldz; e.c_batch_stride = (long)ch->no * ch->ldz;
-        e.accumulate = true;
-        XTD_TRY(gemm(h->gemm, e, s));
-      }
+      // (rows of Lvv gathered per aux function, first output column, width, column block whose weights apply)
+      struct Narrow { const double* L; int col0, w, ab; };
+      std::vector<Narrow> passes;
+      passes.push_back({ch->Lvo[k.tensor].p, 0, v2off, 0});
+      if (ch->tail_w > 0) passes.push_back({ch->Lvt[k.tensor].p, ch->tail_start, ch->tail_w, 1});
+      for (const Narrow& nw : passes)
+        for (size_t ib = 0; ib < iblks.size(); ++ib) {
+          PhaseTimer t(h, XTD_T_K1);
+          BlockSplit bs;                       // the kernel is written for the transposed layout: roles of rows / columns swap
+          bs.o2off = v2off; bs.v2off = o2off;
+          for (int j = 0; j < 2; ++j)
+            for (int b = 0; b < 2; ++b) bs.w[b][j] = k.w[ib][nw.ab][j < k.nob ? j : 0][b < k.nvb ? b : 0];
+          scale_blocks_kernel<<<dim3((unsigned)cdiv(ch->nv, 128), ch->no, nvec), 128, 0, s>>>(Zs, h->Z[k.ch], ch->ldz, (long)ch->no * ch->ldz,
+                                                                                            ch->no, ch->nv, bs);
+          LAUNCH_CHECK();
+          GemmDesc d;
+          d.A = view2d(nw.L, ch->ldvv, (int)(naux * nw.w), ch->nv);
+          d.B = view3d(Zs, ch->ldz, (long)ch->no * ch->ldz, nvec, ch->no, ch->nv);
+          d.M = (int)(naux * nw.w); d.N = ch->no; d.K = ch->nv; d.batches = nvec; d.z_div = 1; d.a_hi = 0; d.b_hi = 1;
+          d.C = R; d.ldc = ldj; d.c_batch_stride = naux * nw.w * ldj;
+          XTD_TRY(gemm(h->gemm, d, s));
+          const int i0 = iblks[ib].first, nr = iblks[ib].second;
+          GemmDesc e;
+          e.A = view3d(Loo, ch->ldoo, (long)ch->no * ch->ldoo, (int)naux, nr, ch->no, i0, 0);
+          e.B = view3d(R, ldj, (long)nw.w * ldj, (int)(nvec * naux), nw.w, ch->no);
+          e.M = nr; e.N = nw.w; e.K = ch->no; e.nouter = (int)naux; e.batches = nvec; e.z_div = 1; e.a_hi = 0; e.b_hi = (int)naux;
+          e.C = h->SIG + h->sig_base[k.ch] + (long)i0 * ch->ldz + nw.col0; e.ldc = ch->ldz; e.c_batch_stride = (long)ch->no * ch->ldz;
+          e.accumulate = true;
+          XTD_TRY(gemm(h->gemm, e, s));
+        }
       ab_first = 1;
+      if (ch->tail_w > 0) ablks[1].second = ch->tail_start - v2off;     // the general pass stops at the last full 128-column tile
     }
     for (size_t ab = ab_first; ab < ablks.size(); ++ab) {
       for (long P0 = 0; P0 < naux; P0 += pc) {
