@@ -32,6 +32,7 @@ typedef struct {
   double flops_gemm;          /* useful FP64 flops issued through the DMMA GEMM since the last reset */
   unsigned long long launches; /* kernels launched by this library since the last reset */
   double ms[12];              /* device time per phase of the last xtd_sigma* call (see XTD_T_* below) */
+  double flops[12];           /* DMMA GEMM flops issued inside each phase of the last xtd_sigma* call */
 } xtd_stats;
 enum { XTD_T_PACK = 0, XTD_T_XC_GEMM = 1, XTD_T_XC_STREAM = 2, XTD_T_K1 = 3, XTD_T_K2 = 4, XTD_T_J = 5,
        XTD_T_LOCAL = 6, XTD_T_UNPACK = 7, XTD_T_TOTAL = 8 };

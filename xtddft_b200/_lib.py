@@ -17,7 +17,7 @@ class XtdError(RuntimeError):
 
 
 class XtdStats(C.Structure):
-    _fields_ = [("flops_gemm", C.c_double), ("launches", C.c_ulonglong), ("ms", C.c_double * 12)]
+    _fields_ = [("flops_gemm", C.c_double), ("launches", C.c_ulonglong), ("ms", C.c_double * 12), ("flops", C.c_double * 12)]
 
 
 _P = C.c_void_p

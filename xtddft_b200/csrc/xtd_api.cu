@@ -167,6 +167,7 @@ struct xtd_engine {
   bool ev_ok = false;
   unsigned long long launches0 = 0;
   double flops0 = 0;
+  double phase_flops[12] = {0};   // GEMM flops per phase of the last call
   // XTD_PROFILE_PHASE=<XTD_T_* id>: cudaProfilerStart/Stop around that phase (ncu --profile-from-start off)
   int prof_phase = -1;
 };
@@ -176,7 +177,9 @@ namespace {
 struct PhaseTimer {
   xtd_engine* h;
   size_t slot = (size_t)-1;
-  PhaseTimer(xtd_engine* h_, int id) : h(h_) {
+  int phase;
+  double f0;
+  PhaseTimer(xtd_engine* h_, int id) : h(h_), phase(id), f0(h_->gemm.flops) {
     if (!h->ev_ok) return;
     if (h->ev_used == h->evpool.size()) {
       if (h->evpool.size() >= 4096) return;
@@ -192,6 +195,7 @@ struct PhaseTimer {
     cudaEventRecord(h->evpool[slot].a, h->stream);
   }
   ~PhaseTimer() {
+    h->phase_flops[phase] += h->gemm.flops - f0;
     if (slot == (size_t)-1) return;
     cudaEventRecord(h->evpool[slot].b, h->stream);
     if (h->evpool[slot].id == h->prof_phase) cudaProfilerStop();
@@ -1231,6 +1235,7 @@ int xtd_sigma_partial(xtd_handle h, int nvec, const double* z_dev) {
   XTD_REQUIRE(nvec >= 1 && nvec <= h->max_nvec && z_dev, XTD_ERR_ARG, "xtd_sigma: nvec %d outside 1..%d", nvec, h->max_nvec);
   cudaStream_t s = h->stream;
   h->ev_used = 0;
+  for (int i = 0; i < 12; ++i) h->phase_flops[i] = 0.0;
   if (h->prof_phase == XTD_T_TOTAL) cudaProfilerStart();
   if (h->ev_ok) cudaEventRecord(h->ev_total[0], s);
   XTD_TRY(setup_call_buffers(h, nvec));
@@ -1323,7 +1328,7 @@ int xtd_get_stats(xtd_handle h, xtd_stats* out) {
   XTD_CUDA(cudaStreamSynchronize(h->stream));
   out->flops_gemm = h->gemm.flops - h->flops0;
   out->launches = g_launch_count - h->launches0;
-  for (int i = 0; i < 12; ++i) out->ms[i] = 0.0;
+  for (int i = 0; i < 12; ++i) { out->ms[i] = 0.0; out->flops[i] = h->phase_flops[i]; }
   for (size_t i = 0; i < h->ev_used; ++i) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, h->evpool[i].a, h->evpool[i].b) == cudaSuccess) out->ms[h->evpool[i].id] += ms;

@@ -288,7 +288,8 @@ class SigmaEngine:
     def stats(self) -> dict:
         st = _lib.XtdStats()
         _lib.check(self.lib.xtd_get_stats(self._h, C.byref(st)), "xtd_get_stats")
-        return dict(flops_gemm=st.flops_gemm, launches=int(st.launches), ms={n: st.ms[i] for i, n in enumerate(_lib.T_NAMES)})
+        return dict(flops_gemm=st.flops_gemm, launches=int(st.launches), ms={n: st.ms[i] for i, n in enumerate(_lib.T_NAMES)},
+                    flops={n: st.flops[i] for i, n in enumerate(_lib.T_NAMES)})
 
     def reset_stats(self):
         _lib.check(self.lib.xtd_reset_stats(self._h), "xtd_reset_stats")

@@ -126,7 +126,7 @@ def molecular_orbital_energies(rng, nc: int, no: int, nv: int) -> np.ndarray:
 
 def make_device_problem(cfg: int, scale: float = 1.0, seed: Optional[int] = None, grid_components: Optional[int] = None,
                         spectrum: str = "molecular", open_shift: float = 0.1, coupling: float = 0.2, fock_noise: float = 0.005,
-                        xc_scale: float = 1.0, **over) -> DeviceProblem:
+                        xc_scale: float = 1.0, hf_exchange: Optional[float] = None, **over) -> DeviceProblem:
     """Host-side small data + scales for BASELINE config `cfg` (optionally shrunk by `scale`).
 
     spectrum: "molecular" (default, see molecular_orbital_energies) or "uniform" (the SURVEY 8d T0 ladder U(-1,-0.3) /
@@ -153,7 +153,14 @@ def make_device_problem(cfg: int, scale: float = 1.0, seed: Optional[int] = None
     shift[nc:nc + no] = open_shift
     fb = fb + np.diag(shift)
     roks_e = 0.5 * (fa.diagonal() + fb.diagonal())
-    fock_hf = np.stack([fa + _sym_noise(rng, nmo, 0.05), fb + _sym_noise(rng, nmo, 0.05)])
+    # ROHF-form Fock matrices (XTDA.py:588-613, XSF_TDA.py:1096-1121).  Their spin difference F^b - F^a is the exchange
+    # field of the open shells: positive semidefinite, a few tenths of a Hartree, dominated by a handful of directions --
+    # not a dense random matrix (whose norm would grow like sqrt(nmo) and swamp the orbital gaps).
+    hf_a = fa + _sym_noise(rng, nmo, fock_noise)
+    nk = no + 3
+    q, _ = np.linalg.qr(rng.standard_normal((nmo, nk)))
+    lam = rng.uniform(0.03, 0.15, nk) if hf_exchange is None else np.full(nk, hf_exchange)
+    fock_hf = np.stack([hf_a, hf_a + np.diag(shift) + (q * lam) @ q.T])
     method = c["method"]
     fxc_kind = {"xtda": "uks", "sf_down": "alda0", "sf_up": "alda0", "xsf": "alda0"}[method]
     # ALDA0 needs only the density component of the AO values (SF_TDA.py:114-116)
