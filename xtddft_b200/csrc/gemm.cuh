@@ -148,6 +148,13 @@ __device__ __forceinline__ void dmma_consume(const GemmKernelParams& p, uint8_t*
                                              int tile_m, int tile_n, int zb, int sp, long it0, long it1) {
   const int g = lane >> 2, t = lane & 3;
   const int wm = (warp % WM) * (8 * IT), wn = (warp / WM) * (8 * JT);
+  // K-strided operand tiles: fragment address = one lane-dependent register + a compile-time constant per (i, kk); the
+  // swizzle XOR is split into its lane bits and its (i, kk) bits by hand (left to the compiler these variants spilled):
+  //   frag_off<false>(r, k) = (r>>4)*2048 + k*128 + ((((r&15)>>1) ^ (k&7)) << 4) + ((r&1) << 3),   r = w + 8 i + g,  k = 4 kk + t
+  //     = [(w>>4)*2048 + t*128 + (((g>>1)^t) << 4) + ((g&1)<<3)]  +  (i>>1)*2048 + kk*512 + (((i&1)^(kk&1)) << 6)
+  // (warp tiles start on multiples of 16 rows in every layout).  K-contiguous tiles keep frag_off<true>.
+  const uint32_t a_lane = (uint32_t)((wm >> 4) * 2048 + t * 128 + ((((g >> 1) ^ t) & 3) << 4) + ((g & 1) << 3));
+  const uint32_t b_lane = (uint32_t)((wn >> 4) * 2048 + t * 128 + ((((g >> 1) ^ t) & 3) << 4) + ((g & 1) << 3));
   double acc[IT][JT][2];
 #pragma unroll
   for (int i = 0; i < IT; ++i)
@@ -166,9 +173,13 @@ __device__ __forceinline__ void dmma_consume(const GemmKernelParams& p, uint8_t*
     for (int kk = 0; kk < BK / 4; ++kk) {
       double a[IT], b[JT];
 #pragma unroll
-      for (int i = 0; i < IT; ++i) a[i] = lds_f64(sa + frag_off<A_KC>(wm + i * 8 + g, kk * 4 + t));
+      for (int i = 0; i < IT; ++i)
+        a[i] = A_KC ? lds_f64(sa + frag_off<true>(wm + i * 8 + g, kk * 4 + t))
+                    : lds_f64(sa + a_lane + ((i >> 1) * 2048 + kk * 512 + (((i & 1) ^ (kk & 1)) << 6)));
 #pragma unroll
-      for (int j = 0; j < JT; ++j) b[j] = lds_f64(sb + frag_off<B_KC>(wn + j * 8 + g, kk * 4 + t));
+      for (int j = 0; j < JT; ++j)
+        b[j] = B_KC ? lds_f64(sb + frag_off<true>(wn + j * 8 + g, kk * 4 + t))
+                    : lds_f64(sb + b_lane + ((j >> 1) * 2048 + kk * 512 + (((j & 1) ^ (kk & 1)) << 6)));
 #pragma unroll
       for (int i = 0; i < IT; ++i)
 #pragma unroll
