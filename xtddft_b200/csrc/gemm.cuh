@@ -9,7 +9,7 @@
 // contraction index is the row index: "row-major K x M").  The second contraction level (q) lets one launch
 // accumulate over e.g. all auxiliary functions P of a density-fitting block:  sum_P sum_b U[P,i,b] L[P,a,b].
 //
-// Tile 128x128x16 doubles, 5 stages of 32 KB, warp tile 64x32 (8x4 DMMA tiles, 64 accumulator doubles per
+// Tile 128x128x16 doubles, 6 stages of 32 KB, warp tile 64x32 (8x4 DMMA tiles, 64 accumulator doubles per
 // thread).  Shared-memory tiles are written by TMA with the 128-byte swizzle; fragment loads undo it.
 // Measured ceiling on B200 for this instruction mix: 37.1 TFLOP/s (profiles/fp64_peaks_r01.json).
 #pragma once
