@@ -776,7 +776,6 @@ int xtd_finalize(xtd_handle h, int max_nvec) {
 // ---------------------------------------------------------------------------------------------------------
 static int setup_call_buffers(xtd_engine* h, int nvec) {
   h->arena.used = 0;
-  const bool xc = (h->fxc_kind != XTD_FXC_NONE) && h->ng > 0;
   long base[2], total;
   sig_layout(h, nvec, base, &total);
   h->SIG = h->arena.take((size_t)total);
