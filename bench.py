@@ -356,6 +356,13 @@ def main():
                            "cuBLAS DGEMM on the same box: 35.4 TFLOP/s)",
             "flops_per_launch_group": k2_flops, "ms_per_step_in_kernel": gemm_ms,
             "all_gemm_flops_per_step": flops / args.steps, "all_gemm_tflops_over_step": flops / args.steps / (ms_step * 1e-3) / 1e12}
+    # the same exchange build counted with the REFERENCE algorithm's flops (tagged DF-K in the AO basis,
+    # 4 naux N^2 nocc per vector and spin block) over the time this build spends on it (K1 + K2): throughput-equivalent
+    ref_flops = sum(4.0 * (dp.naux // world + (1 if rank < dp.naux % world else 0)) * p.nao ** 2 * eng.plan.channels[kt.ch].no * nvec
+                    for kt in eng.plan.k_terms)
+    k_ms = (phase.get("k1", 0.0) + phase.get("k2", 0.0)) / args.steps
+    roof["reference_algorithm_flops_per_step"] = ref_flops
+    roof["reference_algorithm_tflops_equivalent"] = (ref_flops / (k_ms * 1e-3) / 1e12) if k_ms > 0 else None
     # ---- streaming kernel of the grid path (xc_weight_kernel) against HBM bandwidth --------------------------
     roof_xc = None
     xs_ms = phase.get("xc_stream", 0.0) / args.steps
