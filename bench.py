@@ -43,12 +43,13 @@ def _hbm_peak():
 HBM_PEAK_GBS, HBM_PEAK_SOURCE = _hbm_peak()
 
 
-def _ncu_traffic(workload: str, key: str):
+def _ncu_traffic(workload: str, key: str, field: str = "traffic_bytes_per_launch"):
     """DRAM bytes per launch of the named kernel from the committed `ncu --set full` capture of this workload
     (profiles/ncu_traffic_r01.json), or None when no capture of this workload exists."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")) as f:
-            return float(json.load(f)[workload][key]["traffic_bytes_per_launch"])
+            v = json.load(f)[workload][key][field]
+            return float(v) if field == "traffic_bytes_per_launch" else v
     except Exception:
         return None
 
@@ -361,6 +362,9 @@ def main():
     ref_flops = sum(4.0 * (dp.naux // world + (1 if rank < dp.naux % world else 0)) * p.nao ** 2 * eng.plan.channels[kt.ch].no * nvec
                     for kt in eng.plan.k_terms)
     k_ms = (phase.get("k1", 0.0) + phase.get("k2", 0.0)) / args.steps
+    if roof["traffic"] is not None:
+        # `traffic` is per LAUNCH (one aux chunk) as ncu reports it; the launch it was captured on, for comparison
+        roof["traffic_captured_launch"] = _ncu_traffic(dp.name, "k2", "captured_launch")
     roof["reference_algorithm_flops_per_step"] = ref_flops
     roof["reference_algorithm_tflops_equivalent"] = (ref_flops / (k_ms * 1e-3) / 1e12) if k_ms > 0 else None
     # ---- streaming kernel of the grid path (xc_weight_kernel) against HBM bandwidth --------------------------
