@@ -237,6 +237,10 @@ dgemm_dmma_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   const int qa = p.a_q0 + hi * p.a_hi + lo * p.a_lo;
   const int qb = p.b_q0 + hi * p.b_hi + lo * p.b_lo;
 
+  if (threadIdx.x == CONSUMER_WARPS * 32) {   // the producer lane: fetch both tensor maps while the barriers are set up
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
