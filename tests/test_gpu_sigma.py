@@ -236,3 +236,37 @@ def test_meta_gga(torch_cuda, nc, no, nv, restricted):
         eng = _engine(planmod.build_sf_plan(p, isf=-1, method=method), p, max_nvec=8)
         _check(torch_cuda, eng, vind, hd.size, nvec=5)
         eng.close()
+
+
+@pytest.mark.parametrize("method", ["xtda", "xsf"])
+def test_graph_replay(torch_cuda, method):
+    """Launch-bound calls are replayed as CUDA graphs from the third call with the same buffers on (eager, capture, replay):
+    every call must read the CURRENT contents of the trial-vector buffer and count its launches; a different vector
+    count or buffer falls back to the eager path."""
+    torch = torch_cuda
+    p = make_problem(26, 6, 2, 18, 15, 200, xctype="GGA", hyb=0.3, seed=240)
+    if method == "xtda":
+        vind, hd = osig.xtda_gen_vind(p)
+        plan = planmod.build_xtda_plan(p)
+    else:
+        vind, hd = osig.xsf_gen_vind(p, sa=3, method=0, remove=True)
+        plan = planmod.build_sf_plan(p, isf=-1, method=0, sa=3, layout=planmod.LAYOUT_BLOCK, remove=True, hdiag_kind="xsf")
+    eng = _engine(plan, p, max_nvec=8)
+    z = torch.zeros((3, hd.size), dtype=torch.float64, device="cuda")
+    out = torch.empty_like(z)
+    launches = []
+    for it in range(5):
+        zh = np.random.default_rng(it).standard_normal((3, hd.size))
+        z.copy_(torch.from_numpy(zh))
+        eng.reset_stats()
+        eng.sigma(z, out)
+        ref = vind(zh)
+        assert np.abs(out.cpu().numpy() - ref).max() < RTOL * max(1.0, np.abs(ref).max()), it
+        st = eng.stats()
+        launches.append(st["launches"])
+        assert st["ms"]["total"] > 0
+    assert len(set(launches)) == 1 and launches[0] > 10, launches          # replays account for the recorded launches
+    assert eng.stats()["ms"]["k2"] == 0.0                                   # graph replay: only the total is timed
+    # other shapes / buffers still work (eager)
+    _check(torch, eng, vind, hd.size, nvec=2, seed=9)
+    eng.close()

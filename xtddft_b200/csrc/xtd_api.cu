@@ -170,6 +170,19 @@ struct xtd_engine {
   double phase_flops[12] = {0};   // GEMM flops per phase of the last call
   // XTD_PROFILE_PHASE=<XTD_T_* id>: cudaProfilerStart/Stop around that phase (ncu --profile-from-start off)
   int prof_phase = -1;
+  // Launch-bound calls (small molecules: ~50-100 launches of a few microseconds each) are replayed as CUDA graphs: the
+  // first call with a given (nvec, z, hz) runs eagerly, the second is captured, later ones are one cudaGraphLaunch.
+  struct GraphRec {
+    int nvec; const double* z; double* hz;
+    cudaGraphExec_t exec;
+    unsigned long long launches; double flops; double phase_flops[12];
+  };
+  std::vector<GraphRec> graphs;
+  int graph_mode = -1;            // XTD_GRAPH: 0 never, 1 always, unset: when a call issues < 2e10 GEMM flops
+  bool capturing = false;
+  cudaStream_t cap_stream = nullptr;   // calls are recorded on this stream (the caller's may be the legacy default stream,
+                                       // which cannot be captured) and replayed on the caller's
+  int last_eager_nvec = 0; const double* last_eager_z = nullptr; double* last_eager_hz = nullptr; double last_eager_flops = 0;
 };
 
 namespace {
@@ -180,7 +193,7 @@ struct PhaseTimer {
   int phase;
   double f0;
   PhaseTimer(xtd_engine* h_, int id) : h(h_), phase(id), f0(h_->gemm.flops) {
-    if (!h->ev_ok) return;
+    if (!h->ev_ok || h->capturing) return;
     if (h->ev_used == h->evpool.size()) {
       if (h->evpool.size() >= 4096) return;
       xtd_engine::EvRec r;
@@ -367,6 +380,7 @@ int xtd_create(xtd_handle* out, int nao, long workspace_bytes) {
   cudaEventCreate(&h->ev_total[1]);
   h->ev_ok = true;
   if (const char* e = getenv("XTD_PROFILE_PHASE")) h->prof_phase = atoi(e);
+  if (const char* e = getenv("XTD_GRAPH")) h->graph_mode = atoi(e);
   *out = h;
   return XTD_OK;
 }
@@ -391,6 +405,8 @@ int xtd_destroy(xtd_handle h) {
   if (h->s_offs) cudaFree(h->s_offs);
   if (h->s_chans) cudaFree(h->s_chans);
   if (h->s_vals) cudaFree(h->s_vals);
+  for (auto& g : h->graphs) cudaGraphExecDestroy(g.exec);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   if (h->arena.base) cudaFree(h->arena.base);
   if (h->pin_in) cudaFreeHost(h->pin_in);
   if (h->pin_out) cudaFreeHost(h->pin_out);
@@ -1235,8 +1251,8 @@ int xtd_sigma_partial(xtd_handle h, int nvec, const double* z_dev) {
   cudaStream_t s = h->stream;
   h->ev_used = 0;
   for (int i = 0; i < 12; ++i) h->phase_flops[i] = 0.0;
-  if (h->prof_phase == XTD_T_TOTAL) cudaProfilerStart();
-  if (h->ev_ok) cudaEventRecord(h->ev_total[0], s);
+  if (h->prof_phase == XTD_T_TOTAL && !h->capturing) cudaProfilerStart();
+  if (h->ev_ok && !h->capturing) cudaEventRecord(h->ev_total[0], s);
   XTD_TRY(setup_call_buffers(h, nvec));
   long base[2], total;
   sig_layout(h, nvec, base, &total);
@@ -1288,14 +1304,74 @@ int xtd_sigma_finish(xtd_handle h, int nvec, double* hz_dev) {
                                                                              h->s_vals, h->SIG, uc);
     LAUNCH_CHECK();
   }
+  if (h->ev_ok && !h->capturing) cudaEventRecord(h->ev_total[1], s);
+  if (h->prof_phase == XTD_T_TOTAL && !h->capturing) cudaProfilerStop();
+  return XTD_OK;
+}
+
+static int sigma_eager(xtd_handle h, int nvec, const double* z_dev, double* hz_dev) {
+  XTD_TRY(xtd_sigma_partial(h, nvec, z_dev));
+  return xtd_sigma_finish(h, nvec, hz_dev);
+}
+
+static int launch_graph(xtd_engine* h, const xtd_engine::GraphRec& g) {
+  cudaStream_t s = h->stream;
+  h->ev_used = 0;                                    // no per-phase events inside a graph: only the total is timed
+  if (h->ev_ok) cudaEventRecord(h->ev_total[0], s);
+  XTD_CUDA(cudaGraphLaunch(g.exec, s));
   if (h->ev_ok) cudaEventRecord(h->ev_total[1], s);
-  if (h->prof_phase == XTD_T_TOTAL) cudaProfilerStop();
+  for (int i = 0; i < 12; ++i) h->phase_flops[i] = g.phase_flops[i];
+  h->cur_nvec = g.nvec;
   return XTD_OK;
 }
 
 int xtd_sigma(xtd_handle h, int nvec, const double* z_dev, double* hz_dev) {
-  XTD_TRY(xtd_sigma_partial(h, nvec, z_dev));
-  return xtd_sigma_finish(h, nvec, hz_dev);
+  XTD_REQUIRE(h && h->finalized, XTD_ERR_STATE, "xtd_sigma before xtd_finalize");
+  if (h->graph_mode == 0 || h->prof_phase >= 0) return sigma_eager(h, nvec, z_dev, hz_dev);
+  for (const auto& g : h->graphs)
+    if (g.nvec == nvec && g.z == z_dev && g.hz == hz_dev) {
+      g_launch_count += g.launches;                  // the kernels of the recorded call run again
+      h->gemm.flops += g.flops;
+      return launch_graph(h, g);
+    }
+  // second call with the same arguments, and the first one was launch-bound (or graphs are forced): capture it
+  const bool repeat = h->last_eager_nvec == nvec && h->last_eager_z == z_dev && h->last_eager_hz == hz_dev;
+  if (repeat && (h->graph_mode == 1 || h->last_eager_flops < 2e10) && h->graphs.size() < 64) {
+    if (!h->cap_stream && cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess) h->cap_stream = nullptr;
+    cudaStream_t s = h->cap_stream, user_stream = h->stream;
+    const unsigned long long l0 = g_launch_count;
+    const double f0 = h->gemm.flops;
+    cudaGraph_t graph = nullptr;
+    if (s && cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      h->capturing = true;
+      h->stream = s;
+      const int rc = sigma_eager(h, nvec, z_dev, hz_dev);
+      h->stream = user_stream;
+      h->capturing = false;
+      const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+      xtd_engine::GraphRec g;
+      g.nvec = nvec; g.z = z_dev; g.hz = hz_dev; g.exec = nullptr;
+      g.launches = g_launch_count - l0; g.flops = h->gemm.flops - f0;
+      for (int i = 0; i < 12; ++i) g.phase_flops[i] = h->phase_flops[i];
+      if (rc == XTD_OK && ce == cudaSuccess && graph && cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess) {
+        cudaGraphDestroy(graph);
+        h->graphs.push_back(g);
+        return launch_graph(h, h->graphs.back());    // the capture recorded the work without running it: run it now
+      }
+      // capture not possible for this call: undo the bookkeeping, never try again, run eagerly
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      g_launch_count = l0; h->gemm.flops = f0;
+      h->graph_mode = 0;
+    } else {
+      cudaGetLastError();
+      h->graph_mode = 0;
+    }
+  }
+  const double f0 = h->gemm.flops;
+  const int rc = sigma_eager(h, nvec, z_dev, hz_dev);
+  h->last_eager_nvec = nvec; h->last_eager_z = z_dev; h->last_eager_hz = hz_dev; h->last_eager_flops = h->gemm.flops - f0;
+  return rc;
 }
 
 int xtd_sigma_host(xtd_handle h, int nvec, const double* z_host, double* hz_host) {
