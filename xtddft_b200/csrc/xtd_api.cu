@@ -1154,7 +1154,9 @@ static int run_j(xtd_engine* h, int nvec) {
   // Coulomb steps are plain GEMMs over the flattened pair index (the streaming kernels re-read all trial vectors from L2
   // once per aux function); sub-blocks (XSF Delta A) keep the streaming kernels.
   const bool no_gemm = getenv("XTD_J_STREAM") != nullptr;
-  auto flat = [&](const JBlockRec* j) { return !no_gemm && j->c0 == 0 && j->ld == h->ch[j->ch]->ldz; };
+  auto flat = [&](const JBlockRec* j) {      // (the flattened pair index is the N dimension of the second GEMM: grid.y limit)
+    return !no_gemm && j->c0 == 0 && j->ld == h->ch[j->ch]->ldz && (long)j->nr * j->ld <= 65535L * 128;
+  };
   for (int b = 0; b < njb; ++b) {
     JBlockRec* j = h->jblocks[b];
     Channel* ch = h->ch[j->ch];
