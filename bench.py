@@ -408,7 +408,12 @@ def main():
     if dav is not None:
         out_json["davidson"] = dav
     if world == 1 and not args.no_cpu_baseline:
-        out_json["cpu_baseline"] = cpu_reference_rate(dp)
+        cb = cpu_reference_rate(dp)
+        if dav is not None and cb.get("value"):
+            # the CPU time-to-roots is EXTRAPOLATED from the CPU rate and the sigma-vector count of the
+            # solve above (the CPU never runs the full solve)
+            cb["time_to_roots_s_extrapolated"] = dav["sigma_vectors"] / cb["value"]
+        out_json["cpu_baseline"] = cb
     emit(out_json)
     if world > 1:
         torch.distributed.destroy_process_group()
