@@ -114,6 +114,9 @@ int xtd_reset_stats(xtd_handle h);
 /* which GEMM arrangement the grid path uses for nvec vectors: 1 = split-gradient form (value GEMM on either side of the
  * orbital product, gradient halves streamed), 0 = one GEMM per AO component.  Used by the bench to count streamed bytes. */
 int xtd_xc_split_form(xtd_handle h, int nvec);
+/* how many auxiliary-function chunks (exchange build) and grid chunks the last eager xtd_sigma* call looped over; the
+ * environment variables XTD_CHUNK_AUX / XTD_CHUNK_GRID (read by xtd_create) bound the chunk sizes from above */
+int xtd_last_chunks(xtd_handle h, long* aux_chunks, long* grid_chunks);
 
 /* Davidson subspace algebra on device vectors (Davidson.py:152-271): all row vectors of length n */
 int xtd_vec_dots(void* stream, double* g_dev, int ldg, const double* a_dev, long lda, int m, const double* b_dev, long ldb, int k, long n);

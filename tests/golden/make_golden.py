@@ -30,6 +30,7 @@ import types
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.environ.get("XTD_GOLDEN_OUT", HERE)      # tests regenerate into a temporary directory and diff
 ROOT = os.path.dirname(os.path.dirname(HERE))
 REF = "/root/reference"
 sys.path.insert(0, ROOT)
@@ -485,7 +486,7 @@ def main():
     for no in (2, 3, 4):
         dummy = types.SimpleNamespace(no=no)
         helpers[f"vects_{no}"] = R["XSF_TDA"].XSF_TDA.get_vect(dummy)
-    np.savez(os.path.join(HERE, "helpers.npz"), **helpers)
+    np.savez(os.path.join(OUT, "helpers.npz"), **helpers)
 
     # ---- X-TDA (XTDA.py) ---------------------------------------------------------------------
     xtda_cases = [
@@ -509,7 +510,7 @@ def main():
         z = rand_vectors(c["seed"] + 100, 3, dim)
         hx = vind(z)
         x0 = obj.get_init_guess(mf, 3)
-        np.savez(os.path.join(HERE, f"xtda_{c['tag']}.npz"), z=z, hx=hx, hdiag=hdiag, x0=x0,
+        np.savez(os.path.join(OUT, f"xtda_{c['tag']}.npz"), z=z, hx=hx, hdiag=hdiag, x0=x0,
                  params=np.array([c["nc"], c["no"], c["nv"], c["naux"], c["ng"], c["seed"], int(c["restricted"])]),
                  xctype=c["xctype"], hyb=c["hyb"])
         print("xtda", c["tag"], dim, float(np.abs(hx).max()))
@@ -537,7 +538,7 @@ def main():
             v = rand_vectors(5, hdiag.size, 2)
             extra["deal_in"] = v
             extra["deal_out"] = R["SF_TDA"].deal_v_davidson(mf, 2, v)
-        np.savez(os.path.join(HERE, f"sf_{c['tag']}.npz"), z=z, hx=hx, hdiag=hdiag, x0=x0, fxc_alda0=fxc_alda0,
+        np.savez(os.path.join(OUT, f"sf_{c['tag']}.npz"), z=z, hx=hx, hdiag=hdiag, x0=x0, fxc_alda0=fxc_alda0,
                  params=np.array([c["nc"], c["no"], c["nv"], c["naux"], c["ng"], c["seed"], int(c["restricted"]), c["isf"]]),
                  xctype=c["xctype"], hyb=c["hyb"], **extra)
         print("sf", c["tag"], hdiag.size, float(np.abs(hx).max()))
@@ -549,7 +550,7 @@ def main():
     z = rand_vectors(125, 2, p.nocc_a * p.nvir_b).reshape(2, p.nocc_a, p.nvir_b)
     dms = np.einsum("xov,qv,po->xpq", z, cv, co)
     v_mc = R["SF_TDA"].nr_uks_fxc_sf_tda_mc(mf._numint, mf.mol, mf.grids, mf.xc, None, dms, 0, 0, None, None, p.fxc_mcol)
-    np.savez(os.path.join(HERE, "sf_mcol_contraction.npz"), dms=dms, v=v_mc, params=np.array([3, 2, 4, 10, 36, 25]))
+    np.savez(os.path.join(OUT, "sf_mcol_contraction.npz"), dms=dms, v=v_mc, params=np.array([3, 2, 4, 10, 36, 25]))
     # ... and its meta-GGA branch (tau component of the kernel, SF_TDA.py:1028-1040)
     p = make_problem(9, 3, 2, 4, 10, 36, xctype="MGGA", hyb=0.5, seed=27)
     mf = FakeROKS(p)
@@ -557,7 +558,7 @@ def main():
     z = rand_vectors(127, 2, p.nocc_a * p.nvir_b).reshape(2, p.nocc_a, p.nvir_b)
     dms = np.einsum("xov,qv,po->xpq", z, cv, co)
     v_mc = R["SF_TDA"].nr_uks_fxc_sf_tda_mc(mf._numint, mf.mol, mf.grids, mf.xc, None, dms, 0, 0, None, None, p.fxc_mcol)
-    np.savez(os.path.join(HERE, "sf_mcol_contraction_mgga.npz"), dms=dms, v=v_mc, params=np.array([3, 2, 4, 10, 36, 27]))
+    np.savez(os.path.join(OUT, "sf_mcol_contraction_mgga.npz"), dms=dms, v=v_mc, params=np.array([3, 2, 4, 10, 36, 27]))
 
     # ---- XSF-TDA (XSF_TDA.py, block layout) ----------------------------------------------------------
     for (tagname, nc, no, nv, xct, seed) in [("gga_no2", 3, 2, 4, "GGA", 31), ("lda_no3", 2, 3, 3, "LDA", 32)]:
@@ -579,7 +580,7 @@ def main():
         # default fglobal rule (XSF_TDA.py:1511-1518) and init guess
         obj = R["XSF_TDA"].XSF_TDA(mf, SA=3)
         res["x0"] = obj._build_initial_guess_from_gaps(res["hdiag_sa3_re1"], 3)
-        np.savez(os.path.join(HERE, f"xsf_{tagname}.npz"), **res)
+        np.savez(os.path.join(OUT, f"xsf_{tagname}.npz"), **res)
         print("xsf", tagname, float(np.abs(res["hx_sa3_re1"]).max()))
 
     # ---- XSF-TDA GPU class (PySCF order; NumPy stands in for CuPy) -----------------------------
@@ -605,7 +606,7 @@ def main():
         vind, hdiag = obj.gen_vind()
         z = rand_vectors(seed + 200, 2, hdiag.size)
         res["z_up"], res["hx_up"], res["hdiag_up"] = z, np.asarray(vind(z)), np.asarray(hdiag)
-        np.savez(os.path.join(HERE, f"xsfgpu_{tagname}.npz"), **res)
+        np.savez(os.path.join(OUT, f"xsfgpu_{tagname}.npz"), **res)
         print("xsfgpu", tagname, float(np.abs(res["hx_X3_re1"]).max()))
 
 

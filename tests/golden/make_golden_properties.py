@@ -19,6 +19,7 @@ import types
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.environ.get("XTD_GOLDEN_OUT", HERE)      # tests regenerate into a temporary directory and diff
 sys.path.insert(0, HERE)
 import make_golden as mg  # noqa: E402
 
@@ -140,7 +141,7 @@ def main():
         out[f"{tag}_pab"] = np.array([float(XS.deltaS2_U(s, k)) for k in range(ns)])
         print(tag, out[f"{tag}_osc"][0], out[f"{tag}_pab"])
 
-    np.savez(os.path.join(HERE, "properties.npz"), **out)
+    np.savez(os.path.join(OUT, "properties.npz"), **out)
 
 
 if __name__ == "__main__":

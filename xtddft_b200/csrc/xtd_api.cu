@@ -22,14 +22,20 @@ namespace xtd {
 thread_local char g_last_error[512] = {0};
 unsigned long long g_launch_count = 0;
 
+// Owned device buffer, zero-filled on the stream whose kernels will fill it (a cudaMemset on the legacy stream is not
+// ordered against work on a non-blocking side stream and could land after the producer's output).
 struct DevBuf {
   double* p = nullptr;
   size_t bytes = 0;
-  int alloc(size_t n_doubles) {
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  int alloc(size_t n_doubles, cudaStream_t s) {
     release();
     bytes = std::max<size_t>(n_doubles, 2) * 8;
     XTD_CUDA(cudaMalloc(&p, bytes));
-    XTD_CUDA(cudaMemset(p, 0, bytes));
+    XTD_CUDA(cudaMemsetAsync(p, 0, bytes, s));
     return XTD_OK;
   }
   void release() {
@@ -170,6 +176,10 @@ struct xtd_engine {
   double phase_flops[12] = {0};   // GEMM flops per phase of the last call
   // XTD_PROFILE_PHASE=<XTD_T_* id>: cudaProfilerStart/Stop around that phase (ncu --profile-from-start off)
   int prof_phase = -1;
+  // XTD_CHUNK_AUX / XTD_CHUNK_GRID: upper bounds on the aux / grid chunk of a call (tests force the multi-chunk loops that
+  // BASELINE-size runs take at oracle-sized inputs); the chunk counts of the last call are reported by xtd_last_chunks
+  long max_pc = 0, max_gb = 0;
+  long last_aux_chunks = 0, last_grid_chunks = 0;
   // Launch-bound calls (small molecules: ~50-100 launches of a few microseconds each) are replayed as CUDA graphs: the
   // first call with a given (nvec, z, hz) runs eagerly, the second is captured, later ones are one cudaGraphLaunch.
   struct GraphRec {
@@ -225,18 +235,23 @@ inline dim3 grid1d(long n, int threads, int y = 1, int z = 1) { return dim3((uns
 
 int upload_padded(DevBuf& dst, long& ld, const double* host, int rows, int cols, cudaStream_t s) {
   ld = pad_ld(cols);
-  XTD_TRY(dst.alloc((size_t)std::max(rows, 1) * ld));
-  if (rows > 0 && cols > 0)
-    XTD_CUDA(cudaMemcpy2D(dst.p, ld * 8, host, (size_t)cols * 8, (size_t)cols * 8, rows, cudaMemcpyHostToDevice));
+  XTD_TRY(dst.alloc((size_t)std::max(rows, 1) * ld, s));
+  if (rows > 0 && cols > 0) {      // after the zero fill, on the same stream
+    XTD_CUDA(cudaMemcpy2DAsync(dst.p, ld * 8, host, (size_t)cols * 8, (size_t)cols * 8, rows, cudaMemcpyHostToDevice, s));
+    XTD_CUDA(cudaStreamSynchronize(s));
+  }
   return XTD_OK;
 }
 
 template <typename T>
-int upload_array(T** dst, const T* host, size_t n) {
+int upload_array(T** dst, const T* host, size_t n, cudaStream_t s) {
   if (*dst) cudaFree(*dst);
   *dst = nullptr;
   XTD_CUDA(cudaMalloc((void**)dst, std::max<size_t>(n, 1) * sizeof(T)));
-  if (n) XTD_CUDA(cudaMemcpy(*dst, host, n * sizeof(T), cudaMemcpyHostToDevice));
+  if (n) {
+    XTD_CUDA(cudaMemcpyAsync(*dst, host, n * sizeof(T), cudaMemcpyHostToDevice, s));
+    XTD_CUDA(cudaStreamSynchronize(s));
+  }
   return XTD_OK;
 }
 
@@ -256,13 +271,13 @@ int build_channel_matrices(xtd_engine* h, Channel* c) {
   c->ldco = pad_ld(c->no);
   c->ldcv = pad_ld(c->nv);
   c->ldN = h->ldN;
-  XTD_TRY(c->Co.alloc((size_t)N * c->ldco));
-  XTD_TRY(c->Cv.alloc((size_t)N * c->ldcv));
-  XTD_TRY(c->CoT.alloc((size_t)c->no * c->ldN));
-  XTD_TRY(c->CvT.alloc((size_t)c->nv * c->ldN));
+  XTD_TRY(c->Co.alloc((size_t)N * c->ldco, h->stream));
+  XTD_TRY(c->Cv.alloc((size_t)N * c->ldcv, h->stream));
+  XTD_TRY(c->CoT.alloc((size_t)c->no * c->ldN, h->stream));
+  XTD_TRY(c->CvT.alloc((size_t)c->nv * c->ldN, h->stream));
   int *d_oi = nullptr, *d_vi = nullptr;
-  XTD_TRY(upload_array(&d_oi, c->occ_idx.data(), c->occ_idx.size()));
-  XTD_TRY(upload_array(&d_vi, c->vir_idx.data(), c->vir_idx.size()));
+  XTD_TRY(upload_array(&d_oi, c->occ_idx.data(), c->occ_idx.size(), h->stream));
+  XTD_TRY(upload_array(&d_vi, c->vir_idx.data(), c->vir_idx.size(), h->stream));
   gather_cols_kernel<<<dim3((unsigned)cdiv(c->no, 128), N), 128, 0, h->stream>>>(c->Co.p, c->ldco, h->C[c->spin_o], h->ldC[c->spin_o], N,
                                                                                d_oi, c->no);
   LAUNCH_CHECK();
@@ -312,8 +327,8 @@ int grid_commit(xtd_engine* h) {
     for (auto* c : h->ch) {
       c->ldphi = pad_ld(c->no);
       c->ldphiv = pad_ld(c->nv);
-      XTD_TRY(c->phi.alloc((size_t)h->nvar_eff * h->ng * c->ldphi));
-      XTD_TRY(c->phiv.alloc((size_t)h->nvar_eff * h->ng * c->ldphiv));
+      XTD_TRY(c->phi.alloc((size_t)h->nvar_eff * h->ng * c->ldphi, h->stream));
+      XTD_TRY(c->phiv.alloc((size_t)h->nvar_eff * h->ng * c->ldphiv, h->stream));
       GemmDesc d;
       d.A = view3d(h->ao, h->ao_ld, h->ao_comp, h->nvar_eff, (int)h->ng, h->nao);
       d.B = view2d(c->CoT.p, h->ldN, c->no, h->nao);
@@ -330,11 +345,11 @@ int grid_commit(xtd_engine* h) {
     const int nk = h->tau ? 5 : h->nvar;        // kernel components
     if (h->fxc_kind == XTD_FXC_UKS) {
       const int nr = 2 * nk;
-      XTD_TRY(h->wf.alloc((size_t)h->ng * nr * nr));
+      XTD_TRY(h->wf.alloc((size_t)h->ng * nr * nr, h->stream));
       build_wf_uks_kernel<<<grid1d(h->ng, 128), 128, 0, s>>>(h->wf.p, h->fxc, h->wgrid, h->ng, nk);
       LAUNCH_CHECK();
     } else if (h->fxc_kind == XTD_FXC_MCOL) {
-      XTD_TRY(h->wf.alloc((size_t)h->ng * nk * nk));
+      XTD_TRY(h->wf.alloc((size_t)h->ng * nk * nk, h->stream));
       build_wf_mcol_kernel<<<grid1d(h->ng, 128), 128, 0, s>>>(h->wf.p, h->fxc, h->wgrid, h->ng, nk);
       LAUNCH_CHECK();
     }
@@ -360,10 +375,13 @@ unsigned long long xtd_launch_count(void) { return g_launch_count; }
 
 int xtd_create(xtd_handle* out, int nao, long workspace_bytes) {
   XTD_REQUIRE(out && nao > 0 && workspace_bytes >= (64L << 20), XTD_ERR_ARG, "xtd_create: bad arguments (workspace >= 64 MiB)");
-  int dev = 0, major = 0;
+  int dev = 0, major = 0, minor = 0;
   XTD_CUDA(cudaGetDevice(&dev));
   XTD_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
-  XTD_REQUIRE(major >= 10, XTD_ERR_UNSUPPORTED, "xtd_create: needs an sm_100a device (found compute capability %d.x)", major);
+  XTD_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  // the library carries sm_100a SASS only (no PTX): any other device would fail at the first launch
+  XTD_REQUIRE(major == 10 && minor == 0, XTD_ERR_UNSUPPORTED, "xtd_create: needs an sm_100a device (found compute capability %d.%d)", major,
+              minor);
   xtd_engine* h = new xtd_engine();
   h->nao = nao;
   h->ldN = pad_ld(nao);
@@ -381,6 +399,8 @@ int xtd_create(xtd_handle* out, int nao, long workspace_bytes) {
   h->ev_ok = true;
   if (const char* e = getenv("XTD_PROFILE_PHASE")) h->prof_phase = atoi(e);
   if (const char* e = getenv("XTD_GRAPH")) h->graph_mode = atoi(e);
+  if (const char* e = getenv("XTD_CHUNK_AUX")) h->max_pc = atol(e);
+  if (const char* e = getenv("XTD_CHUNK_GRID")) h->max_gb = atol(e);
   *out = h;
   return XTD_OK;
 }
@@ -513,9 +533,11 @@ int xtd_add_jblock(xtd_handle h, int chn, int r0, int nr, int c0, int nc) {
 
 int xtd_set_jmix(xtd_handle h, const double* mix, int n) {
   XTD_REQUIRE(h && n == (int)h->jblocks.size(), XTD_ERR_ARG, "xtd_set_jmix: size != number of J blocks");
+  XTD_REQUIRE(!h->finalized, XTD_ERR_STATE, "xtd_set_jmix after finalize (recorded graphs hold the old buffer)");
   h->jmix.assign(mix, mix + (size_t)n * n);
-  XTD_TRY(h->jmix_dev.alloc((size_t)n * n));
-  XTD_CUDA(cudaMemcpy(h->jmix_dev.p, mix, (size_t)n * n * 8, cudaMemcpyHostToDevice));
+  XTD_TRY(h->jmix_dev.alloc((size_t)n * n, h->stream));
+  XTD_CUDA(cudaMemcpyAsync(h->jmix_dev.p, mix, (size_t)n * n * 8, cudaMemcpyHostToDevice, h->stream));
+  XTD_CUDA(cudaStreamSynchronize(h->stream));
   return XTD_OK;
 }
 
@@ -525,18 +547,18 @@ int xtd_df_begin(xtd_handle h, int tensor, long naux_local) {
   h->naux_filled[tensor] = 0;
   for (auto* c : h->ch) {
     if (!c->need_k[tensor]) continue;
-    XTD_TRY(c->Loo[tensor].alloc((size_t)naux_local * c->no * c->ldoo));
-    XTD_TRY(c->Lvv[tensor].alloc((size_t)naux_local * c->nv * c->ldvv));
-    if (c->need_narrow[tensor]) XTD_TRY(c->Lvo[tensor].alloc((size_t)naux_local * c->v_blocks[1].first * c->ldvv));
-    if (c->need_narrow[tensor] && c->tail_w > 0) XTD_TRY(c->Lvt[tensor].alloc((size_t)naux_local * c->tail_w * c->ldvv));
+    XTD_TRY(c->Loo[tensor].alloc((size_t)naux_local * c->no * c->ldoo, h->stream));
+    XTD_TRY(c->Lvv[tensor].alloc((size_t)naux_local * c->nv * c->ldvv, h->stream));
+    if (c->need_narrow[tensor]) XTD_TRY(c->Lvo[tensor].alloc((size_t)naux_local * c->v_blocks[1].first * c->ldvv, h->stream));
+    if (c->need_narrow[tensor] && c->tail_w > 0) XTD_TRY(c->Lvt[tensor].alloc((size_t)naux_local * c->tail_w * c->ldvv, h->stream));
     if (c->need_split[tensor]) {
       const int o2 = c->o_blocks[1].first;
-      XTD_TRY(c->Loob[tensor][0].alloc((size_t)naux_local * o2 * c->ldoo));
-      XTD_TRY(c->Loob[tensor][1].alloc((size_t)naux_local * (c->no - o2) * c->ldoo));
+      XTD_TRY(c->Loob[tensor][0].alloc((size_t)naux_local * o2 * c->ldoo, h->stream));
+      XTD_TRY(c->Loob[tensor][1].alloc((size_t)naux_local * (c->no - o2) * c->ldoo, h->stream));
     }
   }
   if (tensor == 0)
-    for (auto* j : h->jblocks) XTD_TRY(j->L.alloc((size_t)naux_local * j->nr * j->ld));
+    for (auto* j : h->jblocks) XTD_TRY(j->L.alloc((size_t)naux_local * j->nr * j->ld, h->stream));
   return XTD_OK;
 }
 
@@ -740,10 +762,11 @@ int xtd_add_diag(xtd_handle h, int chn, const double* d_host) {
 
 int xtd_set_gather(xtd_handle h, int chn, const long* indptr, const long* cols, const double* vals, long nnz) {
   XTD_REQUIRE(h && chn >= 0 && chn < (int)h->ch.size() && indptr && nnz >= 0, XTD_ERR_ARG, "xtd_set_gather: bad arguments");
+  XTD_REQUIRE(!h->finalized, XTD_ERR_STATE, "xtd_set_gather after finalize (recorded graphs hold the old map)");
   Channel* c = h->ch[chn];
-  XTD_TRY(upload_array(&c->g_indptr, indptr, (size_t)c->no * c->nv + 1));
-  XTD_TRY(upload_array(&c->g_cols, cols, (size_t)nnz));
-  XTD_TRY(upload_array(&c->g_vals, vals, (size_t)nnz));
+  XTD_TRY(upload_array(&c->g_indptr, indptr, (size_t)c->no * c->nv + 1, h->stream));
+  XTD_TRY(upload_array(&c->g_cols, cols, (size_t)nnz, h->stream));
+  XTD_TRY(upload_array(&c->g_vals, vals, (size_t)nnz, h->stream));
   c->g_nnz = nnz;
   return XTD_OK;
 }
@@ -751,11 +774,12 @@ int xtd_set_gather(xtd_handle h, int chn, const long* indptr, const long* cols, 
 int xtd_set_scatter(xtd_handle h, long ext_dim, const long* indptr, const long* offs, const signed char* chans, const double* vals,
                     long nnz) {
   XTD_REQUIRE(h && ext_dim > 0 && indptr && nnz >= 0, XTD_ERR_ARG, "xtd_set_scatter: bad arguments");
+  XTD_REQUIRE(!h->finalized, XTD_ERR_STATE, "xtd_set_scatter after finalize (recorded graphs hold the old map)");
   h->ext_dim = ext_dim;
-  XTD_TRY(upload_array(&h->s_indptr, indptr, (size_t)ext_dim + 1));
-  XTD_TRY(upload_array(&h->s_offs, offs, (size_t)nnz));
-  XTD_TRY(upload_array(&h->s_chans, chans, (size_t)nnz));
-  XTD_TRY(upload_array(&h->s_vals, vals, (size_t)nnz));
+  XTD_TRY(upload_array(&h->s_indptr, indptr, (size_t)ext_dim + 1, h->stream));
+  XTD_TRY(upload_array(&h->s_offs, offs, (size_t)nnz, h->stream));
+  XTD_TRY(upload_array(&h->s_chans, chans, (size_t)nnz, h->stream));
+  XTD_TRY(upload_array(&h->s_vals, vals, (size_t)nnz, h->stream));
   return XTD_OK;
 }
 
@@ -892,8 +916,10 @@ static int run_xc(xtd_engine* h, int nvec) {
   }
   long GB = (long)(h->scratch_doubles / per_g);
   GB = std::min<long>(GB, 1 << 16);
+  if (h->max_gb > 0) GB = std::min<long>(GB, std::max<long>(h->max_gb, 128));
   GB = (GB / 128) * 128;
   XTD_REQUIRE(GB >= 128, XTD_ERR_NOMEM, "workspace too small for a 128-point grid chunk");
+  h->last_grid_chunks = cdiv(h->ng, GB);
   for (long g0 = 0; g0 < h->ng; g0 += GB) {
     const int gb = (int)std::min<long>(GB, h->ng - g0);
     double *Y[2] = {nullptr, nullptr}, *T[2] = {nullptr, nullptr};
@@ -1013,6 +1039,8 @@ static int run_k(xtd_engine* h, int nvec) {
     XTD_REQUIRE(pc >= 1, XTD_ERR_NOMEM, "workspace too small for the exchange intermediate of one aux function");
     pc = std::min<long>(pc, naux);
     if ((long)pc * nvec > 65535) pc = 65535 / nvec;
+    if (h->max_pc > 0) pc = std::min<long>(pc, h->max_pc);
+    h->last_aux_chunks = std::max<long>(h->last_aux_chunks, cdiv(naux, pc));
     double* U = h->scratch;
     std::vector<std::pair<int, int>> iblks, ablks;
     const int o2off = ch->o_blocks.size() > 1 ? ch->o_blocks[1].first : ch->no;
@@ -1253,6 +1281,7 @@ int xtd_sigma_partial(xtd_handle h, int nvec, const double* z_dev) {
   cudaStream_t s = h->stream;
   h->ev_used = 0;
   for (int i = 0; i < 12; ++i) h->phase_flops[i] = 0.0;
+  h->last_aux_chunks = h->last_grid_chunks = 0;
   if (h->prof_phase == XTD_T_TOTAL && !h->capturing) cudaProfilerStart();
   if (h->ev_ok && !h->capturing) cudaEventRecord(h->ev_total[0], s);
   XTD_TRY(setup_call_buffers(h, nvec));
@@ -1323,8 +1352,8 @@ static int launch_graph(xtd_engine* h, const xtd_engine::GraphRec& g) {
   XTD_CUDA(cudaGraphLaunch(g.exec, s));
   if (h->ev_ok) cudaEventRecord(h->ev_total[1], s);
   for (int i = 0; i < 12; ++i) h->phase_flops[i] = g.phase_flops[i];
-  h->cur_nvec = g.nvec;
-  return XTD_OK;
+  XTD_TRY(setup_call_buffers(h, g.nvec));            // same (deterministic) arena layout the recorded call used: channel bases,
+  return XTD_OK;                                     // Z / SIG pointers for xtd_partial_buffer / xtd_sigma_finish after a replay
 }
 
 int xtd_sigma(xtd_handle h, int nvec, const double* z_dev, double* hz_dev) {
@@ -1378,6 +1407,7 @@ int xtd_sigma(xtd_handle h, int nvec, const double* z_dev, double* hz_dev) {
 
 int xtd_sigma_host(xtd_handle h, int nvec, const double* z_host, double* hz_host) {
   XTD_REQUIRE(h && h->finalized && z_host && hz_host, XTD_ERR_ARG, "xtd_sigma_host: bad arguments");
+  XTD_REQUIRE(nvec >= 1 && nvec <= h->max_nvec, XTD_ERR_ARG, "xtd_sigma_host: nvec %d outside 1..%d", nvec, h->max_nvec);
   const size_t n = (size_t)nvec * h->ext_dim;
   if (n > h->pin_doubles) {
     if (h->pin_in) cudaFreeHost(h->pin_in);
@@ -1414,6 +1444,13 @@ int xtd_get_stats(xtd_handle h, xtd_stats* out) {
   float tot = 0.f;
   if (cudaEventElapsedTime(&tot, h->ev_total[0], h->ev_total[1]) == cudaSuccess) out->ms[XTD_T_TOTAL] = tot;
   else cudaGetLastError();
+  return XTD_OK;
+}
+
+int xtd_last_chunks(xtd_handle h, long* aux_chunks, long* grid_chunks) {
+  XTD_REQUIRE(h, XTD_ERR_ARG, "null handle");
+  if (aux_chunks) *aux_chunks = h->last_aux_chunks;
+  if (grid_chunks) *grid_chunks = h->last_grid_chunks;
   return XTD_OK;
 }
 

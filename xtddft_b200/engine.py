@@ -291,6 +291,12 @@ class SigmaEngine:
         return dict(flops_gemm=st.flops_gemm, launches=int(st.launches), ms={n: st.ms[i] for i, n in enumerate(_lib.T_NAMES)},
                     flops={n: st.flops[i] for i, n in enumerate(_lib.T_NAMES)})
 
+    def last_chunks(self):
+        """(aux chunks, grid chunks) the last eager sigma call looped over."""
+        a, g = C.c_long(), C.c_long()
+        _lib.check(self.lib.xtd_last_chunks(self._h, C.byref(a), C.byref(g)), "xtd_last_chunks")
+        return a.value, g.value
+
     def reset_stats(self):
         _lib.check(self.lib.xtd_reset_stats(self._h), "xtd_reset_stats")
 
