@@ -134,6 +134,12 @@ int xtd_dgemm_tn(void* stream, int m, int n, int k, double alpha, const double* 
 /* general form: A is [M,K] row-major when a_kc != 0, else [K,M]; B is [N,K] when b_kc != 0, else [K,N] */
 int xtd_dgemm(void* stream, int m, int n, int k, double alpha, const double* a_dev, long lda, int a_kc, const double* b_dev, long ldb,
               int b_kc, double* c_dev, long ldc, int accumulate);
+/* FP64 contraction emulated on the INT8 tensor cores (tcgen05.mma kind::i8, Ozaki splitting into `slices` signed 7-bit
+ * digits per operand; csrc/ozaki.cuh):  C[M,N] (+)= alpha * sum_q A[q][M,K] B[q][N,K]^T  with both operands K-contiguous,
+ * row stride ld and q-slice stride sq (even, 16-byte aligned base).  `group` q-slices share one power-of-two row scale and
+ * one exact int32 accumulation (0 = choose).  ms_out[3] (may be null) = device time of slicing A, slicing B, the int8 GEMM. */
+int xtd_ozaki_gemm(void* stream, int m, int n, int k, int nq, int slices, int group, const double* a_dev, long lda, long sqa,
+                   const double* b_dev, long ldb, long sqb, double* c_dev, long ldc, double alpha, int accumulate, double* ms_out);
 unsigned long long xtd_launch_count(void);
 
 #ifdef __cplusplus

@@ -64,6 +64,7 @@ SIGNATURES = {
     "xtd_vec_scale": (_I, [_P, _P, _L, _P, _I, _L]),
     "xtd_dgemm_tn": (_I, [_P, _I, _I, _I, _D, _P, _L, _P, _L, _P, _L, _I]),
     "xtd_dgemm": (_I, [_P, _I, _I, _I, _D, _P, _L, _I, _P, _L, _I, _P, _L, _I]),
+    "xtd_ozaki_gemm": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _L, _L, _P, _L, _L, _P, _L, _D, _I, _P]),
     "xtd_launch_count": (C.c_ulonglong, []),
 }
 

@@ -1,0 +1,411 @@
+// FP64 contraction emulated on the INT8 tensor cores of sm_100a (Ozaki splitting):
+//
+//   C[m][n] (+)= alpha * sum_q sum_k A[q][m][k] * B[q][n][k]                      (fp64 in, fp64 out)
+//
+// tcgen05 has no f64 kind, and the warp-level DMMA pipe tops out at 37 TFLOP/s.  Here every fp64 operand row is scaled by a
+// power of two per (row, group of `group` q-slices) and cut into S signed 7-bit digits (int8 slices, radix 128):
+//   x = scale * sum_l d_l 2^(-7 l),  d_l in [-64, 64]
+// so that  A.B = sa sb sum_{i+j < S} 2^(-7(i+j)) (A_i . B_j)  with every A_i . B_j an EXACT int8 x int8 -> int32 product on
+// `tcgen05.mma.kind::i8`; the S(S+1)/2 slice products are accumulated per level l = i + j in S separate TMEM accumulators
+// (128 lanes x 64 columns each, S <= 8 fills the 512 columns) over one group, then read back with tcgen05.ld, recombined
+// in fp64 (Horner in 2^-7), scaled and added to fp64 register accumulators.  Terms with i + j >= S (below 2^(-7S) of the row
+// scale) are dropped.  int32 never overflows: |d_i d_j| <= 2^12, (l+1) products per level, group * K <= 2^19 / S terms.
+//
+// Sliced operands live in HBM pre-tiled as shared-memory images, so a pipeline stage is two plain bulk copies
+// (cp.async.bulk, no tensor map):   [q][row tile][k block of 32][slice][ 2 chunks x RT rows x 16 bytes ]
+// = the canonical no-swizzle K-major UMMA layout (core matrix 8 rows x 16 B; SBO 128 B, LBO RT*16 B).
+//
+// Warp roles in a CTA of 192 threads: warp 0 bulk-copy producer, warp 1 MMA issuer (+ TMEM allocation), warps 2-5 epilogue
+// (TMEM lane quadrant = warp % 4).  One CTA per (128 x 64 output tile, split of the group range); partial tiles go to a
+// workspace and are reduced deterministically.
+#pragma once
+#include "common.cuh"
+
+namespace xtd {
+
+constexpr int OZ_BM = 128, OZ_BN = 64, OZ_KB = 32, OZ_STAGES = 4, OZ_MAX_S = 8, OZ_MIN_S = 3;
+constexpr int OZ_THREADS = 192;
+
+__device__ __forceinline__ uint32_t oz_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- slicing ------------------------------------------------------------------------------------------------------------
+// scale[g][row] = 2^(e - 6) with max |x| over the row's group < 2^e (0 for an all-zero / padding row)
+__global__ void oz_rowmax_kernel(double* __restrict__ scale, int rows_pad, const double* __restrict__ X, long ld, long sq, int rows, int K,
+                                 int nq, int group) {
+  const int row = blockIdx.x, g = blockIdx.y;
+  double m = 0.0;
+  if (row < rows) {
+    const int q1 = min(nq, (g + 1) * group);
+    for (int q = g * group; q < q1; ++q) {
+      const double* x = X + (long)q * sq + (long)row * ld;
+      for (int k = threadIdx.x; k < K; k += blockDim.x) m = fmax(m, fabs(x[k]));
+    }
+  }
+  __shared__ double red[8];
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, red[w]);
+    double s = 0.0;
+    if (m > 1e-280 && m < 1e280) {
+      int e;
+      frexp(m, &e);                 // m = f 2^e, f in [0.5, 1)
+      s = ldexp(1.0, e - 6);
+    }
+    scale[(long)g * rows_pad + row] = s;
+  }
+}
+
+// one thread: 16 consecutive k of one row -> S 16-byte chunks.  grid (2 nkb, rows_pad / 128, nq), block 128 (lane <-> row)
+template <int S>
+__global__ void __launch_bounds__(128) oz_slice_kernel(int8_t* __restrict__ out, const double* __restrict__ scale, int rows_pad,
+                                                       const double* __restrict__ X, long ld, long sq, int rows, int K, int RT, int nkb,
+                                                       int group) {
+  const int c2 = blockIdx.x, q = blockIdx.z;
+  const int row = blockIdx.y * 128 + threadIdx.x;
+  const int rt = row / RT, r = row - rt * RT, nrt = rows_pad / RT;
+  const int k0 = c2 * 16;
+  double x[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) x[k] = 0.0;
+  double sc = 0.0;
+  if (row < rows) {
+    sc = scale[(long)(q / group) * rows_pad + row];
+    const double* src = X + (long)q * sq + (long)row * ld + k0;
+    if (k0 + 16 <= K) {
+#pragma unroll
+      for (int k = 0; k < 16; k += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(src + k);
+        x[k] = v.x;
+        x[k + 1] = v.y;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 16; ++k)
+        if (k0 + k < K) x[k] = src[k];
+    }
+  }
+  // 1 / scale for a power of two: flip the exponent
+  const double inv = sc > 0.0 ? __hiloint2double(0x7fe00000 - __double2hiint(sc), 0) : 0.0;
+  const double magic = 6755399441055744.0;   // 1.5 * 2^52: (t + magic) has rint(t) in its low mantissa bits (two's complement)
+  uint32_t pk[S][4];
+#pragma unroll
+  for (int sl = 0; sl < S; ++sl)
+#pragma unroll
+    for (int w = 0; w < 4; ++w) pk[sl][w] = 0u;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    double t = x[k] * inv;                    // |t| < 64
+#pragma unroll
+    for (int sl = 0; sl < S; ++sl) {
+      const double u = (sl == 0) ? (t + magic) : fma(t, 128.0, magic);
+      const double qd = u - magic;
+      t = (sl == 0) ? (t - qd) : fma(t, 128.0, -qd);
+      pk[sl][k >> 2] |= ((uint32_t)__double2loint(u) & 0xffu) << ((k & 3) * 8);
+    }
+  }
+  int8_t* dst = out + ((((long)q * nrt + rt) * nkb + (c2 >> 1)) * S) * ((long)RT * OZ_KB) + (long)(c2 & 1) * RT * 16 + (long)r * 16;
+#pragma unroll
+  for (int sl = 0; sl < S; ++sl)
+    *reinterpret_cast<uint4*>(dst + (long)sl * RT * OZ_KB) = make_uint4(pk[sl][0], pk[sl][1], pk[sl][2], pk[sl][3]);
+}
+
+// ---- the INT8 tensor-core kernel ------------------------------------------------------------------------------------------
+struct OzGemmParams {
+  const int8_t* A;      // [nq][nmt][nkb][S][128 x 32]
+  const int8_t* B;      // [..][nnt][nkb][S][ 64 x 32], first slice used: b_q0
+  const double* sa;     // [ngroups][Mpad]           (group index relative to this launch)
+  const double* sb;     // [..][Npad], first group used: b_q0 / group
+  int nmt, nnt, nkb, nq, group, b_q0;
+  int Mpad, Npad, splits;
+  double* W;            // partial tiles [splits][Mpad][Npad]
+  double alpha;
+};
+
+__device__ __forceinline__ void oz_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(oz_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void oz_mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = oz_smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void oz_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(oz_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void oz_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(oz_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void oz_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(oz_smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(oz_smem_u32(bar))
+               : "memory");
+}
+// shared-memory matrix descriptor, K-major, no swizzle: start address, leading (K-direction) and stride (row-group) byte offsets
+__device__ __forceinline__ uint64_t oz_smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((addr & 0x3ffffu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void oz_mma_i8(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void oz_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void oz_tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
+template <int S>
+__global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const OzGemmParams p) {
+  constexpr int A_SLICE = OZ_BM * OZ_KB, B_SLICE = OZ_BN * OZ_KB;
+  constexpr int A_BYTES = S * A_SLICE, B_BYTES = S * B_SLICE, STAGE = A_BYTES + B_BYTES;
+  extern __shared__ __align__(128) uint8_t oz_smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(oz_smem + OZ_STAGES * STAGE);
+  uint64_t* empty = full + OZ_STAGES;
+  uint64_t* tmem_full = empty + OZ_STAGES;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x;
+  const int nt = item % p.nnt, mt = (item / p.nnt) % p.nmt, sp = item / (p.nnt * p.nmt);
+  const int ngroups = (p.nq + p.group - 1) / p.group;
+  const int g0 = (int)((long)ngroups * sp / p.splits), g1 = (int)((long)ngroups * (sp + 1) / p.splits);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < OZ_STAGES; ++s) {
+      oz_mbar_init(&full[s], 1);
+      oz_mbar_init(&empty[s], 1);
+    }
+    oz_mbar_init(tmem_full, 1);
+    oz_mbar_init(tmem_empty, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(oz_smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== producer: two bulk copies per k-step =====================
+    if (lane == 0) {
+      long it = 0;
+      for (int g = g0; g < g1; ++g) {
+        const int q1 = min(p.nq, (g + 1) * p.group);
+        for (int q = g * p.group; q < q1; ++q) {
+          const int8_t* a = p.A + (((long)q * p.nmt + mt) * p.nkb) * A_BYTES;
+          const int8_t* b = p.B + (((long)(q + p.b_q0) * p.nnt + nt) * p.nkb) * B_BYTES;
+          for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+            const int s = (int)(it % OZ_STAGES);
+            const uint32_t ph = (uint32_t)((it / OZ_STAGES) & 1);
+            oz_mbar_wait(&empty[s], ph ^ 1u);
+            oz_mbar_expect_tx(&full[s], STAGE);
+            uint8_t* sa = oz_smem + s * STAGE;
+            oz_bulk_load(sa, a + (long)kb * A_BYTES, A_BYTES, &full[s]);
+            oz_bulk_load(sa + A_BYTES, b + (long)kb * B_BYTES, B_BYTES, &full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: S(S+1)/2 int8 MMAs per k-step, one accumulator per level i + j =====================
+    if (lane == 0) {
+      // instruction descriptor: D = s32, A = B = signed int8, both K-major, N = 64, M = 128
+      constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
+      const uint32_t smem_base = oz_smem_u32(oz_smem);
+      long it = 0;
+      for (int g = g0; g < g1; ++g) {
+        if (g > g0) oz_mbar_wait(tmem_empty, (uint32_t)((g - g0 - 1) & 1));   // epilogue has drained the previous group
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q1 = min(p.nq, (g + 1) * p.group);
+        const long nsteps = (long)(q1 - g * p.group) * p.nkb;
+        for (long st = 0; st < nsteps; ++st, ++it) {
+          const int s = (int)(it % OZ_STAGES);
+          const uint32_t ph = (uint32_t)((it / OZ_STAGES) & 1);
+          oz_mbar_wait(&full[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_base = smem_base + s * STAGE, b_base = a_base + A_BYTES;
+          const uint32_t later = st > 0 ? 1u : 0u;
+#pragma unroll
+          for (int i = 0; i < S; ++i) {
+            const uint64_t da = oz_smem_desc(a_base + i * A_SLICE, OZ_BM * 16, 128);
+#pragma unroll
+            for (int j = 0; j < S - i; ++j) {
+              const uint64_t db = oz_smem_desc(b_base + j * B_SLICE, OZ_BN * 16, 128);
+              oz_mma_i8(tmem_base + (uint32_t)((i + j) * OZ_BN), da, db, idesc, (i > 0) ? 1u : later);
+            }
+          }
+          oz_commit(&empty[s]);      // frees the stage when these MMAs have read it
+        }
+        oz_commit(tmem_full);        // all levels of this group are complete
+      }
+    }
+  } else {
+    // ===================== epilogue: levels -> fp64, scale, accumulate =====================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    double acc[OZ_BN];
+#pragma unroll
+    for (int c = 0; c < OZ_BN; ++c) acc[c] = 0.0;
+    for (int g = g0; g < g1; ++g) {
+      oz_mbar_wait(tmem_full, (uint32_t)((g - g0) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const double sa = p.sa[(long)g * p.Mpad + mt * OZ_BM + row];
+      const double* sb = p.sb + (long)(g + p.b_q0 / p.group) * p.Npad + nt * OZ_BN;
+#pragma unroll
+      for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
+        double v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = 0.0;
+#pragma unroll
+        for (int l = S - 1; l >= 0; --l) {
+          uint32_t r[16];
+          oz_tmem_ld16(taddr + (uint32_t)(l * OZ_BN + c0), r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int k = 0; k < 16; ++k) v[k] = fma(v[k], 0.0078125, (double)(int)r[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc[c0 + k] = fma(v[k], sa * sb[c0 + k], acc[c0 + k]);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      oz_mbar_arrive(tmem_empty);
+    }
+    double* w = p.W + ((long)sp * p.Mpad + mt * OZ_BM + row) * p.Npad + nt * OZ_BN;
+#pragma unroll
+    for (int c = 0; c < OZ_BN; c += 2) *reinterpret_cast<double2*>(w + c) = make_double2(p.alpha * acc[c], p.alpha * acc[c + 1]);
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------------------------------------
+struct OzShape {
+  int rows = 0, RT = 0, rows_pad = 0, nrt = 0, K = 0, nkb = 0;
+  void set(int rows_, int RT_, int K_) {
+    rows = rows_; RT = RT_; K = K_;
+    rows_pad = (int)round_up(rows_, 128);       // 128 rows per slicing block; a multiple of both tile heights
+    nrt = rows_pad / RT_;
+    nkb = (int)cdiv(K_, OZ_KB);
+  }
+  size_t slice_bytes(long nq, int S) const { return (size_t)nq * nrt * nkb * S * RT * OZ_KB; }
+  size_t scale_doubles(long nq, int group) const { return (size_t)cdiv(nq, group) * rows_pad; }
+};
+
+inline size_t oz_gemm_smem(int S) { return (size_t)OZ_STAGES * S * (OZ_BM + OZ_BN) * OZ_KB + 256; }
+
+// the largest group (q-slices sharing one scale and one int32 accumulation) that cannot overflow: group * nkb * 32 * S * 2^12 < 2^31
+inline int oz_max_group(int K, int S) {
+  const long kpad = round_up(K, OZ_KB);
+  const long g = ((1L << 19) - 1) / ((long)S * kpad);
+  return (int)std::max<long>(g, 0);
+}
+
+template <int S>
+inline int oz_slice_launch(int8_t* out, double* scale, const OzShape& sh, const double* X, long ld, long sq, int nq, int group,
+                           cudaStream_t st) {
+  const int ng = (int)cdiv(nq, group);
+  oz_rowmax_kernel<<<dim3(sh.rows_pad, ng), 256, 0, st>>>(scale, sh.rows_pad, X, ld, sq, sh.rows, sh.K, nq, group);
+  XTD_COUNT_LAUNCH();
+  XTD_CUDA(cudaGetLastError());
+  oz_slice_kernel<S><<<dim3(2 * sh.nkb, sh.rows_pad / 128, nq), 128, 0, st>>>(out, scale, sh.rows_pad, X, ld, sq, sh.rows, sh.K, sh.RT, sh.nkb,
+                                                                             group);
+  XTD_COUNT_LAUNCH();
+  XTD_CUDA(cudaGetLastError());
+  return XTD_OK;
+}
+
+inline int oz_slice(int S, int8_t* out, double* scale, const OzShape& sh, const double* X, long ld, long sq, int nq, int group,
+                    cudaStream_t st) {
+  XTD_REQUIRE(nq >= 1 && nq <= 65535, XTD_ERR_ARG, "oz_slice: %d q-slices per launch (1..65535)", nq);
+  XTD_REQUIRE(ld % 2 == 0 && sq % 2 == 0 && ((uintptr_t)X & 15) == 0, XTD_ERR_ALIGN, "oz_slice: operand must be 16-byte aligned with even strides");
+  switch (S) {
+    case 3: return oz_slice_launch<3>(out, scale, sh, X, ld, sq, nq, group, st);
+    case 4: return oz_slice_launch<4>(out, scale, sh, X, ld, sq, nq, group, st);
+    case 5: return oz_slice_launch<5>(out, scale, sh, X, ld, sq, nq, group, st);
+    case 6: return oz_slice_launch<6>(out, scale, sh, X, ld, sq, nq, group, st);
+    case 7: return oz_slice_launch<7>(out, scale, sh, X, ld, sq, nq, group, st);
+    case 8: return oz_slice_launch<8>(out, scale, sh, X, ld, sq, nq, group, st);
+  }
+  XTD_SET_ERR("oz_slice: %d slices (3..8)", S);
+  return XTD_ERR_ARG;
+}
+
+template <int S>
+inline int oz_gemm_launch(const OzGemmParams& p, cudaStream_t st) {
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  XTD_CUDA(cudaGetDevice(&dev));
+  if (!attr_set[dev & 63]) {
+    XTD_CUDA(cudaFuncSetAttribute(oz_gemm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_gemm_smem(S)));
+    attr_set[dev & 63] = true;
+  }
+  oz_gemm_kernel<S><<<(unsigned)(p.nmt * p.nnt * p.splits), OZ_THREADS, oz_gemm_smem(S), st>>>(p);
+  XTD_COUNT_LAUNCH();
+  XTD_CUDA(cudaGetLastError());
+  return XTD_OK;
+}
+
+inline int oz_gemm(int S, const OzGemmParams& p, cudaStream_t st) {
+  XTD_REQUIRE(p.group >= 1 && p.group <= oz_max_group(p.nkb * OZ_KB, S), XTD_ERR_ARG, "oz_gemm: group %d would overflow int32 (max %d)", p.group,
+              oz_max_group(p.nkb * OZ_KB, S));
+  XTD_REQUIRE(p.b_q0 % p.group == 0, XTD_ERR_ARG, "oz_gemm: first B slice %d must sit on a group boundary (%d)", p.b_q0, p.group);
+  switch (S) {
+    case 3: return oz_gemm_launch<3>(p, st);
+    case 4: return oz_gemm_launch<4>(p, st);
+    case 5: return oz_gemm_launch<5>(p, st);
+    case 6: return oz_gemm_launch<6>(p, st);
+    case 7: return oz_gemm_launch<7>(p, st);
+    case 8: return oz_gemm_launch<8>(p, st);
+  }
+  XTD_SET_ERR("oz_gemm: %d slices (3..8)", S);
+  return XTD_ERR_ARG;
+}
+
+// split of the group range that fills the SMs with whole waves
+inline int oz_choose_splits(int tiles, int ngroups, int num_sms) {
+  int best = 1;
+  double best_cost = 1e300;
+  const int max_s = std::min(ngroups, 64);
+  for (int s = 1; s <= max_s; ++s) {
+    const long waves = cdiv((long)tiles * s, num_sms);
+    const double cost = (double)waves * ((double)cdiv(ngroups, s) + 0.05);
+    if (cost < best_cost * 0.995) { best_cost = cost; best = s; }
+  }
+  return best;
+}
+
+}  // namespace xtd

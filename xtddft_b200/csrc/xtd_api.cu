@@ -11,6 +11,7 @@
 #include "../../include/xtd_sigma.h"
 #include "gemm.cuh"
 #include "kernels.cuh"
+#include "ozaki.cuh"
 
 #include <cuda_profiler_api.h>
 
@@ -1521,6 +1522,74 @@ int xtd_dgemm(void* stream, int m, int n, int k, double alpha, const double* a, 
   d.B = d.b_kc ? view2d(b, ldb, n, k) : view2d(b, ldb, k, n);
   d.M = m; d.N = n; d.K = k; d.C = c; d.ldc = ldc; d.alpha = alpha; d.accumulate = accumulate != 0;
   return gemm(ctx, d, (cudaStream_t)stream);
+}
+
+// Emulated-FP64 contraction on the INT8 tensor cores (ozaki.cuh), self-contained: slices both operands, runs the tcgen05 kernel,
+// reduces the split partials.  Temporary buffers are allocated per call: a test / benchmark entry, not the engine path.
+int xtd_ozaki_gemm(void* stream, int m, int n, int k, int nq, int slices, int group, const double* a_dev, long lda, long sqa,
+                   const double* b_dev, long ldb, long sqb, double* c_dev, long ldc, double alpha, int accumulate, double* ms_out) {
+  XTD_REQUIRE(m > 0 && n > 0 && k > 0 && nq > 0 && a_dev && b_dev && c_dev, XTD_ERR_ARG, "xtd_ozaki_gemm: bad arguments");
+  XTD_REQUIRE(slices >= OZ_MIN_S && slices <= OZ_MAX_S, XTD_ERR_ARG, "xtd_ozaki_gemm: slices %d outside %d..%d", slices, OZ_MIN_S, OZ_MAX_S);
+  if (group <= 0) group = std::min(8, oz_max_group(k, slices));
+  XTD_REQUIRE(group >= 1 && group <= oz_max_group(k, slices), XTD_ERR_ARG, "xtd_ozaki_gemm: K = %d too long for one int32 group (max group %d)", k,
+              oz_max_group(k, slices));
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0, sms = 148;
+  XTD_CUDA(cudaGetDevice(&dev));
+  XTD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  OzShape sa, sb;
+  sa.set(m, OZ_BM, k);
+  sb.set(n, OZ_BN, k);
+  const int ngroups = (int)cdiv(nq, group);
+  const int splits = oz_choose_splits(sa.nrt * sb.nrt, ngroups, sms);
+  int8_t *As = nullptr, *Bs = nullptr;
+  double *sca = nullptr, *scb = nullptr, *W = nullptr;
+  XTD_CUDA(cudaMalloc((void**)&As, sa.slice_bytes(nq, slices)));
+  XTD_CUDA(cudaMalloc((void**)&Bs, sb.slice_bytes(nq, slices)));
+  XTD_CUDA(cudaMalloc((void**)&sca, sa.scale_doubles(nq, group) * 8));
+  XTD_CUDA(cudaMalloc((void**)&scb, sb.scale_doubles(nq, group) * 8));
+  XTD_CUDA(cudaMalloc((void**)&W, (size_t)splits * sa.rows_pad * sb.rows_pad * 8));
+  cudaEvent_t ev[4];
+  for (auto& e : ev) cudaEventCreate(&e);
+  int rc = XTD_OK;
+  cudaEventRecord(ev[0], st);
+  for (int q0 = 0; q0 < nq && rc == XTD_OK; q0 += 32768 / group * group) {     // grid.z limit of the slicing kernel
+    const int qn = std::min(nq - q0, 32768 / group * group);
+    rc = oz_slice(slices, As + sa.slice_bytes(q0, slices), sca + (size_t)(q0 / group) * sa.rows_pad, sa, a_dev + (long)q0 * sqa, lda, sqa, qn, group, st);
+  }
+  cudaEventRecord(ev[1], st);
+  for (int q0 = 0; q0 < nq && rc == XTD_OK; q0 += 32768 / group * group) {
+    const int qn = std::min(nq - q0, 32768 / group * group);
+    rc = oz_slice(slices, Bs + sb.slice_bytes(q0, slices), scb + (size_t)(q0 / group) * sb.rows_pad, sb, b_dev + (long)q0 * sqb, ldb, sqb, qn, group, st);
+  }
+  cudaEventRecord(ev[2], st);
+  if (rc == XTD_OK) {
+    OzGemmParams p;
+    p.A = As; p.B = Bs; p.sa = sca; p.sb = scb;
+    p.nmt = sa.nrt; p.nnt = sb.nrt; p.nkb = sa.nkb; p.nq = nq; p.group = group; p.b_q0 = 0;
+    p.Mpad = sa.rows_pad; p.Npad = sb.rows_pad; p.splits = splits; p.W = W; p.alpha = alpha;
+    rc = oz_gemm(slices, p, st);
+    if (rc == XTD_OK) {
+      long nblk = cdiv((long)m * n, 256);
+      reduce_splits_kernel<<<dim3((unsigned)(nblk > 4096 ? 4096 : nblk), 1), 256, 0, st>>>(c_dev, ldc, 0, W, sb.rows_pad, 0,
+                                                                                          (long)sa.rows_pad * sb.rows_pad, splits, m, n,
+                                                                                          accumulate ? 1 : 0, 0, 0, 0);
+      XTD_COUNT_LAUNCH();
+      if (cudaGetLastError() != cudaSuccess) rc = XTD_ERR_CUDA;
+    }
+  }
+  cudaEventRecord(ev[3], st);
+  cudaError_t se = cudaStreamSynchronize(st);
+  if (se != cudaSuccess) { XTD_SET_ERR("xtd_ozaki_gemm: %s", cudaGetErrorString(se)); rc = XTD_ERR_CUDA; }
+  if (ms_out && rc == XTD_OK)
+    for (int i = 0; i < 3; ++i) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, ev[i], ev[i + 1]);
+      ms_out[i] = t;
+    }
+  for (auto& e : ev) cudaEventDestroy(e);
+  cudaFree(As); cudaFree(Bs); cudaFree(sca); cudaFree(scb); cudaFree(W);
+  return rc;
 }
 
 int xtd_dgemm_tn(void* stream, int m, int n, int k, double alpha, const double* a, long lda, const double* b, long ldb, double* c,
