@@ -66,6 +66,8 @@ def parse():
     ap.add_argument("--workspace-gb", type=float, default=0.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--davidson", type=int, default=int(os.environ.get("XTD_BENCH_DAVIDSON", "1")))
+    ap.add_argument("--exchange-slices", type=int, default=int(os.environ.get("XTD_OZAKI", "-1")),
+                    help="exchange contraction: 0 = FP64 DMMA, 3..8 = INT8 tensor-core emulation with that many 7-bit digits, -1 = default")
     return ap.parse_args()
 
 
@@ -253,7 +255,9 @@ def main():
     nvec = args.nvec or dp.nroots
     ws = int(args.workspace_gb * (1 << 30)) if args.workspace_gb > 0 else default_workspace_bytes(dp, world)
     t_setup0 = time.perf_counter()
-    eng = engine_for_device_problem(dp, max_nvec=max(nvec, 16), workspace_bytes=ws, rank=rank, world=world, reducer=reducer)
+    xs = None if args.exchange_slices < 0 else args.exchange_slices
+    eng = engine_for_device_problem(dp, max_nvec=max(nvec, 16), workspace_bytes=ws, rank=rank, world=world, reducer=reducer,
+                                    exchange_slices=xs)
     torch.cuda.synchronize()
     setup_s = time.perf_counter() - t_setup0
     dim = eng.ext_dim

@@ -35,7 +35,7 @@ typedef struct {
   double flops[12];           /* DMMA GEMM flops issued inside each phase of the last xtd_sigma* call */
 } xtd_stats;
 enum { XTD_T_PACK = 0, XTD_T_XC_GEMM = 1, XTD_T_XC_STREAM = 2, XTD_T_K1 = 3, XTD_T_K2 = 4, XTD_T_J = 5,
-       XTD_T_LOCAL = 6, XTD_T_UNPACK = 7, XTD_T_TOTAL = 8 };
+       XTD_T_LOCAL = 6, XTD_T_UNPACK = 7, XTD_T_TOTAL = 8, XTD_T_K2_SLICE = 9 };
 
 const char* xtd_last_error(void);
 int xtd_version(void);
@@ -63,6 +63,12 @@ int xtd_channel_layout(xtd_handle h, int ch, int nvec, long* base, long* vec_str
 int xtd_add_kterm(xtd_handle h, int tensor, int ch, const double* weights_host, int nob, int nvb);
 int xtd_add_jblock(xtd_handle h, int ch, int r0, int nr, int c0, int nc);
 int xtd_set_jmix(xtd_handle h, const double* mix_host, int n);
+/* Exchange contraction sigma += U . Lvv of uniform-weight terms: slices = 0 (default) runs it as FP64 DMMA GEMMs; slices = 3..8
+ * emulates FP64 on the INT8 tensor cores (tcgen05.mma kind::i8, csrc/ozaki.cuh) with that many 7-bit digits per operand
+ * (radix-256 digits: relative truncation 2^(-8 slices) below each row's scale; 6 -> ~1e-12 on sigma) and keeps Lvv as 8-bit
+ * planes only.  Call before xtd_df_begin; with it every xtd_df_add chunk but the last must hold a multiple of the scale group
+ * (at most 4 aux functions; the Python engine carries ragged remainders over). */
+int xtd_set_exchange_emulation(xtd_handle h, int slices);
 int xtd_df_begin(xtd_handle h, int tensor, long naux_local);
 int xtd_df_add(xtd_handle h, int tensor, const double* l_dev, long np, long ld_row, long stride_p, int packed);
 int xtd_jblock_diag(xtd_handle h, int jb, double* out_dev);   /* out[nr*nc] = sum_P L_ia^2 */
@@ -134,8 +140,8 @@ int xtd_dgemm_tn(void* stream, int m, int n, int k, double alpha, const double* 
 /* general form: A is [M,K] row-major when a_kc != 0, else [K,M]; B is [N,K] when b_kc != 0, else [K,N] */
 int xtd_dgemm(void* stream, int m, int n, int k, double alpha, const double* a_dev, long lda, int a_kc, const double* b_dev, long ldb,
               int b_kc, double* c_dev, long ldc, int accumulate);
-/* FP64 contraction emulated on the INT8 tensor cores (tcgen05.mma kind::i8, Ozaki splitting into `slices` signed 7-bit
- * digits per operand; csrc/ozaki.cuh):  C[M,N] (+)= alpha * sum_q A[q][M,K] B[q][N,K]^T  with both operands K-contiguous,
+/* FP64 contraction emulated on the INT8 tensor cores (tcgen05.mma kind::i8, Ozaki splitting into `slices` radix-256
+ * digit planes per operand; csrc/ozaki.cuh):  C[M,N] (+)= alpha * sum_q A[q][M,K] B[q][N,K]^T  with both operands K-contiguous,
  * row stride ld and q-slice stride sq (even, 16-byte aligned base).  `group` q-slices share one power-of-two row scale and
  * one exact int32 accumulation (0 = choose).  ms_out[3] (may be null) = device time of slicing A, slicing B, the int8 GEMM. */
 int xtd_ozaki_gemm(void* stream, int m, int n, int k, int nq, int slices, int group, const double* a_dev, long lda, long sqa,

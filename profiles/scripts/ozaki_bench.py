@@ -42,8 +42,8 @@ def main():
     dmma_ms = e0.elapsed_time(e1)
     print(json.dumps(dict(kind="dmma", nq=nq, ms=dmma_ms, tflops=flops / dmma_ms / 1e9)), flush=True)
     scale = ref[:, :n].abs().max().item()
-    for slices in (5, 6, 7, 8):
-        for group in (8,):
+    for slices in (4, 5, 6, 7, 8):
+        for group in (0,):
             c = torch.zeros((m, 1792), dtype=torch.float64, device="cuda")
             ms = (C.c_double * 3)()
             for it in range(2):

@@ -1,7 +1,8 @@
 """FP64 contraction emulated on the INT8 tensor cores (tcgen05.mma kind::i8 + TMEM, csrc/ozaki.cuh) against an fp64
 reference of the same contraction (numpy on the host: the oracle for a floating-point kernel is the plain fp64 product).
-Error model: each operand row is cut into S signed 7-bit digits below a power-of-two row scale, products with i + j >= S are
-dropped, so |C - C_ref| <~ S 2^(-7 S + 2) * sum_k |a||b| -- with S = 8 that is the fp64 rounding level.  Needs a B200."""
+Error model: each operand row is cut into S radix-256 digit planes below a power-of-two row scale, products with i + j >= S
+are dropped, so |C - C_ref| <~ (S + 2) 2^(7 - 8 S) * K * rowmax(a) rowmax(b) -- with S >= 7 that is the fp64 rounding level.
+Needs a B200."""
 import ctypes as C
 
 import numpy as np
@@ -46,7 +47,7 @@ def _ref(a, b):
 
 @pytest.mark.parametrize("m,n,k,nq", [(128, 64, 32, 1), (100, 50, 70, 3), (300, 200, 129, 5), (17, 9, 5, 2), (257, 130, 64, 20)])
 def test_ozaki_small_exact_level(torch_cuda, m, n, k, nq):
-    """8 slices: 55 bits below the row scale -> agreement at the fp64 rounding level; ragged M, N, K and several q-slices."""
+    """8 planes: 64 bits below the row scale -> agreement at the fp64 rounding level; ragged M, N, K and several q-slices."""
     rng = np.random.default_rng(m + n + k)
     a = rng.standard_normal((nq, m, k))
     b = rng.standard_normal((nq, n, k))
@@ -67,19 +68,19 @@ def test_ozaki_integer_inputs_are_exact(torch_cuda):
         assert np.array_equal(c, _ref(a, b)), s
 
 
-@pytest.mark.parametrize("slices", [4, 5, 6, 7, 8])
+@pytest.mark.parametrize("slices", [3, 4, 5, 6, 7, 8])
 def test_ozaki_error_vs_slices(torch_cuda, slices):
-    """Truncation error drops by 2^-7 per slice; rows with a wide dynamic range (1e-6 .. 1) inside one scale group."""
+    """Truncation error drops by 2^-8 per plane; rows with a wide dynamic range (1e-6 .. 1) inside one scale group."""
     rng = np.random.default_rng(9)
     nq, m, n, k = 6, 200, 150, 300
     a = rng.standard_normal((nq, m, k)) * 10.0 ** rng.uniform(-6, 0, (nq, m, k))
     b = rng.standard_normal((nq, n, k)) * 10.0 ** rng.uniform(-6, 0, (nq, n, k))
     c, _ = _ozaki(torch_cuda, a, b, slices, group=2)
     ref = _ref(a, b)
-    # row / column maxima over a group bound every element; products below 2^(-7 S) of (row max * col max) are dropped
+    # row / column maxima over a group bound every element; products below 2^(-8 S) of (row max * col max) are dropped
     amax = np.abs(a).reshape(3, 2, m, k).max(axis=(1, 3))          # [groups, m]
     bmax = np.abs(b).reshape(3, 2, n, k).max(axis=(1, 3))
-    bound = (slices + 1) * 2.0 ** (-7 * slices + 2) * 2 * k * np.einsum("gm,gn->mn", amax, bmax)
+    bound = (slices + 2) * 2.0 ** (7 - 8 * slices) * 2 * k * np.einsum("gm,gn->mn", amax, bmax)
     assert (np.abs(c - ref) <= bound + 1e-15 * np.abs(ref).max()).all(), float((np.abs(c - ref) / bound).max())
 
 
@@ -103,4 +104,70 @@ def test_ozaki_many_groups_and_splits(torch_cuda):
     b = rng.standard_normal((64, 64, 64))
     c, _ = _ozaki(torch_cuda, a, b, 7, group=4)
     ref = _ref(a, b)
-    assert np.abs(c - ref).max() <= 1e-11 * np.abs(ref).max()
+    assert np.abs(c - ref).max() <= 1e-12 * np.abs(ref).max()
+
+
+# ---- the engine's exchange contraction on the emulated path ------------------------------------------------------------
+@pytest.mark.parametrize("slices,tol", [(8, 1e-12), (7, 1e-12), (6, 1e-11), (5, 1e-9)])
+@pytest.mark.parametrize("method", ["sf", "xtda"])
+def test_engine_emulated_exchange(torch_cuda, monkeypatch, slices, tol, method):
+    """SF-TDA / X-TDA sigma with the uniform-weight exchange contraction on the INT8 tensor cores against the oracle, with
+    several aux chunks (ragged last group: naux = 61), several tiles in M and N, 5 vectors."""
+    from oracle import sigma as osig
+    from xtddft_b200 import plan as planmod
+    from xtddft_b200.engine import SigmaEngine
+    from xtddft_b200.synth import make_problem
+    monkeypatch.setenv("XTD_CHUNK_AUX", "16")
+    p = make_problem(200, 30, 2, 168, 61, 300, xctype="LDA", hyb=0.5, seed=400)
+    if method == "sf":
+        vind, hd = osig.sf_gen_vind(p, -1, 0)
+        plan = planmod.build_sf_plan(p, isf=-1, method=0)
+    else:
+        vind, hd = osig.xtda_gen_vind(p)
+        plan = planmod.build_xtda_plan(p)
+    z = np.random.default_rng(1).standard_normal((5, hd.size))
+    ref = vind(z)
+    eng = SigmaEngine.from_problem(plan, p, workspace_bytes=256 << 20, max_nvec=6, exchange_slices=slices, df_chunk=24)
+    got = eng.sigma(torch_cuda.from_numpy(z).cuda()).cpu().numpy()
+    assert eng.last_chunks()[0] == 4
+    err = float(np.abs(got - ref).max() / max(1.0, np.abs(ref).max()))
+    assert err < tol, err
+    st = eng.stats()
+    assert st["ms"]["k2_slice"] > 0 and st["ms"]["k2"] > 0
+    eng.close()
+
+
+def test_engine_emulated_exchange_ragged_chunks_and_shards(torch_cuda):
+    """Chunks that are not multiples of the scale group (the engine carries the remainder over) and a 3-way aux shard whose
+    partial buffers must add up to the oracle."""
+    import ctypes as C
+    from oracle import sigma as osig
+    from xtddft_b200 import _lib
+    from xtddft_b200 import plan as planmod
+    from xtddft_b200.engine import SigmaEngine, _as_tensor
+    from xtddft_b200.synth import make_problem
+    torch = torch_cuda
+    p = make_problem(60, 10, 2, 48, 37, 100, xctype="LDA", hyb=0.5, seed=401)
+    vind, hd = osig.sf_gen_vind(p, -1, 0)
+    plan = planmod.build_sf_plan(p, isf=-1, method=0)
+    z = np.random.default_rng(2).standard_normal((3, hd.size))
+    ref = vind(z)
+    eng = SigmaEngine.from_problem(plan, p, workspace_bytes=128 << 20, max_nvec=4, exchange_slices=8, df_chunk=13)
+    got = eng.sigma_host(z)
+    assert np.abs(got - ref).max() < 1e-12 * max(1.0, np.abs(ref).max())
+    eng.close()
+    zt = torch.from_numpy(z).cuda()
+    acc = None
+    for r in range(3):
+        eng = SigmaEngine.from_problem(plan, p, workspace_bytes=128 << 20, max_nvec=4, rank=r, world=3, exchange_slices=8)
+        _lib.check(eng.lib.xtd_sigma_partial(eng._h, 3, C.c_void_p(zt.data_ptr())), "partial")
+        ptr, n = C.c_void_p(), C.c_long()
+        _lib.check(eng.lib.xtd_partial_buffer(eng._h, 3, C.byref(ptr), C.byref(n)), "buffer")
+        part = _as_tensor(torch, ptr.value, n.value, eng.device).clone()
+        acc = part if acc is None else acc + part
+        if r == 2:
+            _as_tensor(torch, ptr.value, n.value, eng.device).copy_(acc)
+            out = torch.empty_like(zt)
+            _lib.check(eng.lib.xtd_sigma_finish(eng._h, 3, C.c_void_p(out.data_ptr())), "finish")
+            assert np.abs(out.cpu().numpy() - ref).max() < 1e-12 * max(1.0, np.abs(ref).max())
+        eng.close()

@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(HERE, "libxtdsigma.so")
 
 XTD_FXC_NONE, XTD_FXC_UKS, XTD_FXC_ALDA0, XTD_FXC_MCOL, XTD_FXC_UKS_TAU, XTD_FXC_MCOL_TAU = 0, 1, 2, 3, 4, 5
 XTD_SIDE_RIGHT, XTD_SIDE_LEFT = 0, 1
-T_NAMES = ["pack", "xc_gemm", "xc_stream", "k1", "k2", "j", "local", "unpack", "total"]
+T_NAMES = ["pack", "xc_gemm", "xc_stream", "k1", "k2", "j", "local", "unpack", "total", "k2_slice"]
 
 
 class XtdError(RuntimeError):
@@ -36,6 +36,7 @@ SIGNATURES = {
     "xtd_add_kterm": (_I, [_P, _I, _I, _P, _I, _I]),
     "xtd_add_jblock": (_I, [_P, _I, _I, _I, _I, _I]),
     "xtd_set_jmix": (_I, [_P, _P, _I]),
+    "xtd_set_exchange_emulation": (_I, [_P, _I]),
     "xtd_df_begin": (_I, [_P, _I, _L]),
     "xtd_df_add": (_I, [_P, _I, _P, _L, _L, _L, _I]),
     "xtd_jblock_diag": (_I, [_P, _I, _P]),

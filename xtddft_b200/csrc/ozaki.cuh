@@ -3,13 +3,15 @@
 //   C[m][n] (+)= alpha * sum_q sum_k A[q][m][k] * B[q][n][k]                      (fp64 in, fp64 out)
 //
 // tcgen05 has no f64 kind, and the warp-level DMMA pipe tops out at 37 TFLOP/s.  Here every fp64 operand row is scaled by a
-// power of two per (row, group of `group` q-slices) and cut into S signed 7-bit digits (int8 slices, radix 128):
-//   x = scale * sum_l d_l 2^(-7 l),  d_l in [-64, 64]
-// so that  A.B = sa sb sum_{i+j < S} 2^(-7(i+j)) (A_i . B_j)  with every A_i . B_j an EXACT int8 x int8 -> int32 product on
-// `tcgen05.mma.kind::i8`; the S(S+1)/2 slice products are accumulated per level l = i + j in S separate TMEM accumulators
-// (128 lanes x 64 columns each, S <= 8 fills the 512 columns) over one group, then read back with tcgen05.ld, recombined
-// in fp64 (Horner in 2^-7), scaled and added to fp64 register accumulators.  Terms with i + j >= S (below 2^(-7S) of the row
-// scale) are dropped.  int32 never overflows: |d_i d_j| <= 2^12, (l+1) products per level, group * K <= 2^19 / S terms.
+// power of two per (row, group of `group` q-slices) and cut into S balanced radix-256 digits (signed 8-bit planes):
+//   x = scale * sum_l d_l 2^(-8 l),  d_0 in [-64, 64],  d_l in [-128, 127] (l >= 1)                 -> 8 S - 2 bits below the row scale
+// (floor digits first, then a carry pass from the least significant digit turns [0, 255] into [-128, 127]: balanced digits keep
+// the dropped products zero-mean, so their sum over a long contraction grows like sqrt(K), not K), so that
+//   A.B = sa sb sum_{i+j < S} 2^(-8(i+j)) (A_i . B_j)   with every A_i . B_j an EXACT int8 x int8 -> int32 product on
+// `tcgen05.mma.kind::i8`; the S(S+1)/2 plane products are accumulated per level l = i + j in S separate TMEM accumulators
+// (128 lanes x 64 columns each, S <= 8 fills the 512 columns) over one group, then read back with tcgen05.ld, recombined in
+// fp64 (Horner in 2^-8), scaled and added to fp64 register accumulators.  Terms with i + j >= S (below 2^(-8S) of the row
+// scale) are dropped.  int32 never overflows: |d_i d_j| <= 2^14, at most S products per level and k, `group` bounded accordingly.
 //
 // Sliced operands live in HBM pre-tiled as shared-memory images, so a pipeline stage is two plain bulk copies
 // (cp.async.bulk, no tensor map):   [q][row tile][k block of 32][slice][ 2 chunks x RT rows x 16 bytes ]
@@ -88,7 +90,7 @@ __global__ void __launch_bounds__(128) oz_slice_kernel(int8_t* __restrict__ out,
   }
   // 1 / scale for a power of two: flip the exponent
   const double inv = sc > 0.0 ? __hiloint2double(0x7fe00000 - __double2hiint(sc), 0) : 0.0;
-  const double magic = 6755399441055744.0;   // 1.5 * 2^52: (t + magic) has rint(t) in its low mantissa bits (two's complement)
+  const double magic = 6755399441055744.0;   // 1.5 * 2^52: RD(t + magic) has floor(t) in its low mantissa bits (two's complement)
   uint32_t pk[S][4];
 #pragma unroll
   for (int sl = 0; sl < S; ++sl)
@@ -97,13 +99,24 @@ __global__ void __launch_bounds__(128) oz_slice_kernel(int8_t* __restrict__ out,
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
     double t = x[k] * inv;                    // |t| < 64
+    int dg[S];
 #pragma unroll
     for (int sl = 0; sl < S; ++sl) {
-      const double u = (sl == 0) ? (t + magic) : fma(t, 128.0, magic);
+      const double u = (sl == 0) ? __dadd_rd(t, magic) : __fma_rd(t, 256.0, magic);      // floor: the remainder stays in [0, 1)
       const double qd = u - magic;
-      t = (sl == 0) ? (t - qd) : fma(t, 128.0, -qd);
-      pk[sl][k >> 2] |= ((uint32_t)__double2loint(u) & 0xffu) << ((k & 3) * 8);
+      t = (sl == 0) ? (t - qd) : fma(t, 256.0, -qd);
+      dg[sl] = __double2loint(u);             // floor(t) in [-64, 63], then digits in [0, 255]
     }
+    int carry = 0;                            // balance: [0, 255] -> [-128, 127] with a carry into the next higher digit
+#pragma unroll
+    for (int sl = S - 1; sl >= 1; --sl) {
+      const int v = dg[sl] + carry;
+      carry = v >= 128 ? 1 : 0;
+      dg[sl] = v - (carry << 8);
+    }
+    dg[0] += carry;
+#pragma unroll
+    for (int sl = 0; sl < S; ++sl) pk[sl][k >> 2] |= ((uint32_t)dg[sl] & 0xffu) << ((k & 3) * 8);
   }
   int8_t* dst = out + ((((long)q * nrt + rt) * nkb + (c2 >> 1)) * S) * ((long)RT * OZ_KB) + (long)(c2 & 1) * RT * 16 + (long)r * 16;
 #pragma unroll
@@ -291,7 +304,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const OzGemmPara
           oz_tmem_ld16(taddr + (uint32_t)(l * OZ_BN + c0), r);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int k = 0; k < 16; ++k) v[k] = fma(v[k], 0.0078125, (double)(int)r[k]);
+          for (int k = 0; k < 16; ++k) v[k] = fma(v[k], 0.00390625, (double)(int)r[k]);
         }
 #pragma unroll
         for (int k = 0; k < 16; ++k) acc[c0 + k] = fma(v[k], sa * sb[c0 + k], acc[c0 + k]);
@@ -327,10 +340,11 @@ struct OzShape {
 
 inline size_t oz_gemm_smem(int S) { return (size_t)OZ_STAGES * S * (OZ_BM + OZ_BN) * OZ_KB + 256; }
 
-// the largest group (q-slices sharing one scale and one int32 accumulation) that cannot overflow: group * nkb * 32 * S * 2^12 < 2^31
+// the largest group (q-slices sharing one scale and one int32 accumulation) that cannot overflow: per k a level holds at most
+// S products of magnitude <= 2^14
 inline int oz_max_group(int K, int S) {
   const long kpad = round_up(K, OZ_KB);
-  const long g = ((1L << 19) - 1) / ((long)S * kpad);
+  const long g = ((1L << 31) - 1) / ((long)S * 16384 * kpad);
   return (int)std::max<long>(g, 0);
 }
 

@@ -61,6 +61,12 @@ struct Channel {
   int tail_start = 0, tail_w = 0;   // (a short column tail of the block-weighted output takes the same pass)
   long ldoo, ldvv;
   bool need_k[2] = {false, false};
+  // INT8-emulated exchange contraction (ozaki.cuh): Lvv kept only as int8 slices + row scales, no fp64 copy
+  bool use_oz[2] = {false, false};
+  int8_t* LvvS[2] = {nullptr, nullptr};     // [naux_loc][nnt][nkb][S][64 x 32]
+  double* LvvScale[2] = {nullptr, nullptr}; // [groups][rows_pad]
+  OzShape ozB;
+  int oz_group = 0;
   DevBuf phi;                       // occupied values on the grid  [nvar_eff][ng][ldphi]
   long ldphi = 0;
   DevBuf phiv;                      // virtual values on the grid   [nvar_eff][ng][ldphiv]
@@ -180,6 +186,7 @@ struct xtd_engine {
   // XTD_CHUNK_AUX / XTD_CHUNK_GRID: upper bounds on the aux / grid chunk of a call (tests force the multi-chunk loops that
   // BASELINE-size runs take at oracle-sized inputs); the chunk counts of the last call are reported by xtd_last_chunks
   long max_pc = 0, max_gb = 0;
+  int oz_slices = 0;              // 0: FP64 DMMA exchange contraction; 3..8: INT8 tensor-core emulation with that many slices
   long last_aux_chunks = 0, last_grid_chunks = 0;
   // Launch-bound calls (small molecules: ~50-100 launches of a few microseconds each) are replayed as CUDA graphs: the
   // first call with a given (nvec, z, hz) runs eagerly, the second is captured, later ones are one cudaGraphLaunch.
@@ -412,6 +419,7 @@ int xtd_destroy(xtd_handle h) {
   for (auto* c : h->ch) {
     c->Co.release(); c->Cv.release(); c->CoT.release(); c->CvT.release(); c->phi.release(); c->phiv.release();
     for (int t = 0; t < 2; ++t) { c->Loo[t].release(); c->Lvv[t].release(); c->Lvo[t].release(); c->Lvt[t].release(); c->Loob[t][0].release(); c->Loob[t][1].release(); }
+    for (int t = 0; t < 2; ++t) { if (c->LvvS[t]) cudaFree(c->LvvS[t]); if (c->LvvScale[t]) cudaFree(c->LvvScale[t]); }
     if (c->g_indptr) cudaFree(c->g_indptr);
     if (c->g_cols) cudaFree(c->g_cols);
     if (c->g_vals) cudaFree(c->g_vals);
@@ -542,6 +550,15 @@ int xtd_set_jmix(xtd_handle h, const double* mix, int n) {
   return XTD_OK;
 }
 
+int xtd_set_exchange_emulation(xtd_handle h, int slices) {
+  XTD_REQUIRE(h && !h->finalized, XTD_ERR_STATE, "xtd_set_exchange_emulation after finalize");
+  XTD_REQUIRE(slices == 0 || (slices >= OZ_MIN_S && slices <= OZ_MAX_S), XTD_ERR_ARG, "xtd_set_exchange_emulation: slices %d (0 or %d..%d)", slices,
+              OZ_MIN_S, OZ_MAX_S);
+  XTD_REQUIRE(h->naux_filled[0] == 0 && h->naux_filled[1] == 0, XTD_ERR_STATE, "xtd_set_exchange_emulation must precede xtd_df_add");
+  h->oz_slices = slices;
+  return XTD_OK;
+}
+
 int xtd_df_begin(xtd_handle h, int tensor, long naux_local) {
   XTD_REQUIRE(h && (tensor == 0 || tensor == 1) && naux_local >= 0, XTD_ERR_ARG, "xtd_df_begin: bad arguments");
   h->naux[tensor] = naux_local;
@@ -549,7 +566,26 @@ int xtd_df_begin(xtd_handle h, int tensor, long naux_local) {
   for (auto* c : h->ch) {
     if (!c->need_k[tensor]) continue;
     XTD_TRY(c->Loo[tensor].alloc((size_t)naux_local * c->no * c->ldoo, h->stream));
-    XTD_TRY(c->Lvv[tensor].alloc((size_t)naux_local * c->nv * c->ldvv, h->stream));
+    // emulated path: every exchange term on this (tensor, channel) has uniform weights (no block-weighted pass reads fp64 Lvv)
+    c->use_oz[tensor] = false;
+    if (h->oz_slices > 0 && oz_max_group(c->nv, h->oz_slices) >= 1) {
+      bool all_uniform = true;
+      for (const KTermRec& k : h->kterms)
+        if (k.tensor == tensor && h->ch[k.ch] == c && !k.uniform) all_uniform = false;
+      c->use_oz[tensor] = all_uniform;
+    }
+    if (c->use_oz[tensor]) {
+      c->ozB.set(c->nv, OZ_BN, c->nv);
+      c->oz_group = std::min(4, oz_max_group(c->nv, h->oz_slices));
+      if (c->LvvS[tensor]) cudaFree(c->LvvS[tensor]);
+      if (c->LvvScale[tensor]) cudaFree(c->LvvScale[tensor]);
+      c->LvvS[tensor] = nullptr; c->LvvScale[tensor] = nullptr;
+      XTD_CUDA(cudaMalloc((void**)&c->LvvS[tensor], std::max<size_t>(c->ozB.slice_bytes(naux_local, h->oz_slices), 16)));
+      XTD_CUDA(cudaMalloc((void**)&c->LvvScale[tensor], std::max<size_t>(c->ozB.scale_doubles(naux_local, c->oz_group), 2) * 8));
+      c->Lvv[tensor].release();
+    } else {
+      XTD_TRY(c->Lvv[tensor].alloc((size_t)naux_local * c->nv * c->ldvv, h->stream));
+    }
     if (c->need_narrow[tensor]) XTD_TRY(c->Lvo[tensor].alloc((size_t)naux_local * c->v_blocks[1].first * c->ldvv, h->stream));
     if (c->need_narrow[tensor] && c->tail_w > 0) XTD_TRY(c->Lvt[tensor].alloc((size_t)naux_local * c->tail_w * c->ldvv, h->stream));
     if (c->need_split[tensor]) {
@@ -585,13 +621,28 @@ int xtd_df_add(xtd_handle h, int tensor, const double* l_dev, long np, long ld_r
   size_t split_bytes = std::min<size_t>(h->arena.cap / 4, (size_t)1 << 30);
   h->gemm.split_ws = h->arena.take(split_bytes / 8);
   h->gemm.split_ws_bytes = split_bytes;
-  const size_t per_p = ((size_t)(direct ? 0 : N) + (size_t)max_n) * ldN;
+  size_t oz_tmp = 0;       // emulated path: the fp64 Lvv chunk is a temporary that is cut into int8 slices
+  long oz_align = 1;
+  for (auto* c : h->ch)
+    if (c->use_oz[tensor]) {
+      oz_tmp = std::max(oz_tmp, (size_t)c->nv * c->ldvv);
+      oz_align = std::max<long>(oz_align, c->oz_group);
+    }
+  if (oz_tmp) {
+    const bool last = h->naux_filled[tensor] + np == h->naux[tensor];
+    XTD_REQUIRE(h->naux_filled[tensor] % oz_align == 0 && (np % oz_align == 0 || last), XTD_ERR_ARG,
+                "xtd_df_add: with the INT8-emulated exchange contraction every chunk but the last must hold a multiple of %ld aux functions",
+                oz_align);
+  }
+  const size_t per_p = ((size_t)(direct ? 0 : N) + (size_t)max_n) * ldN + oz_tmp;
   long pc = (long)(h->arena.left() / 8 / per_p);
-  XTD_REQUIRE(pc >= 1, XTD_ERR_NOMEM, "xtd_df_add: workspace too small for one aux function (%zu doubles needed)", per_p);
+  XTD_REQUIRE(pc >= oz_align, XTD_ERR_NOMEM, "xtd_df_add: workspace too small for %ld aux functions (%zu doubles each)", oz_align, per_p);
   pc = std::min<long>(pc, np);
+  if (pc < np) pc = pc / oz_align * oz_align;
   double* stage = direct ? nullptr : h->arena.take((size_t)pc * N * ldN);
   double* half = h->arena.take((size_t)pc * max_n * ldN);
-  XTD_REQUIRE(half && (direct || stage), XTD_ERR_NOMEM, "xtd_df_add: workspace exhausted");
+  double* lvv_tmp = oz_tmp ? h->arena.take((size_t)pc * oz_tmp) : nullptr;
+  XTD_REQUIRE(half && (direct || stage) && (!oz_tmp || lvv_tmp), XTD_ERR_NOMEM, "xtd_df_add: workspace exhausted");
 
   for (long p0 = 0; p0 < np; p0 += pc) {
     const int pn = (int)std::min<long>(pc, np - p0);
@@ -663,8 +714,13 @@ int xtd_df_add(xtd_handle h, int tensor, const double* l_dev, long np, long ld_r
         GemmDesc e;
         e.A = view3d(half, ldN, (long)c->nv * ldN, pn, c->nv, N); e.B = view2d(c->CvT.p, ldN, c->nv, N);
         e.M = c->nv; e.N = c->nv; e.K = N; e.batches = pn; e.a_hi = 1; e.b_hi = 0;
-        e.C = c->Lvv[tensor].p + P0 * c->nv * c->ldvv; e.ldc = c->ldvv; e.c_batch_stride = (long)c->nv * c->ldvv;
+        e.C = c->use_oz[tensor] ? lvv_tmp : c->Lvv[tensor].p + P0 * c->nv * c->ldvv;
+        e.ldc = c->ldvv; e.c_batch_stride = (long)c->nv * c->ldvv;
         XTD_TRY(gemm(h->gemm, e, s));
+        if (c->use_oz[tensor])
+          XTD_TRY(oz_slice(h->oz_slices, c->LvvS[tensor] + c->ozB.slice_bytes(P0, h->oz_slices),
+                           c->LvvScale[tensor] + (size_t)(P0 / c->oz_group) * c->ozB.rows_pad, c->ozB, lvv_tmp, c->ldvv, (long)c->nv * c->ldvv, pn,
+                           c->oz_group, s));
         if (c->need_narrow[tensor]) {
           const size_t v2 = (size_t)c->v_blocks[1].first;
           XTD_CUDA(cudaMemcpy2DAsync(c->Lvo[tensor].p + P0 * v2 * c->ldvv, v2 * c->ldvv * 8, c->Lvv[tensor].p + P0 * c->nv * c->ldvv,
@@ -1026,6 +1082,77 @@ static int run_xc(xtd_engine* h, int nvec) {
   return XTD_OK;
 }
 
+// Uniform-weight exchange term with the contraction over (P, b) emulated on the INT8 tensor cores:
+//   K1 (DMMA)   U[P][(i,x)][b] = sum_j Loo[(P,i)][j] zt[x][b][j]            as in run_k
+//   slice       U -> S int8 digit planes + one power-of-two scale per (row, group of aux functions)
+//   K2 (tcgen05.mma kind::i8, TMEM)   SIG[x][i][a] += w sum_P sum_b U[P][(i,x)][b] Lvv[P][a][b]   against the int8 planes of Lvv
+static int run_k_emulated(xtd_engine* h, const KTermRec& k, int nvec) {
+  cudaStream_t s = h->stream;
+  Channel* ch = h->ch[k.ch];
+  const long naux = h->naux[k.tensor];
+  const int S = h->oz_slices, G = ch->oz_group;
+  OzShape shA;
+  shA.set(nvec * ch->no, OZ_BM, ch->nv);
+  const OzShape& shB = ch->ozB;
+  const int tiles = shA.nrt * shB.nrt;
+  // scratch: W [splits][Mpad][Npad] | per aux function: U fp64 + int8 planes (+ scales per group)
+  int splits_max = std::min<long>(64, std::max<long>(1, cdiv(naux, G)));
+  size_t w_doubles = (size_t)splits_max * shA.rows_pad * shB.rows_pad;
+  while (splits_max > 1 && w_doubles * 4 > h->scratch_doubles) { splits_max /= 2; w_doubles = (size_t)splits_max * shA.rows_pad * shB.rows_pad; }
+  const size_t u_per_p = (size_t)nvec * ch->no * ch->ldz;
+  const size_t a_per_p = shA.slice_bytes(1, S) / 8;
+  const size_t per_p = u_per_p + a_per_p + (size_t)cdiv(shA.rows_pad, G) + 1;
+  XTD_REQUIRE(h->scratch_doubles > w_doubles + (size_t)G * per_p + 4096, XTD_ERR_NOMEM,
+              "workspace too small for one group of the emulated exchange contraction");
+  long pc = (long)((h->scratch_doubles - w_doubles - 4096) / per_p);
+  pc = std::min<long>(pc, naux);
+  if ((long)pc * nvec > 65535) pc = 65535 / nvec;
+  if (pc > 32768) pc = 32768;
+  if (h->max_pc > 0) pc = std::min<long>(pc, h->max_pc);
+  if (pc < naux) pc = std::max<long>(pc / G * G, G);
+  h->last_aux_chunks = std::max<long>(h->last_aux_chunks, cdiv(naux, pc));
+  double* W = h->scratch;
+  double* U = W + ((w_doubles + 31) & ~(size_t)31);
+  int8_t* As = reinterpret_cast<int8_t*>(U + (((size_t)pc * u_per_p + 31) & ~(size_t)31));
+  double* sa = reinterpret_cast<double*>(As) + (((size_t)pc * a_per_p + 31) & ~(size_t)31);
+  const double* Loo = ch->Loo[k.tensor].p;
+  for (long P0 = 0; P0 < naux; P0 += pc) {
+    const int pn = (int)std::min<long>(pc, naux - P0);
+    {
+      PhaseTimer t(h, XTD_T_K1);
+      GemmDesc d;
+      d.A = view2d(Loo + P0 * ch->no * ch->ldoo, ch->ldoo, pn * ch->no, ch->no);
+      d.B = view3d(h->ZT[k.ch], ch->ldzt, (long)ch->nv * ch->ldzt, nvec, ch->nv, ch->no);
+      d.M = pn * ch->no; d.N = ch->nv; d.K = ch->no;
+      d.batches = nvec; d.z_div = 1; d.a_hi = 0; d.b_hi = 1;
+      d.C = U; d.ldc = (long)nvec * ch->ldz; d.c_batch_stride = ch->ldz;
+      XTD_TRY(gemm(h->gemm, d, s));
+    }
+    {
+      PhaseTimer t(h, XTD_T_K2_SLICE);
+      XTD_TRY(oz_slice(S, As, sa, shA, U, ch->ldz, (long)u_per_p, pn, G, s));
+    }
+    {
+      PhaseTimer t(h, XTD_T_K2);
+      OzGemmParams p;
+      p.A = As; p.B = ch->LvvS[k.tensor]; p.sa = sa; p.sb = ch->LvvScale[k.tensor];
+      p.nmt = shA.nrt; p.nnt = shB.nrt; p.nkb = shA.nkb; p.nq = pn; p.group = G; p.b_q0 = (int)P0;
+      p.Mpad = shA.rows_pad; p.Npad = shB.rows_pad;
+      p.splits = std::min(splits_max, oz_choose_splits(tiles, (int)cdiv(pn, G), h->gemm.num_sms));
+      p.W = W; p.alpha = k.w[0][0][0][0];
+      XTD_TRY(oz_gemm(S, p, s));
+      const int M = nvec * ch->no, N = ch->nv;
+      const long nblk = cdiv((long)M * N, 256);
+      reduce_splits_kernel<<<dim3((unsigned)(nblk > 4096 ? 4096 : nblk), 1), 256, 0, s>>>(
+          h->SIG + h->sig_base[k.ch], ch->ldz, 0, W, shB.rows_pad, 0, (long)shA.rows_pad * shB.rows_pad, p.splits, M, N, 1, nvec, ch->ldz,
+          (long)ch->no * ch->ldz);
+      LAUNCH_CHECK();
+      h->gemm.flops += 2.0 * M * N * (double)ch->nv * pn;      // FP64-equivalent flops of the contraction
+    }
+  }
+  return XTD_OK;
+}
+
 static int run_k(xtd_engine* h, int nvec) {
   cudaStream_t s = h->stream;
   for (const KTermRec& k : h->kterms) {
@@ -1034,6 +1161,10 @@ static int run_k(xtd_engine* h, int nvec) {
     if (naux == 0) continue;
     const double* Loo = ch->Loo[k.tensor].p;
     const double* Lvv = ch->Lvv[k.tensor].p;
+    if (ch->use_oz[k.tensor]) {
+      XTD_TRY(run_k_emulated(h, k, nvec));
+      continue;
+    }
     // aux chunk so that U[pc][nvec][no][ldz] fits the scratch region
     const size_t per_p = (size_t)nvec * ch->no * ch->ldz;
     long pc = (long)(h->scratch_doubles / per_p);
@@ -1530,7 +1661,7 @@ int xtd_ozaki_gemm(void* stream, int m, int n, int k, int nq, int slices, int gr
                    const double* b_dev, long ldb, long sqb, double* c_dev, long ldc, double alpha, int accumulate, double* ms_out) {
   XTD_REQUIRE(m > 0 && n > 0 && k > 0 && nq > 0 && a_dev && b_dev && c_dev, XTD_ERR_ARG, "xtd_ozaki_gemm: bad arguments");
   XTD_REQUIRE(slices >= OZ_MIN_S && slices <= OZ_MAX_S, XTD_ERR_ARG, "xtd_ozaki_gemm: slices %d outside %d..%d", slices, OZ_MIN_S, OZ_MAX_S);
-  if (group <= 0) group = std::min(8, oz_max_group(k, slices));
+  if (group <= 0) group = std::min(4, oz_max_group(k, slices));
   XTD_REQUIRE(group >= 1 && group <= oz_max_group(k, slices), XTD_ERR_ARG, "xtd_ozaki_gemm: K = %d too long for one int32 group (max group %d)", k,
               oz_max_group(k, slices));
   cudaStream_t st = (cudaStream_t)stream;

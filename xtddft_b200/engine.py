@@ -11,6 +11,7 @@ inside libxtdsigma.so; if the library is missing, construction fails (no CPU fal
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional
 
 import numpy as np
@@ -38,7 +39,7 @@ def _pad16(n: int) -> int:
 
 class SigmaEngine:
     def __init__(self, plan: Plan, nao: int, mo_coeff: np.ndarray, *, workspace_bytes: int = 2 << 30, device=None,
-                 reducer: Optional[SigmaReducer] = None):
+                 reducer: Optional[SigmaReducer] = None, exchange_slices: Optional[int] = None):
         import torch
         if not torch.cuda.is_available():
             raise _lib.XtdError("SigmaEngine needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -54,6 +55,13 @@ class SigmaEngine:
         self._h = C.c_void_p()
         _lib.check(self.lib.xtd_create(C.byref(self._h), self.nao, int(workspace_bytes)), "xtd_create")
         self._set_stream()
+        # exchange contraction of uniform-weight terms: 0 = FP64 DMMA, 3..8 = INT8 tensor-core emulation with that many
+        # radix-256 digit planes (csrc/ozaki.cuh).  None: the XTD_OZAKI environment variable, else FP64 DMMA.
+        if exchange_slices is None:
+            exchange_slices = int(os.environ.get("XTD_OZAKI", "0") or 0)
+        self.exchange_slices = int(exchange_slices)
+        if self.exchange_slices:
+            _lib.check(self.lib.xtd_set_exchange_emulation(self._h, self.exchange_slices), "xtd_set_exchange_emulation")
         self.finalized = False
         self.max_nvec = 0
         self.ext_dim = int(plan.ext_dim)
@@ -103,10 +111,29 @@ class SigmaEngine:
     # ---- density fitting ----------------------------------------------------------------------------
     def df_begin(self, tensor: int, naux_local: int):
         _lib.check(self.lib.xtd_df_begin(self._h, tensor, int(naux_local)), "xtd_df_begin")
+        self._df_left = getattr(self, "_df_left", {})
+        self._df_carry = getattr(self, "_df_carry", {})
+        self._df_left[tensor] = int(naux_local)
+        self._df_carry[tensor] = None
 
     def df_add(self, tensor: int, chunk, packed: bool = False):
         """chunk: torch cuda fp64 [np, nao, nao] (any row stride) or packed lower-triangular [np, nao(nao+1)/2]."""
         assert chunk.is_cuda and chunk.dtype == self.torch.float64
+        if self.exchange_slices:
+            # emulated exchange: the library wants whole scale groups (<= 4 aux functions) in every chunk but the last;
+            # carry the remainder of a ragged chunk over to the next call
+            carry = self._df_carry.get(tensor)
+            if carry is not None:
+                chunk = self.torch.cat([carry, chunk], dim=0)
+                self._df_carry[tensor] = None
+            n = chunk.shape[0]
+            if n < self._df_left[tensor] and n % 12:
+                keep = n // 12 * 12                      # a multiple of every group size (1, 2, 3, 4)
+                self._df_carry[tensor] = chunk[keep:].clone()
+                chunk = chunk[:keep]
+                if keep == 0:
+                    return
+            self._df_left[tensor] -= chunk.shape[0]
         if packed:
             assert chunk.dim() == 2 and chunk.stride(1) == 1
             _lib.check(self.lib.xtd_df_add(self._h, tensor, _ptr(chunk), chunk.shape[0], 0, chunk.stride(0), 1), "xtd_df_add")
@@ -192,10 +219,11 @@ class SigmaEngine:
 
     @classmethod
     def from_problem(cls, plan: Plan, p: ProblemData, *, max_nvec: int = 40, workspace_bytes: int = 2 << 30, device=None,
-                     reducer: Optional[SigmaReducer] = None, rank: int = 0, world: int = 1, df_chunk: int = 64) -> "SigmaEngine":
+                     reducer: Optional[SigmaReducer] = None, rank: int = 0, world: int = 1, df_chunk: int = 64,
+                     exchange_slices: Optional[int] = None) -> "SigmaEngine":
         """Upload a host ProblemData; with world > 1 this rank keeps only its aux block and grid batch."""
         import torch
-        eng = cls(plan, p.nao, p.mo_coeff, workspace_bytes=workspace_bytes, device=device, reducer=reducer)
+        eng = cls(plan, p.nao, p.mo_coeff, workspace_bytes=workspace_bytes, device=device, reducer=reducer, exchange_slices=exchange_slices)
         g0, g1 = split_range(p.ng, rank, world) if plan.xc_kind != "none" else (0, 0)
         if g1 > g0:                             # a rank whose grid batch is empty simply has no grid term
             ld = _pad16(p.nao)

@@ -35,9 +35,9 @@ def default_workspace_bytes(dp: DeviceProblem, world: int = 1) -> int:
 
 
 def engine_for_device_problem(dp: DeviceProblem, *, max_nvec: int, workspace_bytes: int, rank: int = 0, world: int = 1,
-                              reducer=None) -> SigmaEngine:
+                              reducer=None, exchange_slices=None) -> SigmaEngine:
     plan = plan_for(dp.p, dp.method)
-    eng = SigmaEngine(plan, dp.p.nao, dp.p.mo_coeff, workspace_bytes=workspace_bytes, reducer=reducer)
+    eng = SigmaEngine(plan, dp.p.nao, dp.p.mo_coeff, workspace_bytes=workspace_bytes, reducer=reducer, exchange_slices=exchange_slices)
     dp.make_grid(eng, rank, world)
     eng.grid_commit()                   # MO values on the grid; the AO array is released before the tensor streams in
     eng.torch.cuda.empty_cache()
