@@ -14,8 +14,13 @@
 // scale) are dropped.  int32 never overflows: |d_i d_j| <= 2^14, at most S products per level and k, `group` bounded accordingly.
 //
 // Sliced operands live in HBM pre-tiled as shared-memory images, so a pipeline stage is two plain bulk copies
-// (cp.async.bulk, no tensor map):   [q][row tile][k block of 32][slice][ 2 chunks x RT rows x 16 bytes ]
-// = the canonical no-swizzle K-major UMMA layout (core matrix 8 rows x 16 B; SBO 128 B, LBO RT*16 B).
+// (cp.async.bulk, no tensor map), in the canonical no-swizzle K-major UMMA layout (core matrix 8 rows x 16 B, SBO 128 B):
+//   A  [q][row tile][k block of 32][plane][2 chunks][128 rows][16 B]          one descriptor per plane, LBO 2 KB
+//   B  [q][row tile][k block of 32][2 chunks][plane][ 64 rows][16 B]          planes stacked along N, LBO S KB
+// With the planes of B stacked along N, ONE instruction multiplies plane A_i with planes B_0 .. B_{S-1-i} (N = 64 (S - i),
+// in pieces of <= 256) and lands in the contiguous TMEM columns of levels i .. S-1: 8 (S = 6) instead of 21 MMAs per k-step,
+// and A_i is read from shared memory once or twice instead of S - i times (an N = 64 instruction re-reads 4 KB of A for 2 KB
+// of B: 192 B/clk of shared-memory reads against the 128 B/clk the SM has).
 //
 // Warp roles in a CTA of 192 threads: warp 0 bulk-copy producer, warp 1 MMA issuer (+ TMEM allocation), warps 2-5 epilogue
 // (TMEM lane quadrant = warp % 4).  One CTA per (128 x 64 output tile, split of the group range); partial tiles go to a
@@ -63,7 +68,7 @@ __global__ void oz_rowmax_kernel(double* __restrict__ scale, int rows_pad, const
 template <int S>
 __global__ void __launch_bounds__(128) oz_slice_kernel(int8_t* __restrict__ out, const double* __restrict__ scale, int rows_pad,
                                                        const double* __restrict__ X, long ld, long sq, int rows, int K, int RT, int nkb,
-                                                       int group) {
+                                                       int group, int stacked) {
   const int c2 = blockIdx.x, q = blockIdx.z;
   const int row = blockIdx.y * 128 + threadIdx.x;
   const int rt = row / RT, r = row - rt * RT, nrt = rows_pad / RT;
@@ -118,16 +123,18 @@ __global__ void __launch_bounds__(128) oz_slice_kernel(int8_t* __restrict__ out,
 #pragma unroll
     for (int sl = 0; sl < S; ++sl) pk[sl][k >> 2] |= ((uint32_t)dg[sl] & 0xffu) << ((k & 3) * 8);
   }
-  int8_t* dst = out + ((((long)q * nrt + rt) * nkb + (c2 >> 1)) * S) * ((long)RT * OZ_KB) + (long)(c2 & 1) * RT * 16 + (long)r * 16;
+  // plane-major image (A): [plane][chunk][row]; stacked image (B): [chunk][plane][row]
+  int8_t* dst = out + ((((long)q * nrt + rt) * nkb + (c2 >> 1)) * S) * ((long)RT * OZ_KB) + (long)r * 16 +
+                (stacked ? (long)(c2 & 1) * S * RT * 16 : (long)(c2 & 1) * RT * 16);
+  const long plane = stacked ? (long)RT * 16 : (long)RT * OZ_KB;
 #pragma unroll
-  for (int sl = 0; sl < S; ++sl)
-    *reinterpret_cast<uint4*>(dst + (long)sl * RT * OZ_KB) = make_uint4(pk[sl][0], pk[sl][1], pk[sl][2], pk[sl][3]);
+  for (int sl = 0; sl < S; ++sl) *reinterpret_cast<uint4*>(dst + sl * plane) = make_uint4(pk[sl][0], pk[sl][1], pk[sl][2], pk[sl][3]);
 }
 
 // ---- the INT8 tensor-core kernel ------------------------------------------------------------------------------------------
 struct OzGemmParams {
   const int8_t* A;      // [nq][nmt][nkb][S][128 x 32]
-  const int8_t* B;      // [..][nnt][nkb][S][ 64 x 32], first slice used: b_q0
+  const int8_t* B;      // [..][nnt][nkb][2][S][64 x 16] (planes stacked along N), first slice used: b_q0
   const double* sa;     // [ngroups][Mpad]           (group index relative to this launch)
   const double* sb;     // [..][Npad], first group used: b_q0 / group
   int nmt, nnt, nkb, nq, group, b_q0;
@@ -165,6 +172,26 @@ __device__ __forceinline__ void oz_bulk_load(void* dst, const void* src, uint32_
                "r"(bytes), "r"(oz_smem_u32(bar))
                : "memory");
 }
+// the same copy delivered to the same shared-memory offset (and signalled on the same barrier offset) of every CTA in `mask`
+__device__ __forceinline__ void oz_bulk_load_mc(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+                   oz_smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(oz_smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void oz_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(oz_smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t oz_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void oz_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // shared-memory matrix descriptor, K-major, no swizzle: start address, leading (K-direction) and stride (row-group) byte offsets
 __device__ __forceinline__ uint64_t oz_smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
   return (uint64_t)((addr & 0x3ffffu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
@@ -190,7 +217,9 @@ __device__ __forceinline__ void oz_tmem_ld16(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
 }
 
-template <int S>
+// CN = CTAs per cluster along N: they share the A tile (same output row tile, consecutive column tiles); each loads 1 / CN of
+// every A stage and multicasts it to the whole cluster, so the L2 -> SM traffic per MMA drops from A + B to A / CN + B.
+template <int S, int CN>
 __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const OzGemmParams p) {
   constexpr int A_SLICE = OZ_BM * OZ_KB, B_SLICE = OZ_BN * OZ_KB;
   constexpr int A_BYTES = S * A_SLICE, B_BYTES = S * B_SLICE, STAGE = A_BYTES + B_BYTES;
@@ -207,10 +236,12 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const OzGemmPara
   const int ngroups = (p.nq + p.group - 1) / p.group;
   const int g0 = (int)((long)ngroups * sp / p.splits), g1 = (int)((long)ngroups * (sp + 1) / p.splits);
 
+  const uint32_t crank = CN > 1 ? oz_cluster_rank() : 0u;
+  constexpr uint16_t cmask = (uint16_t)((1u << CN) - 1u);
   if (threadIdx.x == 0) {
     for (int s = 0; s < OZ_STAGES; ++s) {
       oz_mbar_init(&full[s], 1);
-      oz_mbar_init(&empty[s], 1);
+      oz_mbar_init(&empty[s], CN);          // a stage is rewritten by every CTA of the cluster: all of them must have drained it
     }
     oz_mbar_init(tmem_full, 1);
     oz_mbar_init(tmem_empty, 128);
@@ -223,6 +254,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const OzGemmPara
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (CN > 1) oz_cluster_sync();            // every CTA's barriers exist before the first multicast copy / arrive
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
@@ -241,7 +273,12 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const OzGemmPara
             oz_mbar_wait(&empty[s], ph ^ 1u);
             oz_mbar_expect_tx(&full[s], STAGE);
             uint8_t* sa = oz_smem + s * STAGE;
-            oz_bulk_load(sa, a + (long)kb * A_BYTES, A_BYTES, &full[s]);
+            if (CN == 1) {
+              oz_bulk_load(sa, a + (long)kb * A_BYTES, A_BYTES, &full[s]);
+            } else {
+              constexpr int PART = A_BYTES / CN;
+              oz_bulk_load_mc(sa + crank * PART, a + (long)kb * A_BYTES + crank * PART, PART, &full[s], cmask);
+            }
             oz_bulk_load(sa + A_BYTES, b + (long)kb * B_BYTES, B_BYTES, &full[s]);
           }
         }
@@ -250,8 +287,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const OzGemmPara
   } else if (warp == 1) {
     // ===================== MMA issuer: S(S+1)/2 int8 MMAs per k-step, one accumulator per level i + j =====================
     if (lane == 0) {
-      // instruction descriptor: D = s32, A = B = signed int8, both K-major, N = 64, M = 128
-      constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
+      // instruction descriptor: D = s32, A = B = signed int8, both K-major, M = 128; N = 64 x (planes of B in the instruction)
+      constexpr uint32_t idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24);
       const uint32_t smem_base = oz_smem_u32(oz_smem);
       long it = 0;
       for (int g = g0; g < g1; ++g) {
@@ -269,13 +306,17 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const OzGemmPara
 #pragma unroll
           for (int i = 0; i < S; ++i) {
             const uint64_t da = oz_smem_desc(a_base + i * A_SLICE, OZ_BM * 16, 128);
+            // planes B_0 .. B_{S-1-i} at once, in pieces of at most 256 columns: levels i .. S-1
 #pragma unroll
-            for (int j = 0; j < S - i; ++j) {
-              const uint64_t db = oz_smem_desc(b_base + j * B_SLICE, OZ_BN * 16, 128);
-              oz_mma_i8(tmem_base + (uint32_t)((i + j) * OZ_BN), da, db, idesc, (i > 0) ? 1u : later);
+            for (int j0 = 0; j0 < S - i; j0 += 4) {
+              const int nj = (S - i - j0) < 4 ? (S - i - j0) : 4;
+              const uint64_t db = oz_smem_desc(b_base + j0 * (OZ_BN * 16), S * OZ_BN * 16, 128);
+              const uint32_t idesc = idesc0 | ((uint32_t)((nj * OZ_BN) >> 3) << 17);
+              oz_mma_i8(tmem_base + (uint32_t)((i + j0) * OZ_BN), da, db, idesc, (i > 0) ? 1u : later);
             }
           }
-          oz_commit(&empty[s]);      // frees the stage when these MMAs have read it
+          if (CN == 1) oz_commit(&empty[s]);      // frees the stage when these MMAs have read it
+          else oz_commit_mc(&empty[s], cmask);    // ... in every CTA of the cluster (each of them writes a part of it)
         }
         oz_commit(tmem_full);        // all levels of this group are complete
       }
@@ -319,6 +360,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const OzGemmPara
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (CN > 1) oz_cluster_sync();            // no CTA leaves while a peer may still multicast into it or arrive on its barriers
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -356,7 +398,7 @@ inline int oz_slice_launch(int8_t* out, double* scale, const OzShape& sh, const 
   XTD_COUNT_LAUNCH();
   XTD_CUDA(cudaGetLastError());
   oz_slice_kernel<S><<<dim3(2 * sh.nkb, sh.rows_pad / 128, nq), 128, 0, st>>>(out, scale, sh.rows_pad, X, ld, sq, sh.rows, sh.K, sh.RT, sh.nkb,
-                                                                             group);
+                                                                             group, sh.RT == OZ_BN ? 1 : 0);
   XTD_COUNT_LAUNCH();
   XTD_CUDA(cudaGetLastError());
   return XTD_OK;
@@ -378,19 +420,52 @@ inline int oz_slice(int S, int8_t* out, double* scale, const OzShape& sh, const 
   return XTD_ERR_ARG;
 }
 
-template <int S>
-inline int oz_gemm_launch(const OzGemmParams& p, cudaStream_t st) {
+template <int S, int CN>
+inline int oz_gemm_launch_cn(const OzGemmParams& p, cudaStream_t st) {
   static bool attr_set[64] = {false};
   int dev = 0;
   XTD_CUDA(cudaGetDevice(&dev));
   if (!attr_set[dev & 63]) {
-    XTD_CUDA(cudaFuncSetAttribute(oz_gemm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_gemm_smem(S)));
+    XTD_CUDA(cudaFuncSetAttribute(oz_gemm_kernel<S, CN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_gemm_smem(S)));
     attr_set[dev & 63] = true;
   }
-  oz_gemm_kernel<S><<<(unsigned)(p.nmt * p.nnt * p.splits), OZ_THREADS, oz_gemm_smem(S), st>>>(p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(p.nmt * p.nnt * p.splits));
+  cfg.blockDim = dim3(OZ_THREADS);
+  cfg.dynamicSmemBytes = oz_gemm_smem(S);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CN;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  XTD_CUDA(cudaLaunchKernelEx(&cfg, oz_gemm_kernel<S, CN>, p));
   XTD_COUNT_LAUNCH();
   XTD_CUDA(cudaGetLastError());
   return XTD_OK;
+}
+
+// cluster width along N: the widest of 4, 2, 1 that divides the number of column tiles (XTD_OZ_CLUSTER overrides)
+inline int oz_cluster_width(int nnt) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("XTD_OZ_CLUSTER");
+    forced = e ? atoi(e) : 0;
+  }
+  int cn = forced > 0 ? forced : 2;
+  while (cn > 1 && nnt % cn) cn /= 2;
+  return cn;
+}
+
+template <int S>
+inline int oz_gemm_launch(const OzGemmParams& p, cudaStream_t st) {
+  switch (oz_cluster_width(p.nnt)) {
+    case 4: return oz_gemm_launch_cn<S, 4>(p, st);
+    case 2: return oz_gemm_launch_cn<S, 2>(p, st);
+    default: return oz_gemm_launch_cn<S, 1>(p, st);
+  }
 }
 
 inline int oz_gemm(int S, const OzGemmParams& p, cudaStream_t st) {
