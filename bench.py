@@ -43,6 +43,21 @@ def _hbm_peak():
 HBM_PEAK_GBS, HBM_PEAK_SOURCE = _hbm_peak()
 
 
+def _int8_peak():
+    """Dense INT8 tensor-core peak for the emulated exchange contraction.  MEASURED_PEAKS.json holds a measured bf16 figure only;
+    the sm_100a tensor core issues int8 (kind::i8, K = 32 per instruction) at twice the bf16 rate (K = 16), so the roofline
+    denominator is 2 x the measured SUSTAINED bf16 figure (the kernel runs inside a long, power-capped step)."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            d = json.load(f)
+        return 2.0 * float(d["bf16_tflops_sustained"]), "2 x MEASURED_PEAKS.json bf16_tflops_sustained (int8 issues at twice the bf16 rate; no measured int8 entry)"
+    except Exception:
+        return 2.0 * 1400.0, "fallback: 2 x 1.4 PFLOP/s sustained bf16 of the profiling recipe (MEASURED_PEAKS.json absent)"
+
+
+INT8_PEAK_TOPS, INT8_PEAK_SOURCE = _int8_peak()
+
+
 def _ncu_traffic(workload: str, key: str, field: str = "traffic_bytes_per_launch"):
     """DRAM bytes per launch of the named kernel from the committed `ncu --set full` capture of this workload
     (profiles/ncu_traffic_r01.json), or None when no capture of this workload exists."""
@@ -116,24 +131,35 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------
 # CPU arm (oracle port of the reference algorithm), bounded sample + linear extrapolation
 # ---------------------------------------------------------------------------------------------------------
-def cpu_reference_rate(dp, nvec_sample: int = 1, target_s: float = 12.0):
-    """Time the oracle's AO-route sigma build (reference algorithm: back-transform, (L_P D) L_P exchange, grid
-    contraction, projection) on the host cores for a SAMPLE of the aux functions / grid points of this workload;
-    sigma is linear in both, so the full-size time per vector is t_k*naux/naux_s + t_xc*ng/ng_s + t_rest."""
-    from oracle import jk, numint
-    from xtddft_b200.synth_device import host_sample
-    from oracle.workloads import oracle_vind_for
+def _host_threads():
+    """Give the host BLAS every core of the box, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1, which would
+    make the CPU arm an 1-core run): returns (threads in force, BLAS name)."""
+    ncpu = os.cpu_count() or 1
     try:
-        from threadpoolctl import threadpool_info
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=ncpu)
         info = threadpool_info()
         threads = max([i.get("num_threads", 1) for i in info] or [1])
         blas = ",".join(sorted({i.get("internal_api", "?") for i in info}))
+        return int(threads), blas
     except Exception:
-        threads, blas = os.cpu_count(), "?"
+        return ncpu, "?"
+
+
+def cpu_reference_rate(dp, nvec_sample: int = 1, target_s: float = 20.0):
+    """Time the oracle's AO-route sigma build (reference algorithm: back-transform, (L_P D) L_P exchange, grid contraction,
+    projection) ONCE on all host cores.  If one full-size sigma vector fits the time budget it is timed at full size
+    (`extrapolated: false`); otherwise a SAMPLE of the aux functions / grid points sized for the budget is timed and the
+    full-size time follows from linearity: t_df * naux / naux_s + t_grid * ng / ng_s + t_rest (`extrapolated: true`)."""
+    from oracle import jk, numint
+    from xtddft_b200.synth_device import host_sample
+    from oracle.workloads import oracle_vind_for
+    threads, blas = _host_threads()
     n = dp.p.nao
-    # calibrate the sample so the K part takes a few seconds: ~4*N^3 flops per aux function per density
-    t0 = time.perf_counter()
+    # calibrate: host DGEMM rate -> seconds per aux function (~4 N^3 flops per density) and per grid point
     a = np.random.default_rng(0).standard_normal((min(n, 1500), min(n, 1500)))
+    _ = a @ a
+    t0 = time.perf_counter()
     _ = a @ a
     gf = 2.0 * a.shape[0] ** 3 / (time.perf_counter() - t0) / 1e9
     per_aux = 4.0 * n ** 3 / 1e9 / max(gf, 1.0)
@@ -141,11 +167,18 @@ def cpu_reference_rate(dp, nvec_sample: int = 1, target_s: float = 12.0):
     naux_s = int(max(1, min(dp.naux, (target_s * 0.6) / max(per_aux * ndens, 1e-9))))
     per_g = 4.0 * n ** 2 * (2 if dp.nvar == 4 else 1) / 1e9 / max(gf, 1.0)
     ng_s = int(max(64, min(dp.ng, (target_s * 0.3) / max(per_g * (2 if dp.method == "xtda" else 1), 1e-9))))
+    full = naux_s == dp.naux and ng_s == dp.ng
     ps = host_sample(dp, naux_s, ng_s)
     vind, hd = oracle_vind_for(ps, dp.method)
     z = np.random.default_rng(1).standard_normal((nvec_sample, hd.size))
     # whole sampled call
     t0 = time.perf_counter(); vind(z); t_all = time.perf_counter() - t0
+    if full:
+        t_full = t_all / nvec_sample
+        return {"value": 1.0 / t_full, "unit": "sigma-vectors/s", "cores": int(threads), "kind": "port", "extrapolated": False,
+                "sample": f"oracle AO-route sigma build of {nvec_sample} FULL-SIZE vector(s) ({dp.naux} aux functions, {dp.ng} grid points), "
+                          f"timed once; {blas} {threads} threads, host DGEMM {gf:.0f} GF/s",
+                "seconds_per_vector_full_size": t_full, "seconds_measured": t_all}
     # parts: exchange/Coulomb on the sampled tensor, grid on the sampled points
     ps_nodf = host_sample(dp, naux_s, ng_s); ps_nodf.cderi = None
     v2, _ = oracle_vind_for(ps_nodf, dp.method) if dp.method != "xsf" else (None, None)
@@ -157,7 +190,6 @@ def cpu_reference_rate(dp, nvec_sample: int = 1, target_s: float = 12.0):
         dm = np.random.default_rng(2).standard_normal((5 * nvec_sample, n, n))
         t0 = time.perf_counter(); jk.get_jk(ps.cderi, dm); t_df = time.perf_counter() - t0
         t_nodf = max(t_all - t_df, 1e-9)
-    ps_nogrid = host_sample(dp, naux_s, ng_s)
     t_grid = 0.0
     if dp.fxc_kind != "none":
         dm = np.random.default_rng(3).standard_normal((nvec_sample, n, n))
@@ -171,11 +203,12 @@ def cpu_reference_rate(dp, nvec_sample: int = 1, target_s: float = 12.0):
         t_grid = time.perf_counter() - t0
     t_rest = max(t_nodf - t_grid, 0.0)
     t_full = (t_df * dp.naux / naux_s + t_grid * dp.ng / ng_s + t_rest) / nvec_sample
-    return {"value": 1.0 / t_full, "unit": "sigma-vectors/s", "cores": int(threads), "kind": "port",
-            "sample": f"oracle AO-route sigma build of {nvec_sample} vector(s) on {naux_s}/{dp.naux} aux functions and {ng_s}/{dp.ng} "
-                      f"grid points, extrapolated linearly (sigma is linear in both); {blas} {threads} threads, host DGEMM {gf:.0f} GF/s; "
+    return {"value": 1.0 / t_full, "unit": "sigma-vectors/s", "cores": int(threads), "kind": "port", "extrapolated": True,
+            "sample": f"oracle AO-route sigma build of {nvec_sample} vector(s) on {naux_s}/{dp.naux} aux functions "
+                      f"({100.0 * naux_s / dp.naux:.1f} %) and {ng_s}/{dp.ng} grid points ({100.0 * ng_s / dp.ng:.1f} %), timed once and "
+                      f"extrapolated linearly (sigma is linear in both); {blas} {threads} threads, host DGEMM {gf:.0f} GF/s; "
                       f"t_df={t_df:.2f}s t_grid={t_grid:.2f}s t_rest={t_rest:.2f}s",
-            "seconds_per_vector_full_size": t_full}
+            "seconds_per_vector_full_size": t_full, "seconds_measured": t_all}
 
 
 def config_dict(dp, nvec: int, dim: int, world: int) -> dict:
@@ -189,7 +222,11 @@ def config_dict(dp, nvec: int, dim: int, world: int) -> dict:
 
 def run_reference(args):
     """`--impl reference`: the reference's CPU implementation of the path.  PySCF is not installable here (no wheel,
-    no network) and the reference tree does not import without it, so this arm times the oracle port (kind "port")."""
+    no network) and the reference tree does not import without it (`baseline/_ref` and `import pyscf` are probed and
+    reported), so this arm times the oracle port (kind "port") on ALL host cores -- the BLAS thread count is set explicitly,
+    whatever OMP_NUM_THREADS the launcher exported.  One measurement with a ~60 s budget: a full-size sigma vector when it
+    fits (configs 1, 2), else a sample of the aux functions / grid points extrapolated linearly (`extrapolated: true`);
+    `--steps` / `--warmup` do not repeat a minute-long CPU run."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -197,16 +234,20 @@ def run_reference(args):
     from xtddft_b200.workloads import plan_for
     dp = make_device_problem(args.config, args.scale)
     nvec = args.nvec or dp.nroots
-    vals = []
-    for i in range(args.warmup + args.steps):
-        r = cpu_reference_rate(dp, 1, target_s=6.0)
-        if i >= args.warmup:
-            vals.append(r)
-    v = float(np.mean([r["value"] for r in vals]))
-    cb = dict(vals[-1]); cb["value"] = v
+    cb = cpu_reference_rate(dp, 1, target_s=float(os.environ.get("XTD_REF_BUDGET_S", "60")))
+    v = float(cb["value"])
+    have_pyscf = False
+    try:
+        import pyscf  # noqa: F401
+        have_pyscf = True
+    except Exception:
+        pass
+    cb["pyscf_importable"] = have_pyscf
+    cb["baseline_ref_present"] = os.path.isdir(os.path.join(ROOT, "baseline", "_ref"))
     out = {"impl": "reference", "metric": "davidson_sigma_vectors_per_s", "value": v, "unit": "sigma-vectors/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * nvec / v, "higher_is_better": True, "scaling": "strong",
-           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "extrapolated": bool(cb.get("extrapolated")),
+           "seconds_measured": cb.get("seconds_measured"),
            "config": config_dict(dp, nvec, int(plan_for(dp.p, dp.method).ext_dim), 1),
            "cpu_baseline": cb, "e2e": {"value": v, "unit": "sigma-vectors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(out)
@@ -353,7 +394,22 @@ def main():
     gemm_ms = phase.get("k2", 0.0) / args.steps
     k2_flops = phase_flops.get("k2", 0.0) / args.steps
     p = dp.p
-    roof = {"bound": "tensor", "kernel": "dgemm_dmma_tma_kernel (exchange contraction sigma += U . Lvv)",
+    xs_on = int(getattr(eng, "exchange_slices", 0) or 0)
+    if xs_on and gemm_ms > 0:
+        # emulated path: `achieved` counts the int8 multiply-adds the tensor core executes, S(S+1)/2 plane products per fp64 product
+        pairs = xs_on * (xs_on + 1) // 2
+        tops = k2_flops * pairs / (gemm_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": f"oz_gemm_kernel<{xs_on}> (exchange contraction sigma += U . Lvv emulated on tcgen05.mma kind::i8, "
+                                             f"{xs_on} balanced radix-256 digit planes per operand, {pairs} int8 plane products per fp64 product)",
+                "achieved": tops, "peak": INT8_PEAK_TOPS, "unit": "TOP/s (int8, dense)", "frac": tops / INT8_PEAK_TOPS,
+                "traffic": _ncu_traffic(dp.name, "k2_int8") if world == 1 and args.scale == 1.0 else None, "peak_source": INT8_PEAK_SOURCE,
+                "fp64_equivalent_tflops": k2_flops / (gemm_ms * 1e-3) / 1e12,
+                "fp64_equivalent_vs_dmma_peak": k2_flops / (gemm_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
+                "fp64_dmma_peak_tflops": FP64_PEAK_TFLOPS,
+                "flops_per_launch_group": k2_flops, "int8_ops_per_step": k2_flops * pairs, "ms_per_step_in_kernel": gemm_ms,
+                "all_gemm_flops_per_step": flops / args.steps, "all_gemm_tflops_over_step": flops / args.steps / (ms_step * 1e-3) / 1e12}
+    else:
+      roof = {"bound": "tensor", "kernel": "dgemm_dmma_tma_kernel (exchange contraction sigma += U . Lvv)",
             "achieved": (k2_flops / (gemm_ms * 1e-3) / 1e12) if gemm_ms > 0 else None, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
             "frac": (k2_flops / (gemm_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS) if gemm_ms > 0 else None,
             "traffic": _ncu_traffic(dp.name, "k2") if world == 1 and args.scale == 1.0 else None,
@@ -365,7 +421,7 @@ def main():
     # 4 naux N^2 nocc per vector and spin block) over the time this build spends on it (K1 + K2): throughput-equivalent
     ref_flops = sum(4.0 * (dp.naux // world + (1 if rank < dp.naux % world else 0)) * p.nao ** 2 * eng.plan.channels[kt.ch].no * nvec
                     for kt in eng.plan.k_terms)
-    k_ms = (phase.get("k1", 0.0) + phase.get("k2", 0.0)) / args.steps
+    k_ms = (phase.get("k1", 0.0) + phase.get("k2", 0.0) + phase.get("k2_slice", 0.0)) / args.steps
     if roof["traffic"] is not None:
         # `traffic` is per LAUNCH (one aux chunk) as ncu reports it; the launch it was captured on, for comparison
         roof["traffic_captured_launch"] = _ncu_traffic(dp.name, "k2", "captured_launch")

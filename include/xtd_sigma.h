@@ -35,7 +35,7 @@ typedef struct {
   double flops[12];           /* DMMA GEMM flops issued inside each phase of the last xtd_sigma* call */
 } xtd_stats;
 enum { XTD_T_PACK = 0, XTD_T_XC_GEMM = 1, XTD_T_XC_STREAM = 2, XTD_T_K1 = 3, XTD_T_K2 = 4, XTD_T_J = 5,
-       XTD_T_LOCAL = 6, XTD_T_UNPACK = 7, XTD_T_TOTAL = 8, XTD_T_K2_SLICE = 9 };
+       XTD_T_LOCAL = 6, XTD_T_UNPACK = 7, XTD_T_TOTAL = 8, XTD_T_K2_SLICE = 9, XTD_T_XC_SLICE = 10 };
 
 const char* xtd_last_error(void);
 int xtd_version(void);

@@ -110,9 +110,13 @@ def test_ozaki_many_groups_and_splits(torch_cuda):
 # ---- the engine's exchange contraction on the emulated path ------------------------------------------------------------
 @pytest.mark.parametrize("slices,tol", [(8, 1e-12), (7, 1e-12), (6, 1e-11), (5, 1e-9)])
 @pytest.mark.parametrize("method", ["sf", "xtda"])
-def test_engine_emulated_exchange(torch_cuda, monkeypatch, slices, tol, method):
+@pytest.mark.parametrize("fuse", ["1", "0"])
+def test_engine_emulated_exchange(torch_cuda, monkeypatch, slices, tol, method, fuse):
     """SF-TDA / X-TDA sigma with the uniform-weight exchange contraction on the INT8 tensor cores against the oracle, with
-    several aux chunks (ragged last group: naux = 61), several tiles in M and N, 5 vectors."""
+    several aux chunks (ragged last group: naux = 61), several tiles in M and N, 5 vectors.  fuse = 1: the half-transform
+    U = Loo . z runs on the INT8 tensor cores too and writes the digit planes of U directly (a-priori row scales);
+    fuse = 0: DMMA half-transform + slicing pass with exact row maxima."""
+    monkeypatch.setenv("XTD_OZ_FUSE", fuse)
     from oracle import sigma as osig
     from xtddft_b200 import plan as planmod
     from xtddft_b200.engine import SigmaEngine
@@ -171,3 +175,35 @@ def test_engine_emulated_exchange_ragged_chunks_and_shards(torch_cuda):
             _lib.check(eng.lib.xtd_sigma_finish(eng._h, 3, C.c_void_p(out.data_ptr())), "finish")
             assert np.abs(out.cpu().numpy() - ref).max() < 1e-12 * max(1.0, np.abs(ref).max())
         eng.close()
+
+
+@pytest.mark.parametrize("method,xct", [("sf", "GGA"), ("sf", "LDA"), ("xtda", "LDA"), ("xsf", "GGA")])
+def test_engine_emulated_grid_path(torch_cuda, monkeypatch, method, xct):
+    """One-component grid kernels (ALDA0 of SF / XSF-TDA, LDA kernels of X-TDA on two channels) with both grid GEMMs on the INT8
+    tensor cores: forward Y = phiv . z^T and backward sigma += A^T . phiv (contraction over grid points, several 8192-point
+    blocks, ragged last block, two grid chunks) against the oracle."""
+    from oracle import sigma as osig
+    from xtddft_b200 import plan as planmod
+    from xtddft_b200.engine import SigmaEngine
+    from xtddft_b200.synth import make_problem
+    monkeypatch.setenv("XTD_CHUNK_GRID", "16384")
+    p = make_problem(60, 10, 2, 48, 12, 20000, xctype=xct, hyb=0.4, seed=410)
+    if method == "sf":
+        vind, hd = osig.sf_gen_vind(p, -1, 0)
+        plan = planmod.build_sf_plan(p, isf=-1, method=0)
+    elif method == "xsf":
+        vind, hd = osig.xsf_gen_vind(p, sa=3, method=0, remove=True, foo=0.8, fglobal=0.7)
+        plan = planmod.build_sf_plan(p, isf=-1, method=0, sa=3, layout=planmod.LAYOUT_BLOCK, remove=True, foo=0.8, fglobal=0.7, hdiag_kind="xsf")
+    else:
+        vind, hd = osig.xtda_gen_vind(p)
+        plan = planmod.build_xtda_plan(p)
+    z = np.random.default_rng(3).standard_normal((3, hd.size))
+    ref = vind(z)
+    eng = SigmaEngine.from_problem(plan, p, workspace_bytes=512 << 20, max_nvec=4, exchange_slices=7)
+    got = eng.sigma(torch_cuda.from_numpy(z).cuda()).cpu().numpy()
+    st = eng.stats()
+    assert st["ms"]["xc_slice"] > 0, st["ms"]
+    assert eng.last_chunks()[1] == 2
+    err = float(np.abs(got - ref).max() / max(1.0, np.abs(ref).max()))
+    assert err < 1e-11, err
+    eng.close()

@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(HERE, "libxtdsigma.so")
 
 XTD_FXC_NONE, XTD_FXC_UKS, XTD_FXC_ALDA0, XTD_FXC_MCOL, XTD_FXC_UKS_TAU, XTD_FXC_MCOL_TAU = 0, 1, 2, 3, 4, 5
 XTD_SIDE_RIGHT, XTD_SIDE_LEFT = 0, 1
-T_NAMES = ["pack", "xc_gemm", "xc_stream", "k1", "k2", "j", "local", "unpack", "total", "k2_slice"]
+T_NAMES = ["pack", "xc_gemm", "xc_stream", "k1", "k2", "j", "local", "unpack", "total", "k2_slice", "xc_slice"]
 
 
 class XtdError(RuntimeError):

@@ -36,16 +36,49 @@ constexpr int OZ_THREADS = 192;
 __device__ __forceinline__ uint32_t oz_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // ---- slicing ------------------------------------------------------------------------------------------------------------
+// Source element (q, row, k):  X[q * sq + row * ld + k]   (K-contiguous rows), or for a TRANSPOSED source (the contraction
+// index is the row index of the array, e.g. grid points)  X[q * sq + k * ld + row].  Only k with q * K + k < k_valid are read
+// (a ragged last q-slice); everything else is zero.
+__device__ __forceinline__ double oz_scale_of(double m) {
+  if (!(m > 1e-280 && m < 1e280)) return 0.0;
+  int e;
+  frexp(m, &e);                 // m = f 2^e, f in [0.5, 1)
+  return ldexp(1.0, e - 6);
+}
+
+// transposed source: block (32 rows, 8 k-lanes); grid (rows_pad / 32, ngroups)
+__global__ void oz_rowmax_t_kernel(double* __restrict__ scale, int rows_pad, const double* __restrict__ X, long ld, long sq, int rows, int K,
+                                   int nq, int group, long k_valid) {
+  const int row = blockIdx.x * 32 + threadIdx.x, g = blockIdx.y;
+  double m = 0.0;
+  if (row < rows) {
+    const int q1 = min(nq, (g + 1) * group);
+    for (int q = g * group; q < q1; ++q) {
+      const long kmax = min((long)K, k_valid - (long)q * K);
+      const double* x = X + (long)q * sq + row;
+      for (long k = threadIdx.y; k < kmax; k += 8) m = fmax(m, fabs(x[k * ld]));
+    }
+  }
+  __shared__ double red[8][33];
+  red[threadIdx.y][threadIdx.x] = m;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    for (int w = 1; w < 8; ++w) m = fmax(m, red[w][threadIdx.x]);
+    if (row < rows_pad) scale[(long)g * rows_pad + row] = oz_scale_of(m);
+  }
+}
+
 // scale[g][row] = 2^(e - 6) with max |x| over the row's group < 2^e (0 for an all-zero / padding row)
 __global__ void oz_rowmax_kernel(double* __restrict__ scale, int rows_pad, const double* __restrict__ X, long ld, long sq, int rows, int K,
-                                 int nq, int group) {
+                                 int nq, int group, long k_valid) {
   const int row = blockIdx.x, g = blockIdx.y;
   double m = 0.0;
   if (row < rows) {
     const int q1 = min(nq, (g + 1) * group);
     for (int q = g * group; q < q1; ++q) {
+      const int kmax = (int)min((long)K, k_valid - (long)q * K);
       const double* x = X + (long)q * sq + (long)row * ld;
-      for (int k = threadIdx.x; k < K; k += blockDim.x) m = fmax(m, fabs(x[k]));
+      for (int k = threadIdx.x; k < kmax; k += blockDim.x) m = fmax(m, fabs(x[k]));
     }
   }
   __shared__ double red[8];
@@ -54,21 +87,15 @@ __global__ void oz_rowmax_kernel(double* __restrict__ scale, int rows_pad, const
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, red[w]);
-    double s = 0.0;
-    if (m > 1e-280 && m < 1e280) {
-      int e;
-      frexp(m, &e);                 // m = f 2^e, f in [0.5, 1)
-      s = ldexp(1.0, e - 6);
-    }
-    scale[(long)g * rows_pad + row] = s;
+    scale[(long)g * rows_pad + row] = oz_scale_of(m);
   }
 }
 
 // one thread: 16 consecutive k of one row -> S 16-byte chunks.  grid (2 nkb, rows_pad / 128, nq), block 128 (lane <-> row)
-template <int S>
+template <int S, bool TRANS>
 __global__ void __launch_bounds__(128) oz_slice_kernel(int8_t* __restrict__ out, const double* __restrict__ scale, int rows_pad,
                                                        const double* __restrict__ X, long ld, long sq, int rows, int K, int RT, int nkb,
-                                                       int group, int stacked) {
+                                                       int group, int stacked, long k_valid) {
   const int c2 = blockIdx.x, q = blockIdx.z;
   const int row = blockIdx.y * 128 + threadIdx.x;
   const int rt = row / RT, r = row - rt * RT, nrt = rows_pad / RT;
@@ -79,18 +106,26 @@ __global__ void __launch_bounds__(128) oz_slice_kernel(int8_t* __restrict__ out,
   double sc = 0.0;
   if (row < rows) {
     sc = scale[(long)(q / group) * rows_pad + row];
-    const double* src = X + (long)q * sq + (long)row * ld + k0;
-    if (k0 + 16 <= K) {
-#pragma unroll
-      for (int k = 0; k < 16; k += 2) {
-        const double2 v = *reinterpret_cast<const double2*>(src + k);
-        x[k] = v.x;
-        x[k + 1] = v.y;
-      }
-    } else {
+    const int kmax = (int)min((long)K, k_valid - (long)q * K);      // valid k of this q-slice
+    if (TRANS) {
+      const double* src = X + (long)q * sq + (long)k0 * ld + row;    // lanes = consecutive rows: coalesced for every k
 #pragma unroll
       for (int k = 0; k < 16; ++k)
-        if (k0 + k < K) x[k] = src[k];
+        if (k0 + k < kmax) x[k] = src[(long)k * ld];
+    } else {
+      const double* src = X + (long)q * sq + (long)row * ld + k0;
+      if (k0 + 16 <= kmax) {
+#pragma unroll
+        for (int k = 0; k < 16; k += 2) {
+          const double2 v = *reinterpret_cast<const double2*>(src + k);
+          x[k] = v.x;
+          x[k + 1] = v.y;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+          if (k0 + k < kmax) x[k] = src[k];
+      }
     }
   }
   // 1 / scale for a power of two: flip the exponent
@@ -367,6 +402,272 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const OzGemmPara
   }
 }
 
+// ---- fused half-transform: U = Loo . z on the INT8 tensor cores, written directly as the A planes of the contraction above ----
+//
+//   U[P][(x,i)][b] = sum_j Loo[P][i][j] zt[x][b][j]            (K = occupied count: a few k-steps per tile)
+//
+// A = int8 planes of Loo (static, one q-slice per aux function, rows padded to 128 per aux function), B = planes of zt (per
+// call, one q-slice per trial vector).  A persistent CTA walks tiles (P, 128 rows i, x, 64 columns b); its epilogue recombines the
+// levels in fp64, and instead of storing fp64 U it cuts the value into the digit planes of row m = x no + i of the NEXT GEMM's A
+// operand, under an a-priori power-of-two scale per (row, group) -- the Cauchy-Schwarz bound |U| <= |Loo[P,i,:]| |z[x,:,b]| --
+// so the 190 GB fp64 intermediate of a config-5 step (written once, read twice by the slicing pass) never exists.
+struct OzK1Params {
+  const int8_t* A;    // [np][nit][nkb1][S][128 x 32]
+  const int8_t* B;    // [nvec][nbt][nkb1][2][S][64 x 16]
+  const double* sa;   // [np][nit * 128]      row scales of the Loo planes
+  const double* sb;   // [nvec][nbt * 64]     row scales of the zt planes
+  const double* so;   // [groups][Mpad2]      output row scales (2^(e-6), |U| < 2^e guaranteed by the bound)
+  int8_t* out;        // [np][nmt2][nkb2][S][128 x 32]
+  int np, nit, nbt, nkb1, nvec, no, group, nmt2, nkb2, Mpad2;
+  long ntiles;
+};
+
+template <int S>
+__global__ void __launch_bounds__(OZ_THREADS, 1) oz_k1_kernel(const OzK1Params p) {
+  constexpr int A_SLICE = OZ_BM * OZ_KB, B_SLICE = OZ_BN * OZ_KB;
+  constexpr int A_BYTES = S * A_SLICE, B_BYTES = S * B_SLICE, STAGE = A_BYTES + B_BYTES;
+  extern __shared__ __align__(128) uint8_t oz_smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(oz_smem + OZ_STAGES * STAGE);
+  uint64_t* empty = full + OZ_STAGES;
+  uint64_t* tmem_full = empty + OZ_STAGES;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < OZ_STAGES; ++s) {
+      oz_mbar_init(&full[s], 1);
+      oz_mbar_init(&empty[s], 1);
+    }
+    oz_mbar_init(tmem_full, 1);
+    oz_mbar_init(tmem_empty, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(oz_smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const long per_p = (long)p.nit * p.nvec * p.nbt, per_it = (long)p.nvec * p.nbt;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      long it = 0;
+      for (long t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+        const int P = (int)(t / per_p);
+        const long r0 = t - (long)P * per_p;
+        const int itile = (int)(r0 / per_it);
+        const long r1 = r0 - (long)itile * per_it;
+        const int x = (int)(r1 / p.nbt), bt = (int)(r1 - (long)x * p.nbt);
+        const int8_t* a = p.A + (((long)P * p.nit + itile) * p.nkb1) * A_BYTES;
+        const int8_t* b = p.B + (((long)x * p.nbt + bt) * p.nkb1) * B_BYTES;
+        for (int kb = 0; kb < p.nkb1; ++kb, ++it) {
+          const int s = (int)(it % OZ_STAGES);
+          const uint32_t ph = (uint32_t)((it / OZ_STAGES) & 1);
+          oz_mbar_wait(&empty[s], ph ^ 1u);
+          oz_mbar_expect_tx(&full[s], STAGE);
+          uint8_t* sa = oz_smem + s * STAGE;
+          oz_bulk_load(sa, a + (long)kb * A_BYTES, A_BYTES, &full[s]);
+          oz_bulk_load(sa + A_BYTES, b + (long)kb * B_BYTES, B_BYTES, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24);
+      const uint32_t smem_base = oz_smem_u32(oz_smem);
+      long it = 0, n = 0;
+      for (long t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++n) {
+        if (n > 0) oz_mbar_wait(tmem_empty, (uint32_t)((n - 1) & 1));      // the epilogue has drained the previous tile
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int kb = 0; kb < p.nkb1; ++kb, ++it) {
+          const int s = (int)(it % OZ_STAGES);
+          const uint32_t ph = (uint32_t)((it / OZ_STAGES) & 1);
+          oz_mbar_wait(&full[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_base = smem_base + s * STAGE, b_base = a_base + A_BYTES;
+          const uint32_t later = kb > 0 ? 1u : 0u;
+#pragma unroll
+          for (int i = 0; i < S; ++i) {
+            const uint64_t da = oz_smem_desc(a_base + i * A_SLICE, OZ_BM * 16, 128);
+#pragma unroll
+            for (int j0 = 0; j0 < S - i; j0 += 4) {
+              const int nj = (S - i - j0) < 4 ? (S - i - j0) : 4;
+              const uint64_t db = oz_smem_desc(b_base + j0 * (OZ_BN * 16), S * OZ_BN * 16, 128);
+              const uint32_t idesc = idesc0 | ((uint32_t)((nj * OZ_BN) >> 3) << 17);
+              oz_mma_i8(tmem_base + (uint32_t)((i + j0) * OZ_BN), da, db, idesc, (i > 0) ? 1u : later);
+            }
+          }
+          oz_commit(&empty[s]);
+        }
+        oz_commit(tmem_full);
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const double magic = 6755399441055744.0;
+    const int rowsA = p.nit * OZ_BM, rowsB = p.nbt * OZ_BN;
+    long n = 0;
+    for (long t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++n) {
+      const int P = (int)(t / per_p);
+      const long r0 = t - (long)P * per_p;
+      const int itile = (int)(r0 / per_it);
+      const long r1 = r0 - (long)itile * per_it;
+      const int x = (int)(r1 / p.nbt), bt = (int)(r1 - (long)x * p.nbt);
+      const int i = itile * OZ_BM + row;
+      const bool valid = i < p.no;
+      const int m = x * p.no + i;
+      const double sa = valid ? p.sa[(long)P * rowsA + i] : 0.0;
+      const double so = valid ? p.so[(long)(P / p.group) * p.Mpad2 + m] : 0.0;
+      const double inv = so > 0.0 ? __hiloint2double(0x7fe00000 - __double2hiint(so), 0) : 0.0;
+      const double f = sa * inv;                       // both powers of two: exact
+      const double* sb = p.sb + (long)x * rowsB + bt * OZ_BN;
+      int8_t* dst = p.out + ((((long)P * p.nmt2 + (m >> 7)) * p.nkb2 + bt * 2) * S) * (long)A_SLICE + (long)(m & 127) * 16;
+      oz_mbar_wait(tmem_full, (uint32_t)(n & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
+        double v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = 0.0;
+#pragma unroll
+        for (int l = S - 1; l >= 0; --l) {
+          uint32_t r[16];
+          oz_tmem_ld16(taddr + (uint32_t)(l * OZ_BN + c0), r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int k = 0; k < 16; ++k)     // int32 -> fp64 through the 2^52 + 2^31 offset (no conversion instruction)
+            v[k] = fma(v[k], 0.00390625, __hiloint2double(0x43300000, (int)(r[k] ^ 0x80000000u)) - 4503601774854144.0);
+        }
+        uint32_t pk[S][4];
+#pragma unroll
+        for (int sl = 0; sl < S; ++sl)
+#pragma unroll
+          for (int w = 0; w < 4; ++w) pk[sl][w] = 0u;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          double tt = v[k] * (f * sb[c0 + k]);            // U / output scale, |tt| < 64 by the a-priori bound
+          int dg[S];
+#pragma unroll
+          for (int sl = 0; sl < S; ++sl) {
+            const double u = (sl == 0) ? __dadd_rd(tt, magic) : __fma_rd(tt, 256.0, magic);
+            const double qd = u - magic;
+            tt = (sl == 0) ? (tt - qd) : fma(tt, 256.0, -qd);
+            dg[sl] = __double2loint(u);
+          }
+          int carry = 0;
+#pragma unroll
+          for (int sl = S - 1; sl >= 1; --sl) {
+            const int vv = dg[sl] + carry;
+            carry = vv >= 128 ? 1 : 0;
+            dg[sl] = vv - (carry << 8);
+          }
+          dg[0] += carry;
+#pragma unroll
+          for (int sl = 0; sl < S; ++sl) pk[sl][k >> 2] |= ((uint32_t)dg[sl] & 0xffu) << ((k & 3) * 8);
+        }
+        if (valid && bt * 2 + (c0 >> 5) < p.nkb2) {     // (a column tile may reach past the last k block of the output operand)
+          // columns c0 .. c0+15 of this tile = k block (bt * 2 + c0 / 32) of the output operand, 16-byte chunk (c0 / 16) & 1
+          int8_t* d = dst + (long)(c0 >> 5) * S * A_SLICE + ((c0 >> 4) & 1) * (OZ_BM * 16);
+#pragma unroll
+          for (int sl = 0; sl < S; ++sl) *reinterpret_cast<uint4*>(d + (long)sl * A_SLICE) = make_uint4(pk[sl][0], pk[sl][1], pk[sl][2], pk[sl][3]);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      oz_mbar_arrive(tmem_empty);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// 2-norms of the rows of a [nq][rows][K] operand (K-contiguous): out[q * rows_pad + row]
+__global__ void oz_rownorm_kernel(double* __restrict__ out, int rows_pad, const double* __restrict__ X, long ld, long sq, int rows, int K) {
+  const int row = blockIdx.x, q = blockIdx.y;
+  double a = 0.0;
+  if (row < rows) {
+    const double* x = X + (long)q * sq + (long)row * ld;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) a = fma(x[k], x[k], a);
+  }
+  __shared__ double red[8];
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) a += red[w];
+    out[(long)q * rows_pad + row] = sqrt(a);
+  }
+}
+// zmax[x] = max_b |z[x][b][:]|  from the row norms [nvec][rows_pad]
+__global__ void oz_colmax_kernel(double* __restrict__ zmax, const double* __restrict__ norms, int rows_pad, int rows) {
+  const int x = blockIdx.x;
+  double m = 0.0;
+  for (int r = threadIdx.x; r < rows; r += blockDim.x) m = fmax(m, norms[(long)x * rows_pad + r]);
+  __shared__ double red[8];
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, red[w]);
+    zmax[x] = m;
+  }
+}
+// so[g][m = x no + i] = scale of the bound  zmax[x] * max_{P in group g} |Loo[P][i][:]|   (1 + 1e-9 covers rounding of the norms and
+// the emulation error of U itself)
+__global__ void oz_bound_scale_kernel(double* __restrict__ so, int Mpad2, const double* __restrict__ loo_norm, int rowsA, const double* __restrict__ zmax,
+                                      int np, int group, int nvec, int no) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x, g = blockIdx.y;
+  if (m >= Mpad2) return;
+  double s = 0.0;
+  if (m < nvec * no) {
+    const int x = m / no, i = m - x * no;
+    double nl = 0.0;
+    const int p1 = min(np, (g + 1) * group);
+    for (int P = g * group; P < p1; ++P) nl = fmax(nl, loo_norm[(long)P * rowsA + i]);
+    s = oz_scale_of(nl * zmax[x] * (1.0 + 1e-9));
+  }
+  so[(long)g * Mpad2 + m] = s;
+}
+
+template <int S>
+inline int oz_k1_launch(const OzK1Params& p, int num_sms, cudaStream_t st) {
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  XTD_CUDA(cudaGetDevice(&dev));
+  if (!attr_set[dev & 63]) {
+    XTD_CUDA(cudaFuncSetAttribute(oz_k1_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)OZ_STAGES * S * (OZ_BM + OZ_BN) * OZ_KB + 256)));
+    attr_set[dev & 63] = true;
+  }
+  const unsigned grid = (unsigned)std::min<long>(p.ntiles, num_sms);
+  oz_k1_kernel<S><<<grid, OZ_THREADS, (size_t)OZ_STAGES * S * (OZ_BM + OZ_BN) * OZ_KB + 256, st>>>(p);
+  XTD_COUNT_LAUNCH();
+  XTD_CUDA(cudaGetLastError());
+  return XTD_OK;
+}
+
+inline int oz_k1(int S, const OzK1Params& p, int num_sms, cudaStream_t st) {
+  switch (S) {
+    case 3: return oz_k1_launch<3>(p, num_sms, st);
+    case 4: return oz_k1_launch<4>(p, num_sms, st);
+    case 5: return oz_k1_launch<5>(p, num_sms, st);
+    case 6: return oz_k1_launch<6>(p, num_sms, st);
+    case 7: return oz_k1_launch<7>(p, num_sms, st);
+    case 8: return oz_k1_launch<8>(p, num_sms, st);
+  }
+  XTD_SET_ERR("oz_k1: %d slices (3..8)", S);
+  return XTD_ERR_ARG;
+}
+
 // ---- host side --------------------------------------------------------------------------------------------------------------
 struct OzShape {
   int rows = 0, RT = 0, rows_pad = 0, nrt = 0, K = 0, nkb = 0;
@@ -392,29 +693,41 @@ inline int oz_max_group(int K, int S) {
 
 template <int S>
 inline int oz_slice_launch(int8_t* out, double* scale, const OzShape& sh, const double* X, long ld, long sq, int nq, int group,
-                           cudaStream_t st) {
+                           bool trans, long k_valid, cudaStream_t st) {
   const int ng = (int)cdiv(nq, group);
-  oz_rowmax_kernel<<<dim3(sh.rows_pad, ng), 256, 0, st>>>(scale, sh.rows_pad, X, ld, sq, sh.rows, sh.K, nq, group);
-  XTD_COUNT_LAUNCH();
-  XTD_CUDA(cudaGetLastError());
-  oz_slice_kernel<S><<<dim3(2 * sh.nkb, sh.rows_pad / 128, nq), 128, 0, st>>>(out, scale, sh.rows_pad, X, ld, sq, sh.rows, sh.K, sh.RT, sh.nkb,
-                                                                             group, sh.RT == OZ_BN ? 1 : 0);
+  const int stacked = sh.RT == OZ_BN ? 1 : 0;
+  const dim3 sgrid(2 * sh.nkb, sh.rows_pad / 128, nq);
+  if (trans) {
+    oz_rowmax_t_kernel<<<dim3(sh.rows_pad / 32, ng), dim3(32, 8), 0, st>>>(scale, sh.rows_pad, X, ld, sq, sh.rows, sh.K, nq, group, k_valid);
+    XTD_COUNT_LAUNCH();
+    XTD_CUDA(cudaGetLastError());
+    oz_slice_kernel<S, true><<<sgrid, 128, 0, st>>>(out, scale, sh.rows_pad, X, ld, sq, sh.rows, sh.K, sh.RT, sh.nkb, group, stacked, k_valid);
+  } else {
+    oz_rowmax_kernel<<<dim3(sh.rows_pad, ng), 256, 0, st>>>(scale, sh.rows_pad, X, ld, sq, sh.rows, sh.K, nq, group, k_valid);
+    XTD_COUNT_LAUNCH();
+    XTD_CUDA(cudaGetLastError());
+    oz_slice_kernel<S, false><<<sgrid, 128, 0, st>>>(out, scale, sh.rows_pad, X, ld, sq, sh.rows, sh.K, sh.RT, sh.nkb, group, stacked, k_valid);
+  }
   XTD_COUNT_LAUNCH();
   XTD_CUDA(cudaGetLastError());
   return XTD_OK;
 }
 
+// trans: the contraction index is the ROW index of the source array (element (row, k) at X[q sq + k ld + row]).
+// k_valid: number of valid contraction indices over all q-slices together (q K + k < k_valid), <= 0 = all.
 inline int oz_slice(int S, int8_t* out, double* scale, const OzShape& sh, const double* X, long ld, long sq, int nq, int group,
-                    cudaStream_t st) {
+                    cudaStream_t st, bool trans = false, long k_valid = 0) {
   XTD_REQUIRE(nq >= 1 && nq <= 65535, XTD_ERR_ARG, "oz_slice: %d q-slices per launch (1..65535)", nq);
-  XTD_REQUIRE(ld % 2 == 0 && sq % 2 == 0 && ((uintptr_t)X & 15) == 0, XTD_ERR_ALIGN, "oz_slice: operand must be 16-byte aligned with even strides");
+  XTD_REQUIRE(trans || (ld % 2 == 0 && sq % 2 == 0 && ((uintptr_t)X & 15) == 0), XTD_ERR_ALIGN,
+              "oz_slice: operand must be 16-byte aligned with even strides");
+  if (k_valid <= 0) k_valid = (long)nq * sh.K;
   switch (S) {
-    case 3: return oz_slice_launch<3>(out, scale, sh, X, ld, sq, nq, group, st);
-    case 4: return oz_slice_launch<4>(out, scale, sh, X, ld, sq, nq, group, st);
-    case 5: return oz_slice_launch<5>(out, scale, sh, X, ld, sq, nq, group, st);
-    case 6: return oz_slice_launch<6>(out, scale, sh, X, ld, sq, nq, group, st);
-    case 7: return oz_slice_launch<7>(out, scale, sh, X, ld, sq, nq, group, st);
-    case 8: return oz_slice_launch<8>(out, scale, sh, X, ld, sq, nq, group, st);
+    case 3: return oz_slice_launch<3>(out, scale, sh, X, ld, sq, nq, group, trans, k_valid, st);
+    case 4: return oz_slice_launch<4>(out, scale, sh, X, ld, sq, nq, group, trans, k_valid, st);
+    case 5: return oz_slice_launch<5>(out, scale, sh, X, ld, sq, nq, group, trans, k_valid, st);
+    case 6: return oz_slice_launch<6>(out, scale, sh, X, ld, sq, nq, group, trans, k_valid, st);
+    case 7: return oz_slice_launch<7>(out, scale, sh, X, ld, sq, nq, group, trans, k_valid, st);
+    case 8: return oz_slice_launch<8>(out, scale, sh, X, ld, sq, nq, group, trans, k_valid, st);
   }
   XTD_SET_ERR("oz_slice: %d slices (3..8)", S);
   return XTD_ERR_ARG;

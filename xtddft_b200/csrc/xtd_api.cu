@@ -67,6 +67,17 @@ struct Channel {
   double* LvvScale[2] = {nullptr, nullptr}; // [groups][rows_pad]
   OzShape ozB;
   int oz_group = 0;
+  // ... and the occupied-occupied block as the A operand of the fused half-transform (oz_k1_kernel): planes, row scales, row 2-norms
+  int8_t* LooS[2] = {nullptr, nullptr};
+  double *LooScale[2] = {nullptr, nullptr}, *LooNorm[2] = {nullptr, nullptr};
+  OzShape ozL;
+  // grid path on the emulated GEMMs (one AO component): MO values of the virtual orbitals kept as int8 planes in both operand
+  // roles -- rows = grid points, K = virtual index (forward Y = phiv . z^T) and rows = virtual index, K = blocks of OZ_XC_KQ grid
+  // points (backward sigma += A^T . phiv) -- instead of the fp64 array
+  bool xc_oz = false;
+  int8_t *phivF = nullptr, *phivB = nullptr;
+  double *phivFs = nullptr, *phivBs = nullptr;
+  OzShape ozPF, ozPB;
   DevBuf phi;                       // occupied values on the grid  [nvar_eff][ng][ldphi]
   long ldphi = 0;
   DevBuf phiv;                      // virtual values on the grid   [nvar_eff][ng][ldphiv]
@@ -77,6 +88,7 @@ struct Channel {
   long g_nnz = 0;
 };
 
+constexpr int OZ_XC_KQ = 8192;   // grid points per int32 accumulation group of the backward grid GEMM (8192 * S * 2^14 < 2^31)
 constexpr int NARROW_MAX = 16;   // widest first virtual block that takes the narrow-output exchange pass
 
 struct KTermRec {
@@ -186,6 +198,7 @@ struct xtd_engine {
   // XTD_CHUNK_AUX / XTD_CHUNK_GRID: upper bounds on the aux / grid chunk of a call (tests force the multi-chunk loops that
   // BASELINE-size runs take at oracle-sized inputs); the chunk counts of the last call are reported by xtd_last_chunks
   long max_pc = 0, max_gb = 0;
+  bool oz_fuse = true;            // emulated path: half-transform on the INT8 tensor cores too, fused with the slicing (XTD_OZ_FUSE=0: DMMA + slicing pass)
   int oz_slices = 0;              // 0: FP64 DMMA exchange contraction; 3..8: INT8 tensor-core emulation with that many slices
   long last_aux_chunks = 0, last_grid_chunks = 0;
   // Launch-bound calls (small molecules: ~50-100 launches of a few microseconds each) are replayed as CUDA graphs: the
@@ -348,6 +361,23 @@ int grid_commit(xtd_engine* h) {
       e.N = c->nv;
       e.C = c->phiv.p; e.ldc = c->ldphiv; e.c_batch_stride = h->ng * c->ldphiv;
       XTD_TRY(gemm(h->gemm, e, s));
+      if (h->oz_slices > 0 && h->nvar_eff == 1) {
+        // both operand roles of phiv as int8 planes; the fp64 array is dropped
+        const int S = h->oz_slices;
+        c->ozPF.set((int)h->ng, OZ_BM, c->nv);
+        c->ozPB.set(c->nv, OZ_BN, OZ_XC_KQ);
+        const long nqg = cdiv(h->ng, OZ_XC_KQ);
+        XTD_REQUIRE(nqg <= 65535, XTD_ERR_UNSUPPORTED, "grid too long for the emulated grid path");
+        XTD_CUDA(cudaMalloc((void**)&c->phivF, c->ozPF.slice_bytes(1, S)));
+        XTD_CUDA(cudaMalloc((void**)&c->phivFs, c->ozPF.scale_doubles(1, 1) * 8));
+        XTD_CUDA(cudaMalloc((void**)&c->phivB, c->ozPB.slice_bytes(nqg, S)));
+        XTD_CUDA(cudaMalloc((void**)&c->phivBs, c->ozPB.scale_doubles(nqg, 1) * 8));
+        XTD_TRY(oz_slice(S, c->phivF, c->phivFs, c->ozPF, c->phiv.p, c->ldphiv, 0, 1, 1, s));
+        XTD_TRY(oz_slice(S, c->phivB, c->phivBs, c->ozPB, c->phiv.p, c->ldphiv, (long)OZ_XC_KQ * c->ldphiv, (int)nqg, 1, s, true, h->ng));
+        XTD_CUDA(cudaStreamSynchronize(s));
+        c->phiv.release();
+        c->xc_oz = true;
+      }
     }
     if (h->tau) XTD_REQUIRE(h->nvar == 4, XTD_ERR_ARG, "meta-GGA kernels need value + gradient AO components (nvar = 4)");
     const int nk = h->tau ? 5 : h->nvar;        // kernel components
@@ -407,6 +437,7 @@ int xtd_create(xtd_handle* out, int nao, long workspace_bytes) {
   h->ev_ok = true;
   if (const char* e = getenv("XTD_PROFILE_PHASE")) h->prof_phase = atoi(e);
   if (const char* e = getenv("XTD_GRAPH")) h->graph_mode = atoi(e);
+  if (const char* e = getenv("XTD_OZ_FUSE")) h->oz_fuse = atoi(e) != 0;
   if (const char* e = getenv("XTD_CHUNK_AUX")) h->max_pc = atol(e);
   if (const char* e = getenv("XTD_CHUNK_GRID")) h->max_gb = atol(e);
   *out = h;
@@ -419,7 +450,17 @@ int xtd_destroy(xtd_handle h) {
   for (auto* c : h->ch) {
     c->Co.release(); c->Cv.release(); c->CoT.release(); c->CvT.release(); c->phi.release(); c->phiv.release();
     for (int t = 0; t < 2; ++t) { c->Loo[t].release(); c->Lvv[t].release(); c->Lvo[t].release(); c->Lvt[t].release(); c->Loob[t][0].release(); c->Loob[t][1].release(); }
-    for (int t = 0; t < 2; ++t) { if (c->LvvS[t]) cudaFree(c->LvvS[t]); if (c->LvvScale[t]) cudaFree(c->LvvScale[t]); }
+    for (int t = 0; t < 2; ++t) {
+      if (c->LvvS[t]) cudaFree(c->LvvS[t]);
+      if (c->LvvScale[t]) cudaFree(c->LvvScale[t]);
+      if (c->LooS[t]) cudaFree(c->LooS[t]);
+      if (c->LooScale[t]) cudaFree(c->LooScale[t]);
+      if (c->LooNorm[t]) cudaFree(c->LooNorm[t]);
+    }
+    if (c->phivF) cudaFree(c->phivF);
+    if (c->phivB) cudaFree(c->phivB);
+    if (c->phivFs) cudaFree(c->phivFs);
+    if (c->phivBs) cudaFree(c->phivBs);
     if (c->g_indptr) cudaFree(c->g_indptr);
     if (c->g_cols) cudaFree(c->g_cols);
     if (c->g_vals) cudaFree(c->g_vals);
@@ -583,6 +624,14 @@ int xtd_df_begin(xtd_handle h, int tensor, long naux_local) {
       XTD_CUDA(cudaMalloc((void**)&c->LvvS[tensor], std::max<size_t>(c->ozB.slice_bytes(naux_local, h->oz_slices), 16)));
       XTD_CUDA(cudaMalloc((void**)&c->LvvScale[tensor], std::max<size_t>(c->ozB.scale_doubles(naux_local, c->oz_group), 2) * 8));
       c->Lvv[tensor].release();
+      c->ozL.set(c->no, OZ_BM, c->no);
+      if (c->LooS[tensor]) cudaFree(c->LooS[tensor]);
+      if (c->LooScale[tensor]) cudaFree(c->LooScale[tensor]);
+      if (c->LooNorm[tensor]) cudaFree(c->LooNorm[tensor]);
+      c->LooS[tensor] = nullptr; c->LooScale[tensor] = c->LooNorm[tensor] = nullptr;
+      XTD_CUDA(cudaMalloc((void**)&c->LooS[tensor], std::max<size_t>(c->ozL.slice_bytes(naux_local, h->oz_slices), 16)));
+      XTD_CUDA(cudaMalloc((void**)&c->LooScale[tensor], std::max<size_t>((size_t)naux_local * c->ozL.rows_pad, 2) * 8));
+      XTD_CUDA(cudaMalloc((void**)&c->LooNorm[tensor], std::max<size_t>((size_t)naux_local * c->ozL.rows_pad, 2) * 8));
     } else {
       XTD_TRY(c->Lvv[tensor].alloc((size_t)naux_local * c->nv * c->ldvv, h->stream));
     }
@@ -680,6 +729,15 @@ int xtd_df_add(xtd_handle h, int tensor, const double* l_dev, long np, long ld_r
           e.batches = pn; e.a_hi = 1; e.b_hi = 0;
           e.C = c->Loo[tensor].p + P0 * c->no * c->ldoo; e.ldc = c->ldoo; e.c_batch_stride = (long)c->no * c->ldoo;
           XTD_TRY(gemm(h->gemm, e, s));
+          if (c->use_oz[tensor]) {
+            // A operand of the fused half-transform: one q-slice per aux function, one scale per (aux function, row)
+            const double* lc = c->Loo[tensor].p + P0 * c->no * c->ldoo;
+            XTD_TRY(oz_slice(h->oz_slices, c->LooS[tensor] + c->ozL.slice_bytes(P0, h->oz_slices), c->LooScale[tensor] + (size_t)P0 * c->ozL.rows_pad,
+                             c->ozL, lc, c->ldoo, (long)c->no * c->ldoo, pn, 1, s));
+            oz_rownorm_kernel<<<dim3(c->ozL.rows_pad, pn), 128, 0, s>>>(c->LooNorm[tensor] + (size_t)P0 * c->ozL.rows_pad, c->ozL.rows_pad, lc, c->ldoo,
+                                                                        (long)c->no * c->ldoo, c->no, c->no);
+            LAUNCH_CHECK();
+          }
           if (c->need_split[tensor]) {
             const int o2 = c->o_blocks[1].first;
             const int r0s[2] = {0, o2}, nrs[2] = {o2, c->no - o2};
@@ -959,7 +1017,115 @@ static bool xc_use_split(const xtd_engine* h, int nvec) {
   return split < 0.9 * four;
 }
 
+// Grid path with both GEMMs emulated on the INT8 tensor cores (one AO component: ALDA0 and LDA kernels):
+//   forward   Y[g][(x,o)] = sum_v phiv[g][v] Z[(x,o)][v]          A = int8 planes of phiv (static), B = planes of Z (per call)
+//   weighting xc_weight_kernel in place (unchanged)
+//   backward  SIG[(x,o)][v] += sum_g A[g][(x,o)] phiv[g][v]        contraction over grid points: both operands sliced from
+//             their transposed sources, q-slices = blocks of OZ_XC_KQ points, one power-of-two scale per (row, block)
+static int run_xc_emulated(xtd_engine* h, int nvec) {
+  cudaStream_t s = h->stream;
+  const int nch = (int)h->ch.size();
+  const int S = h->oz_slices;
+  OzShape shZ[2], shA[2];
+  size_t per_g = 0, fixed = 0, w_doubles = 0;
+  int splits_max = 8;
+  for (int c = 0; c < nch; ++c) {
+    Channel* ch = h->ch[c];
+    shZ[c].set(nvec * ch->no, OZ_BN, ch->nv);
+    shA[c].set(nvec * ch->no, OZ_BM, OZ_XC_KQ);
+    per_g += (size_t)shZ[c].rows_pad + (size_t)shA[c].rows_pad * S / 8 + 1;
+    fixed += shZ[c].slice_bytes(1, S) / 8 + shZ[c].rows_pad + 64;
+    fixed += (size_t)(65536 / OZ_XC_KQ) * shA[c].rows_pad + 64;
+    w_doubles = std::max(w_doubles, (size_t)splits_max * shA[c].rows_pad * ch->ozPB.rows_pad);
+  }
+  fixed += w_doubles + 4096;
+  XTD_REQUIRE(h->scratch_doubles > fixed + per_g * OZ_XC_KQ, XTD_ERR_NOMEM, "workspace too small for one block of the emulated grid path");
+  long GB = (long)((h->scratch_doubles - fixed) / per_g);
+  GB = std::min<long>(GB, 1 << 16);
+  if (h->max_gb > 0) GB = std::min<long>(GB, std::max<long>(h->max_gb, OZ_XC_KQ));
+  GB = GB / OZ_XC_KQ * OZ_XC_KQ;
+  h->last_grid_chunks = cdiv(h->ng, GB);
+  // carve the scratch region
+  double* cur = h->scratch;
+  auto take = [&](size_t n) { double* p = cur; cur += (n + 31) & ~(size_t)31; return p; };
+  double* W = take(w_doubles);
+  int8_t* zS[2]; double* zsc[2]; double* Y[2]; int8_t* aS[2]; double* asc[2];
+  const long gbmax = std::min<long>(GB, round_up(h->ng, 128));
+  for (int c = 0; c < nch; ++c) {
+    zS[c] = reinterpret_cast<int8_t*>(take(shZ[c].slice_bytes(1, S) / 8));
+    zsc[c] = take(shZ[c].rows_pad);
+    Y[c] = take((size_t)gbmax * shZ[c].rows_pad);
+    aS[c] = reinterpret_cast<int8_t*>(take((size_t)cdiv(gbmax, OZ_XC_KQ) * shA[c].slice_bytes(1, S) / 8));
+    asc[c] = take((size_t)cdiv(gbmax, OZ_XC_KQ) * shA[c].rows_pad);
+  }
+  {
+    PhaseTimer t(h, XTD_T_XC_SLICE);
+    for (int c = 0; c < nch; ++c)
+      XTD_TRY(oz_slice(S, zS[c], zsc[c], shZ[c], h->Z[c], h->ch[c]->ldz, 0, 1, 1, s));
+  }
+  for (long g0 = 0; g0 < h->ng; g0 += GB) {
+    const int gb = (int)std::min<long>(GB, h->ng - g0);
+    const int nmt_g = (int)cdiv(gb, OZ_BM);
+    {
+      PhaseTimer t(h, XTD_T_XC_GEMM);
+      for (int c = 0; c < nch; ++c) {
+        Channel* ch = h->ch[c];
+        OzGemmParams p;
+        p.A = ch->phivF + (size_t)(g0 / OZ_BM) * ch->ozPF.nkb * S * (OZ_BM * OZ_KB);
+        p.B = zS[c]; p.sa = ch->phivFs + g0; p.sb = zsc[c];
+        p.nmt = nmt_g; p.nnt = shZ[c].nrt; p.nkb = ch->ozPF.nkb; p.nq = 1; p.group = 1; p.b_q0 = 0;
+        p.Mpad = nmt_g * OZ_BM; p.Npad = shZ[c].rows_pad; p.splits = 1; p.W = Y[c]; p.alpha = 1.0;
+        XTD_TRY(oz_gemm(S, p, s));
+        h->gemm.flops += 2.0 * gb * (double)(nvec * ch->no) * ch->nv;
+      }
+    }
+    {
+      PhaseTimer t(h, XTD_T_XC_STREAM);
+      XcArgs a;
+      a.nch = nch; a.nvec = nvec; a.gb = gb; a.g0 = g0;
+      for (int c = 0; c < 2; ++c) {
+        const bool on = c < nch;
+        a.Y[c] = on ? Y[c] : nullptr; a.ldY[c] = on ? shZ[c].rows_pad : 0; a.y_comp[c] = 0;
+        a.phi[c] = on ? h->ch[c]->phi.p : nullptr; a.ldphi[c] = on ? h->ch[c]->ldphi : 0; a.phi_comp[c] = on ? h->ng * h->ch[c]->ldphi : 0;
+        a.no[c] = on ? h->ch[c]->no : 0;
+      }
+      a.wf = (h->fxc_kind == XTD_FXC_ALDA0) ? h->fxc : h->wf.p;
+      if (h->fxc_kind == XTD_FXC_UKS) launch_xc<1, XC_KIND_UKS, false>(a, s);
+      else if (h->fxc_kind == XTD_FXC_ALDA0) launch_xc<1, XC_KIND_ALDA0, false>(a, s);
+      else launch_xc<1, XC_KIND_MCOL, false>(a, s);
+      LAUNCH_CHECK();
+    }
+    const int nqc = (int)cdiv(gb, OZ_XC_KQ);
+    {
+      PhaseTimer t(h, XTD_T_XC_SLICE);
+      for (int c = 0; c < nch; ++c)
+        XTD_TRY(oz_slice(S, aS[c], asc[c], shA[c], Y[c], shZ[c].rows_pad, (long)OZ_XC_KQ * shZ[c].rows_pad, nqc, 1, s, true, gb));
+    }
+    {
+      PhaseTimer t(h, XTD_T_XC_GEMM);
+      for (int c = 0; c < nch; ++c) {
+        Channel* ch = h->ch[c];
+        OzGemmParams p;
+        p.A = aS[c]; p.B = ch->phivB; p.sa = asc[c]; p.sb = ch->phivBs;
+        p.nmt = shA[c].nrt; p.nnt = ch->ozPB.nrt; p.nkb = shA[c].nkb; p.nq = nqc; p.group = 1; p.b_q0 = (int)(g0 / OZ_XC_KQ);
+        p.Mpad = shA[c].rows_pad; p.Npad = ch->ozPB.rows_pad;
+        p.splits = std::min(splits_max, oz_choose_splits(p.nmt * p.nnt, nqc, h->gemm.num_sms));
+        p.W = W; p.alpha = 1.0;
+        XTD_TRY(oz_gemm(S, p, s));
+        const int M = nvec * ch->no, N = ch->nv;
+        const long nblk = cdiv((long)M * N, 256);
+        reduce_splits_kernel<<<dim3((unsigned)(nblk > 4096 ? 4096 : nblk), 1), 256, 0, s>>>(
+            h->SIG + h->sig_base[c], ch->ldz, 0, W, ch->ozPB.rows_pad, 0, (long)shA[c].rows_pad * ch->ozPB.rows_pad, p.splits, M, N, 1, 0, 0, 0);
+        LAUNCH_CHECK();
+        h->gemm.flops += 2.0 * gb * (double)M * N;
+      }
+    }
+  }
+  return XTD_OK;
+}
+
 static int run_xc(xtd_engine* h, int nvec) {
+  if (h->ch[0]->xc_oz) return run_xc_emulated(h, nvec);
   cudaStream_t s = h->stream;
   const int nch = (int)h->ch.size();
   const int nve = h->nvar_eff;
@@ -1086,7 +1252,87 @@ static int run_xc(xtd_engine* h, int nvec) {
 //   K1 (DMMA)   U[P][(i,x)][b] = sum_j Loo[(P,i)][j] zt[x][b][j]            as in run_k
 //   slice       U -> S int8 digit planes + one power-of-two scale per (row, group of aux functions)
 //   K2 (tcgen05.mma kind::i8, TMEM)   SIG[x][i][a] += w sum_P sum_b U[P][(i,x)][b] Lvv[P][a][b]   against the int8 planes of Lvv
+// ... with the half-transform fused (oz_k1_kernel): U never exists in fp64; the A planes of the contraction are written directly
+static int run_k_fused(xtd_engine* h, const KTermRec& k, int nvec) {
+  cudaStream_t s = h->stream;
+  Channel* ch = h->ch[k.ch];
+  const long naux = h->naux[k.tensor];
+  const int S = h->oz_slices, G = ch->oz_group;
+  OzShape shA, shZt;
+  shA.set(nvec * ch->no, OZ_BM, ch->nv);          // rows m = x no + i of the contraction's A operand
+  shZt.set(ch->nv, OZ_BN, ch->no);                // zt[x][b][j]: one q-slice per trial vector
+  const OzShape &shB = ch->ozB, &shL = ch->ozL;
+  const int tiles = shA.nrt * shB.nrt;
+  int splits_max = std::min<long>(64, std::max<long>(1, cdiv(naux, G)));
+  size_t w_doubles = (size_t)splits_max * shA.rows_pad * shB.rows_pad;
+  while (splits_max > 1 && w_doubles * 4 > h->scratch_doubles) { splits_max /= 2; w_doubles = (size_t)splits_max * shA.rows_pad * shB.rows_pad; }
+  const size_t zt_doubles = shZt.slice_bytes(nvec, S) / 8 + 2 * (size_t)nvec * shZt.rows_pad + nvec + 256;
+  const size_t a_per_p = shA.slice_bytes(1, S) / 8;
+  const size_t per_p = a_per_p + (size_t)cdiv(shA.rows_pad, G) + 1;
+  XTD_REQUIRE(h->scratch_doubles > w_doubles + zt_doubles + (size_t)G * per_p + 4096, XTD_ERR_NOMEM,
+              "workspace too small for one group of the emulated exchange contraction");
+  long pc = (long)((h->scratch_doubles - w_doubles - zt_doubles - 4096) / per_p);
+  pc = std::min<long>(pc, naux);
+  if (pc > 32768) pc = 32768;
+  if (h->max_pc > 0) pc = std::min<long>(pc, h->max_pc);
+  if (pc < naux) pc = std::max<long>(pc / G * G, G);
+  h->last_aux_chunks = std::max<long>(h->last_aux_chunks, cdiv(naux, pc));
+  double* cur = h->scratch;
+  auto take = [&](size_t n) { double* p = cur; cur += (n + 31) & ~(size_t)31; return p; };
+  double* W = take(w_doubles);
+  int8_t* ztS = reinterpret_cast<int8_t*>(take(shZt.slice_bytes(nvec, S) / 8));
+  double* ztScale = take((size_t)nvec * shZt.rows_pad);
+  double* ztNorm = take((size_t)nvec * shZt.rows_pad);
+  double* zmax = take(nvec);
+  int8_t* As = reinterpret_cast<int8_t*>(take((size_t)pc * a_per_p));
+  double* so = take((size_t)cdiv(pc, G) * shA.rows_pad);
+  {
+    PhaseTimer t(h, XTD_T_K2_SLICE);
+    XTD_TRY(oz_slice(S, ztS, ztScale, shZt, h->ZT[k.ch], ch->ldzt, (long)ch->nv * ch->ldzt, nvec, 1, s));
+    oz_rownorm_kernel<<<dim3(shZt.rows_pad, nvec), 128, 0, s>>>(ztNorm, shZt.rows_pad, h->ZT[k.ch], ch->ldzt, (long)ch->nv * ch->ldzt, ch->nv, ch->no);
+    LAUNCH_CHECK();
+    oz_colmax_kernel<<<nvec, 256, 0, s>>>(zmax, ztNorm, shZt.rows_pad, ch->nv);
+    LAUNCH_CHECK();
+  }
+  for (long P0 = 0; P0 < naux; P0 += pc) {
+    const int pn = (int)std::min<long>(pc, naux - P0);
+    const int ng = (int)cdiv(pn, G);
+    {
+      PhaseTimer t(h, XTD_T_K1);
+      oz_bound_scale_kernel<<<dim3((unsigned)cdiv(shA.rows_pad, 256), ng), 256, 0, s>>>(so, shA.rows_pad, ch->LooNorm[k.tensor] + (size_t)P0 * shL.rows_pad,
+                                                                                        shL.rows_pad, zmax, pn, G, nvec, ch->no);
+      LAUNCH_CHECK();
+      OzK1Params q;
+      q.A = ch->LooS[k.tensor] + shL.slice_bytes(P0, S); q.B = ztS;
+      q.sa = ch->LooScale[k.tensor] + (size_t)P0 * shL.rows_pad; q.sb = ztScale; q.so = so; q.out = As;
+      q.np = pn; q.nit = shL.nrt; q.nbt = shZt.nrt; q.nkb1 = shL.nkb; q.nvec = nvec; q.no = ch->no; q.group = G;
+      q.nmt2 = shA.nrt; q.nkb2 = shA.nkb; q.Mpad2 = shA.rows_pad;
+      q.ntiles = (long)pn * q.nit * nvec * q.nbt;
+      XTD_TRY(oz_k1(S, q, h->gemm.num_sms, s));
+      h->gemm.flops += 2.0 * pn * (double)ch->no * ch->no * ch->nv * nvec;
+    }
+    {
+      PhaseTimer t(h, XTD_T_K2);
+      OzGemmParams p;
+      p.A = As; p.B = ch->LvvS[k.tensor]; p.sa = so; p.sb = ch->LvvScale[k.tensor];
+      p.nmt = shA.nrt; p.nnt = shB.nrt; p.nkb = shA.nkb; p.nq = pn; p.group = G; p.b_q0 = (int)P0;
+      p.Mpad = shA.rows_pad; p.Npad = shB.rows_pad;
+      p.splits = std::min(splits_max, oz_choose_splits(tiles, ng, h->gemm.num_sms));
+      p.W = W; p.alpha = k.w[0][0][0][0];
+      XTD_TRY(oz_gemm(S, p, s));
+      const int M = nvec * ch->no, N = ch->nv;
+      const long nblk = cdiv((long)M * N, 256);
+      reduce_splits_kernel<<<dim3((unsigned)(nblk > 4096 ? 4096 : nblk), 1), 256, 0, s>>>(
+          h->SIG + h->sig_base[k.ch], ch->ldz, 0, W, shB.rows_pad, 0, (long)shA.rows_pad * shB.rows_pad, p.splits, M, N, 1, 0, 0, 0);
+      LAUNCH_CHECK();
+      h->gemm.flops += 2.0 * M * N * (double)ch->nv * pn;
+    }
+  }
+  return XTD_OK;
+}
+
 static int run_k_emulated(xtd_engine* h, const KTermRec& k, int nvec) {
+  if (h->oz_fuse) return run_k_fused(h, k, nvec);
   cudaStream_t s = h->stream;
   Channel* ch = h->ch[k.ch];
   const long naux = h->naux[k.tensor];

@@ -58,7 +58,14 @@ class SigmaEngine:
         # exchange contraction of uniform-weight terms: 0 = FP64 DMMA, 3..8 = INT8 tensor-core emulation with that many
         # radix-256 digit planes (csrc/ozaki.cuh).  None: the XTD_OZAKI environment variable, else FP64 DMMA.
         if exchange_slices is None:
-            exchange_slices = int(os.environ.get("XTD_OZAKI", "0") or 0)
+            env = os.environ.get("XTD_OZAKI", "")
+            if env != "":
+                exchange_slices = int(env)
+            else:
+                # default: 6 planes (46 bits below each row scale, ~4e-12 on sigma, 4x the DMMA rate) once the virtual block spans
+                # several 128-column tiles; small problems are launch-bound and stay on the FP64 DMMA GEMM
+                big = max((len(ch.vir_idx) for ch in plan.channels), default=0) >= 512
+                exchange_slices = 6 if big else 0
         self.exchange_slices = int(exchange_slices)
         if self.exchange_slices:
             _lib.check(self.lib.xtd_set_exchange_emulation(self._h, self.exchange_slices), "xtd_set_exchange_emulation")
