@@ -32,6 +32,7 @@ namespace xtd {
 
 constexpr int OZ_BM = 128, OZ_BN = 64, OZ_KB = 32, OZ_STAGES = 4, OZ_MAX_S = 8, OZ_MIN_S = 3;
 constexpr int OZ_THREADS = 192;
+constexpr int OZ_K1_THREADS = 320;     // producer + MMA issuer + 8 epilogue warps
 
 __device__ __forceinline__ uint32_t oz_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -423,7 +424,7 @@ struct OzK1Params {
 };
 
 template <int S>
-__global__ void __launch_bounds__(OZ_THREADS, 1) oz_k1_kernel(const OzK1Params p) {
+__global__ void __launch_bounds__(OZ_K1_THREADS, 1) oz_k1_kernel(const OzK1Params p) {
   constexpr int A_SLICE = OZ_BM * OZ_KB, B_SLICE = OZ_BN * OZ_KB;
   constexpr int A_BYTES = S * A_SLICE, B_BYTES = S * B_SLICE, STAGE = A_BYTES + B_BYTES;
   extern __shared__ __align__(128) uint8_t oz_smem[];
@@ -440,7 +441,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_k1_kernel(const OzK1Params p
       oz_mbar_init(&empty[s], 1);
     }
     oz_mbar_init(tmem_full, 1);
-    oz_mbar_init(tmem_empty, 128);
+    oz_mbar_init(tmem_empty, OZ_K1_THREADS - 64);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -508,7 +509,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_k1_kernel(const OzK1Params p
       }
     }
   } else {
-    const int quad = warp & 3;
+    // eight epilogue warps: two per TMEM lane quadrant, each takes half of the 64 columns (latency hiding for the fp64 chains)
+    const int quad = warp & 3, half = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
     const double magic = 6755399441055744.0;
@@ -532,7 +534,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_k1_kernel(const OzK1Params p
       oz_mbar_wait(tmem_full, (uint32_t)(n & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-      for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
+      for (int cc = 0; cc < OZ_BN / 2; cc += 16) {
+        const int c0 = half * (OZ_BN / 2) + cc;
         double v[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) v[k] = 0.0;
@@ -649,7 +652,7 @@ inline int oz_k1_launch(const OzK1Params& p, int num_sms, cudaStream_t st) {
     attr_set[dev & 63] = true;
   }
   const unsigned grid = (unsigned)std::min<long>(p.ntiles, num_sms);
-  oz_k1_kernel<S><<<grid, OZ_THREADS, (size_t)OZ_STAGES * S * (OZ_BM + OZ_BN) * OZ_KB + 256, st>>>(p);
+  oz_k1_kernel<S><<<grid, OZ_K1_THREADS, (size_t)OZ_STAGES * S * (OZ_BM + OZ_BN) * OZ_KB + 256, st>>>(p);
   XTD_COUNT_LAUNCH();
   XTD_CUDA(cudaGetLastError());
   return XTD_OK;
