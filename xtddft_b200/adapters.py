@@ -3,9 +3,11 @@
   * a `ProblemData` (or a `SynthMF` wrapping one): synthetic / pre-extracted SCF quantities -- the path that is
     exercised and tested here (PySCF, libcint and libxc are not installable in the build or bench containers);
   * a PySCF ROKS/UKS (or ROHF/UHF) object: `from_pyscf` extracts exactly what the reference's `gen_vind()` closures
-    capture (xtddft/XTDA.py:558-613, xtddft/SF_TDA.py:39-88,162-221, xtddft/XSF_TDA.py:1029-1121).  This adapter follows the
-    PySCF 2.11/2.12 API from the reference's own call sites; it could NOT be executed here and is therefore
-    "parity unpinned" until run next to a PySCF install.
+    capture (xtddft/XTDA.py:558-613, xtddft/SF_TDA.py:39-88,162-221, xtddft/XSF_TDA.py:1029-1121), duck-typed on the
+    attributes the reference itself touches.  PySCF is not installable here, so the adapter is executed in the tests against
+    the stand-in mean-field objects that tests/golden/make_golden.py feeds to the REFERENCE's own classes: driver class ->
+    adapter -> engine must reproduce the golden sigma vectors the reference produced from the same object.  Real-molecule
+    energies (Be, HF, CH2O+) stay unpinned until a PySCF install is reachable (tests/test_gpu_adapter.py has the skip-if test).
 """
 from __future__ import annotations
 
@@ -90,100 +92,184 @@ def problem_from_mf(mf, **kw) -> ProblemData:
     return from_pyscf(mf, **kw)
 
 
-def from_pyscf(mf, kernel: str = "uks", collinear_samples: int = 60, auxbasis=None) -> ProblemData:   # pragma: no cover
-    """Extract a ProblemData from a PySCF mean-field object.  kernel: 'uks' (X-TDA), 'alda0', 'mcol', 'none'.
+class NotDensityFittedError(ValueError):
+    """The mean-field object carries no density-fitting tensor: the reference would contract exact 4-centre integrals for it
+    (`mf.get_jk`, XTDA.py:520-539), this build is density-fitted only."""
 
-    Needs `pyscf` (and `mcfun` for kernel='mcol').  Untested in this repository's environments (no PySCF)."""
-    try:
-        from pyscf import df, lib, scf
-    except ImportError as e:
-        raise ImportError("from_pyscf needs PySCF; pass a ProblemData / SynthMF instead") from e
+
+def _tril_source(with_df):
+    """(source, naux) of PySCF's packed 3-centre tensor: the in-memory array `_cderi` itself, or `with_df.loop` for a tensor that
+    lives on disk -- both in lower-triangular packed rows [naux, nao(nao+1)/2]; never unpacked on the host."""
+    cd = getattr(with_df, "_cderi", None)
+    if cd is None and hasattr(with_df, "build"):
+        with_df.build()
+        cd = with_df._cderi
+    if isinstance(cd, np.ndarray):
+        return np.asarray(cd, dtype=np.float64), int(cd.shape[0])
+    naux = int(with_df.get_naoaux())
+    return (lambda: with_df.loop()), naux
+
+
+def _kernel_and_grid(mf, mol, kernel, mo_coeff, mo_occ2, restricted, collinear_samples, fxc_mcol):
+    """AO values on the grid and the cached kernel, through the same numint calls as the reference: `ni.block_loop`
+    (XTDA.py:514 via nr_uks_fxc, SF_TDA.py:63-64), `ni.cache_xc_kernel(..., spin=1)` (XTDA.py:504), the ALDA0 formula of
+    SF_TDA.cache_xc_kernel_sf (SF_TDA.py:39-88), the multicollinear sampling of cache_xc_kernel_sf_mc (SF_TDA.py:942-974)."""
+    ni = mf._numint
+    xt = ni._xc_type(mf.xc)
+    if xt not in ("LDA", "GGA", "MGGA"):
+        raise NotImplementedError(f"kernel type {xt} is not supported by the B200 path")
+    xctype = {"LDA": XC_LDA, "GGA": XC_GGA, "MGGA": XC_MGGA}[xt]
+    nao = mol.nao_nr()
+    ao_deriv = 0 if xt == "LDA" else 1        # meta-GGA: value + gradient only (MGGA_DENSITY_LAPL off, as in the reference)
+    make_rho = None
+    if kernel in ("alda0", "mcol"):
+        dm0 = mf.make_rdm1()
+        if restricted:
+            try:                               # SF_TDA.py:58-60
+                dm0.mo_coeff = (mf.mo_coeff, mf.mo_coeff)
+                dm0.mo_occ = mo_occ2
+            except AttributeError:
+                pass
+        make_rho = ni._gen_rho_evaluator(mol, dm0, hermi=0, with_lapl=False)[0]
+    aos, ws, f_alda0, rhoa_all, rhob_all = [], [], [], [], []
+    for ao, mask, weight, coords in ni.block_loop(mol, mf.grids, nao, ao_deriv, getattr(mf, "max_memory", 2000)):
+        ao = np.asarray(ao)
+        aos.append(ao[None] if ao.ndim == 2 else ao[:4])
+        ws.append(np.asarray(weight))
+        if make_rho is not None:
+            rhoa, rhob = make_rho(0, ao, mask, xt), make_rho(1, ao, mask, xt)
+            if kernel == "mcol":
+                rhoa_all.append(np.asarray(rhoa)); rhob_all.append(np.asarray(rhob))
+                continue
+            if xt == "LDA":
+                rho = (rhoa, rhob)
+            else:                              # GGA / meta-GGA evaluated with the gradients zeroed (SF_TDA.py:74-80)
+                rha, rhb = np.zeros_like(rhoa), np.zeros_like(rhob)
+                rha[0], rhb[0] = rhoa[0], rhob[0]
+                rho = (rha, rhb)
+                rhoa, rhob = rhoa[0], rhob[0]
+            vxc = ni.eval_xc_eff(mf.xc, rho, deriv=1, xctype=xt)[1]
+            f_alda0.append((vxc[0, 0] * weight - vxc[1, 0] * weight) / (np.asarray(rhoa) - np.asarray(rhob) + 1e-9))
+    ao = np.ascontiguousarray(np.concatenate(aos, axis=1), dtype=np.float64)
+    weights = np.ascontiguousarray(np.concatenate(ws), dtype=np.float64)
+    fxc_uks = fxc_alda0 = None
+    if kernel == "uks":
+        fxc_uks = np.asarray(ni.cache_xc_kernel(mol, mf.grids, mf.xc, mo_coeff, mo_occ2, 1)[2], dtype=np.float64)
+    elif kernel == "alda0":
+        fxc_alda0 = np.ascontiguousarray(np.concatenate(f_alda0), dtype=np.float64)
+    elif kernel == "mcol" and fxc_mcol is None:
+        try:
+            import mcfun
+            from pyscf.dft import xc_deriv
+        except ImportError as e:
+            raise ImportError("the multicollinear kernel is sampled by the third-party `mcfun` package (SF_TDA.py:924-938), which is "
+                              "not importable here: install it, or pass the cached kernel as fxc_mcol=[nvar, nvar, ngrids]") from e
+        rho_ab = np.asarray((np.hstack(rhoa_all), np.hstack(rhob_all)))
+        rho_tmz = np.zeros_like(rho_ab) + 1e-11            # SF_TDA.py:967-970
+        rho_tmz[0] += rho_ab[0] + rho_ab[1]
+        rho_tmz[1] += rho_ab[0] - rho_ab[1]
+
+        def fn_eval_xc(rho, deriv):
+            evfk = list(ni.eval_xc_eff(mf.xc, rho, deriv=deriv, xctype=xt))
+            for order in range(1, deriv + 1):
+                if evfk[order] is not None:
+                    evfk[order] = xc_deriv.ud2ts(evfk[order])
+            return evfk
+        fxc_mcol = mcfun.eval_xc_eff_sf(fn_eval_xc, rho_tmz, 2, collinear_samples=collinear_samples)
+        fxc_mcol = fxc_mcol[2] if isinstance(fxc_mcol, (tuple, list)) else fxc_mcol
+    if fxc_mcol is not None:
+        fxc_mcol = np.ascontiguousarray(fxc_mcol, dtype=np.float64)
+    return xctype, ao, weights, fxc_uks, fxc_alda0, fxc_mcol
+
+
+def from_pyscf(mf, kernel: str = "uks", collinear_samples: int = 60, auxbasis=None, fxc_mcol=None) -> ProblemData:
+    """Extract a ProblemData from a converged PySCF-style ROKS / UKS (ROHF / UHF) object -- exactly what the reference's
+    `gen_vind()` closures capture (XTDA.py:558-613, SF_TDA.py:162-221, XSF_TDA.py:1029-1121).  kernel: 'uks' (X-TDA),
+    'alda0', 'mcol', 'none'.
+
+    Duck-typed: only attributes and methods of `mf` are used (`mol.nao_nr`, `mo_coeff/mo_occ/mo_energy`, `make_rdm1`, `get_veff`,
+    `get_hcore`, `xc`, `_numint`, `grids`, `with_df`), so it runs on PySCF objects and on the stand-in mean-field objects of
+    tests/golden/make_golden.py alike (tests/test_adapter_cpu.py, tests/test_gpu_adapter.py execute it).  `scf.ROHF(mol)` --
+    the pure-HF Fock provider of the spin-adaptation terms (XTDA.py:607-613, XSF_TDA.py:1103-1111) -- is looked up in
+    `pyscf.scf` when that is importable.
+
+    The engine is density-fitted only.  An `mf` without `with_df` raises NotDensityFittedError unless `auxbasis` is given
+    explicitly (the caller then accepts the DF approximation, which differs from the reference's exact integrals by the fitting
+    error).  The 3-centre tensor stays in PySCF's packed storage and is streamed to the device block by block."""
     mol = mf.mol
     nao = mol.nao_nr()
     restricted = np.asarray(mf.mo_coeff).ndim == 2
     if restricted:
-        c = np.asarray(mf.mo_coeff)
+        c = np.asarray(mf.mo_coeff, dtype=np.float64)
         occ = np.asarray(mf.mo_occ)
         nc, no = int((occ >= 2).sum()), int(((occ >= 1) & (occ < 2)).sum())
         nv = int((occ == 0).sum())
         mo_coeff = np.stack([c, c])
-        mo_energy = np.stack([mf.mo_energy, mf.mo_energy])
+        mo_energy = np.stack([mf.mo_energy, mf.mo_energy]).astype(np.float64)
     else:
-        mo_coeff = np.asarray(mf.mo_coeff)
+        mo_coeff = np.asarray(mf.mo_coeff, dtype=np.float64)
         occ = np.asarray(mf.mo_occ)
         na, nb = int((occ[0] > 0).sum()), int((occ[1] > 0).sum())
         nc, no, nv = nb, na - nb, mo_coeff.shape[2] - na
-        mo_energy = np.asarray(mf.mo_energy)
+        mo_energy = np.asarray(mf.mo_energy, dtype=np.float64)
+    nmo = mo_coeff.shape[2]
+    mo_occ2 = np.zeros((2, nmo))
+    mo_occ2[0, :nc + no] = 1
+    mo_occ2[1, :nc] = 1
     dm = mf.make_rdm1()
     vhf = mf.get_veff(mol, dm)
     if getattr(mf, "with_solvent", None) is not None:
         vhf = vhf + vhf.v_solvent
-    h1e = mf.get_hcore()
+    h1e = np.asarray(mf.get_hcore())
+    vhf = np.asarray(vhf)
     fock_ks = np.stack([mo_coeff[s].T @ (h1e + vhf[s]) @ mo_coeff[s] for s in (0, 1)])
     fock_hf = None
     if restricted:
+        import importlib
+        try:
+            scf = importlib.import_module("pyscf.scf")
+        except ImportError as e:
+            raise ImportError("the ROHF-form Fock matrix of the spin-adaptation terms comes from pyscf.scf.ROHF(mol).get_veff "
+                              "(XTDA.py:607-613); PySCF is not importable -- pass a ProblemData with fock_hf instead") from e
         hf = scf.ROHF(mol)
         if getattr(mf, "with_x2c", None) is not None:
             hf = hf.x2c()
-        veff = hf.get_veff(mol, dm)
-        h1 = hf.get_hcore()
+        veff = np.asarray(hf.get_veff(mol, dm))
+        h1 = np.asarray(hf.get_hcore())
         fock_hf = np.stack([mo_coeff[s].T @ (h1 + veff[s]) @ mo_coeff[s] for s in (0, 1)])
     is_dft = hasattr(mf, "xc") and hasattr(mf, "_numint")
     omega = alpha = 0.0
     hyb = 1.0
     if is_dft:
-        ni = mf._numint
-        omega, alpha, hyb = ni.rsh_and_hybrid_coeff(mf.xc, mol.spin)
-    # density-fitting tensor (the engine is DF-only; an mf without .with_df gets a fresh DF object)
+        omega, alpha, hyb = mf._numint.rsh_and_hybrid_coeff(mf.xc, mol.spin)
+    # ---- density fitting ---------------------------------------------------------------------------------------
     with_df = getattr(mf, "with_df", None)
     if with_df is None:
+        if auxbasis is None:
+            raise NotDensityFittedError(
+                "this mean-field object is not density-fitted: the reference would contract exact 4-centre integrals (mf.get_jk), the "
+                "B200 path is DF-only.  Use mf.density_fit(), or pass auxbasis=... to accept the fitting error explicitly")
+        from pyscf import df
         with_df = df.DF(mol, auxbasis=auxbasis)
-    if with_df._cderi is None:
-        with_df.build()
-    cderi = lib.unpack_tril(np.asarray(with_df._cderi)) if not isinstance(with_df._cderi, str) else \
-        lib.unpack_tril(np.vstack([blk for blk in with_df.loop()]))
-    cderi_lr = None
+    cderi_packed, naux = _tril_source(with_df)
+    cderi_lr_packed = None
     if omega != 0 and alpha != hyb:
+        from pyscf import df
         with mol.with_range_coulomb(omega):
-            lr = df.DF(mol, auxbasis=with_df.auxbasis).build()
-            cderi_lr = lib.unpack_tril(np.asarray(lr._cderi))
-    ao = weights = fxc_uks = fxc_alda0 = fxc_mcol = None
+            lr = df.DF(mol, auxbasis=getattr(with_df, "auxbasis", auxbasis)).build()
+        cderi_lr_packed, naux_lr = _tril_source(lr)
+        assert naux_lr == naux
+    # ---- grid --------------------------------------------------------------------------------------------------
+    ao = weights = fxc_uks = fxc_alda0 = None
     xctype = XC_NONE
+    if fxc_mcol is None:
+        fxc_mcol = getattr(mf, "fxc_sf_mc", None)      # a multicollinear kernel the caller cached on the object
     if is_dft and kernel != "none":
-        ni = mf._numint
-        xt = ni._xc_type(mf.xc)
-        if xt not in ("LDA", "GGA", "MGGA"):
-            raise NotImplementedError(f"kernel type {xt} is not supported by the B200 path")
-        # meta-GGA: value + gradient AO components and kernel tables with a tau component (no Laplacian, as in the reference)
-        xctype = {"LDA": XC_LDA, "GGA": XC_GGA, "MGGA": XC_MGGA}[xt]
-        coords, weights = mf.grids.coords, np.asarray(mf.grids.weights)
-        aov = ni.eval_ao(mol, coords, deriv=0 if xt == "LDA" else 1)
-        ao = aov[None] if xt == "LDA" else aov[:4]
-        mo_occ2 = np.zeros((2, mo_coeff.shape[2]))
-        mo_occ2[0, :nc + no] = 1
-        mo_occ2[1, :nc] = 1
-        if kernel == "uks":
-            fxc_uks = ni.cache_xc_kernel(mol, mf.grids, mf.xc, mo_coeff, mo_occ2, 1)[2]
-        elif kernel == "alda0":
-            # SF_TDA.cache_xc_kernel_sf: (w v_a - w v_b) / (rho_a - rho_b + 1e-9), GGA evaluated with zeroed gradients
-            rho = []
-            for s in (0, 1):
-                cs = mo_coeff[s][:, mo_occ2[s] > 0]
-                rho.append(((ao[0] @ cs) ** 2).sum(1))
-            if xt == "LDA":
-                rr = (rho[0], rho[1])
-            else:
-                z = np.zeros((3, rho[0].size))
-                rr = (np.vstack([rho[0], z]), np.vstack([rho[1], z]))
-            vxc = ni.eval_xc_eff(mf.xc, rr, deriv=1, xctype=xt)[1]
-            fxc_alda0 = (vxc[0, 0] * weights - vxc[1, 0] * weights) / (rho[0] - rho[1] + 1e-9)
-        elif kernel == "mcol":
-            from pyscf.dft import numint2c
-            ni2 = numint2c.NumInt2C()
-            ni2.collinear = "mcol"
-            ni2.collinear_samples = collinear_samples
-            raise NotImplementedError("multicollinear kernel extraction needs mcfun's eval_xc_eff_sf; supply fxc_mcol explicitly")
+        xctype, ao, weights, fxc_uks, fxc_alda0, fxc_mcol = _kernel_and_grid(mf, mol, kernel, mo_coeff, mo_occ2, restricted,
+                                                                             collinear_samples, fxc_mcol)
+    else:
+        fxc_mcol = None
     return ProblemData(nao=nao, nc=nc, no=no, nv=nv, restricted=restricted, mo_coeff=mo_coeff, mo_energy=mo_energy, fock_ks=fock_ks,
-                       fock_hf=fock_hf, cderi=cderi, cderi_lr=cderi_lr, hyb=hyb, alpha=alpha, omega=omega, xctype=xctype, ao=ao,
-                       weights=weights, fxc_uks=fxc_uks, fxc_alda0=fxc_alda0, fxc_mcol=fxc_mcol,
-                       level_shift=getattr(mf, "level_shift", 0.0) or 0.0, meta=dict(source="pyscf"))
+                       fock_hf=fock_hf, cderi_packed=cderi_packed, cderi_lr_packed=cderi_lr_packed, naux_packed=naux, hyb=hyb, alpha=alpha,
+                       omega=omega, xctype=xctype, ao=ao, weights=weights, fxc_uks=fxc_uks, fxc_alda0=fxc_alda0, fxc_mcol=fxc_mcol,
+                       level_shift=getattr(mf, "level_shift", 0.0) or 0.0, meta=dict(source="mean-field object"))

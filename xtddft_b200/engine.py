@@ -158,6 +158,22 @@ class SigmaEngine:
             blk = torch.from_numpy(np.ascontiguousarray(cderi[p0:p0 + chunk])).to(self.device)
             self.df_add(tensor, blk)
 
+    def load_cderi_packed(self, tensor: int, src, naux: int, rank: int = 0, world: int = 1, chunk: int = 64):
+        """Stream lower-triangular packed rows [naux, nao(nao+1)/2] (PySCF `with_df._cderi`): `src` is a 2-D host array or a
+        zero-argument callable returning an iterator of row blocks (`with_df.loop()`); this rank keeps rows [p0, p1)."""
+        torch = self.torch
+        p0, p1 = split_range(int(naux), rank, world)
+        self.df_begin(tensor, p1 - p0)
+        blocks = src() if callable(src) else (src[i:i + chunk] for i in range(0, src.shape[0], chunk))
+        row = 0
+        for blk in blocks:
+            blk = np.asarray(blk)
+            lo, hi = max(p0 - row, 0), min(p1 - row, blk.shape[0])
+            row += blk.shape[0]
+            for i in range(lo, hi, chunk):
+                part = torch.from_numpy(np.ascontiguousarray(blk[i:min(i + chunk, hi)], dtype=np.float64)).to(self.device)
+                self.df_add(tensor, part, packed=True)
+
     # ---- grid ---------------------------------------------------------------------------------------
     def set_grid(self, ao, weights):
         """ao: torch cuda [nvar, ng, nao(+pad)] fp64, weights: torch cuda [ng]."""
@@ -250,6 +266,9 @@ class SigmaEngine:
             torch.cuda.empty_cache()
         for t in eng.tensors_used:
             full = p.cderi if t == 0 else p.cderi_lr
+            if full is None:                    # PySCF's packed storage: streamed block by block, never unpacked on the host
+                eng.load_cderi_packed(t, p.cderi_packed if t == 0 else p.cderi_lr_packed, p.naux_packed, rank, world, chunk=df_chunk)
+                continue
             p0, p1 = split_range(full.shape[0], rank, world)
             eng.load_cderi(t, full[p0:p1], chunk=df_chunk)
         eng.finalize(max_nvec)

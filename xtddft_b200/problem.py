@@ -45,6 +45,12 @@ class ProblemData:
     fock_hf: Optional[np.ndarray] = None  # [2, nmo, nmo]  ROHF-form Fock of the KS density (ROKS only)
     cderi: Optional[np.ndarray] = None    # [naux, nao, nao] symmetric in the last two indices
     cderi_lr: Optional[np.ndarray] = None  # long-range (erf-attenuated) tensor for range-separated hybrids
+    # PySCF's native storage of the same tensors: lower-triangular packed rows [naux, nao(nao+1)/2] (`with_df._cderi`) or a
+    # zero-argument callable returning an iterator over such row blocks (`with_df.loop()` for an on-disk tensor).  Streamed to
+    # the engine block by block (xtd_df_add(packed=1)); never unpacked on the host.
+    cderi_packed: object = None
+    cderi_lr_packed: object = None
+    naux_packed: int = 0
     hyb: float = 0.0
     alpha: float = 0.0
     omega: float = 0.0
@@ -82,7 +88,9 @@ class ProblemData:
 
     @property
     def naux(self) -> int:
-        return 0 if self.cderi is None else int(self.cderi.shape[0])
+        if self.cderi is None:
+            return int(self.naux_packed)
+        return int(self.cderi.shape[0])
 
     @property
     def ng(self) -> int:
@@ -104,11 +112,11 @@ class ProblemData:
 
     @property
     def has_df(self) -> bool:
-        return self.cderi is not None or self.df_external
+        return self.cderi is not None or self.cderi_packed is not None or self.df_external
 
     @property
     def has_df_lr(self) -> bool:
-        return self.cderi_lr is not None or (self.df_external and self.omega != 0.0)
+        return self.cderi_lr is not None or self.cderi_lr_packed is not None or (self.df_external and self.omega != 0.0)
 
     @property
     def hybrid(self) -> bool:
