@@ -81,6 +81,8 @@ def parse():
     ap.add_argument("--workspace-gb", type=float, default=0.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--davidson", type=int, default=int(os.environ.get("XTD_BENCH_DAVIDSON", "1")))
+    ap.add_argument("--configs-table", type=int, default=int(os.environ.get("XTD_BENCH_TABLE", "1")),
+                    help="at N=1 with the headline config: append compact records of BASELINE configs 1-4 measured in the same run")
     ap.add_argument("--exchange-slices", type=int, default=int(os.environ.get("XTD_OZAKI", "-1")),
                     help="exchange contraction: 0 = FP64 DMMA, 3..8 = INT8 tensor-core emulation with that many 7-bit digits, -1 = default")
     return ap.parse_args()
@@ -251,6 +253,61 @@ def run_reference(args):
            "config": config_dict(dp, nvec, int(plan_for(dp.p, dp.method).ext_dim), 1),
            "cpu_baseline": cb, "e2e": {"value": v, "unit": "sigma-vectors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(out)
+
+
+def compact_config_record(cfg: int, steps: int = 2, warmup: int = 3, cpu_budget_s: float = 5.0) -> dict:
+    """One BASELINE configuration measured like the headline one, reduced to a few numbers: ms per step, sigma-vectors/s, Davidson
+    time-to-roots, the dominant phase with its share of the step and its rate, and the CPU baseline (bounded sample)."""
+    import torch
+    from xtddft_b200.davidson import davidson_for_engine
+    from xtddft_b200.synth_device import make_device_problem
+    from xtddft_b200.workloads import default_workspace_bytes, engine_for_device_problem
+    dp = make_device_problem(cfg, 1.0)
+    nvec = dp.nroots
+    eng = engine_for_device_problem(dp, max_nvec=max(nvec, 16), workspace_bytes=default_workspace_bytes(dp, 1))
+    try:
+        dev = eng.device
+        g = torch.Generator(device=dev); g.manual_seed(4242)
+        z = torch.randn((nvec, eng.ext_dim), generator=g, device=dev, dtype=torch.float64)
+        z /= z.norm(dim=1, keepdim=True)
+        out = torch.empty_like(z)
+        for _ in range(warmup):
+            eng.sigma(z, out)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        phase, pflops = {}, {}
+        e0.record()
+        for _ in range(steps):
+            eng.sigma(z, out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_step = e0.elapsed_time(e1) / steps
+        # per-phase times need the eager path (a replayed CUDA graph times only the total): one more call with stats
+        eng.sigma(z, out)
+        st = eng.stats()
+        phase = {k: v for k, v in st["ms"].items() if k != "total" and v > 0}
+        pflops = st["flops"]
+        rec = {"config": cfg, "workload": dp.name, "method": dp.method, "nvec_per_step": nvec, "dim": int(eng.ext_dim),
+               "ms_per_step": ms_step, "sigma_vectors_per_s": nvec / (ms_step * 1e-3), "exchange_slices": int(eng.exchange_slices)}
+        if phase:
+            top = max(phase, key=phase.get)
+            rec["dominant_phase"] = top
+            rec["dominant_phase_share"] = phase[top] / max(sum(phase.values()), 1e-12)
+            if pflops.get(top, 0.0) > 0:
+                rec["dominant_phase_fp64_equiv_tflops"] = pflops[top] / (phase[top] * 1e-3) / 1e12
+        t0 = time.perf_counter()
+        conv, e, x, info = davidson_for_engine(eng, dp.nroots, dp.method)
+        torch.cuda.synchronize()
+        rec["davidson"] = {"time_to_roots_s": time.perf_counter() - t0, "nroots": dp.nroots, "converged": bool(np.all(conv)),
+                           "cycles": int(info[0]), "sigma_vectors": int(info[1]), "lowest_root_ha": float(e[0])}
+    finally:
+        eng.close()
+        del eng
+        torch.cuda.empty_cache()
+    cb = cpu_reference_rate(dp, 1, target_s=cpu_budget_s)
+    rec["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "extrapolated", "sample")}
+    rec["cpu_baseline"]["time_to_roots_s_extrapolated"] = rec["davidson"]["sigma_vectors"] / cb["value"]
+    return rec
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -474,6 +531,18 @@ def main():
             # solve above (the CPU never runs the full solve)
             cb["time_to_roots_s_extrapolated"] = dav["sigma_vectors"] / cb["value"]
         out_json["cpu_baseline"] = cb
+    if world == 1 and args.configs_table and args.config == 5 and args.scale == 1.0:
+        # BASELINE configs 1-4 in the same driver-run record (the headline config needs the whole GPU: release it first)
+        eng.close()
+        del eng, z, out
+        torch.cuda.empty_cache()
+        table = []
+        for c in (1, 2, 3, 4):
+            try:
+                table.append(compact_config_record(c))
+            except Exception as ex:      # a failed side measurement must not lose the headline record
+                table.append({"config": c, "error": f"{type(ex).__name__}: {ex}"})
+        out_json["configs"] = table
     emit(out_json)
     if world > 1:
         torch.distributed.destroy_process_group()

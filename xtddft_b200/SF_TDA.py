@@ -12,7 +12,7 @@ import numpy as np
 from . import plan as planmod
 from . import utils
 from .adapters import problem_from_mf
-from .drivers_common import TimeCounter, make_engine, solve
+from .drivers_common import TimeCounter, solve, timed_engine
 
 ha2eV = utils.ha2eV
 
@@ -43,7 +43,7 @@ class _SFBase:
         if self._engine is None:
             self.plan = planmod.build_sf_plan(self.problem, isf=self.isf, method=self.method, sa=0, layout=planmod.LAYOUT_PYSCF,
                                               hdiag_kind="sf")
-            self._engine = make_engine(self.plan, self.problem, max_nvec=40)
+            self._engine = timed_engine(self.tc, self.plan, self.problem, max_nvec=40)
         return self._engine
 
     def gen_tda_operation_sf(self):

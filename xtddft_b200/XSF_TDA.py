@@ -11,7 +11,7 @@ import numpy as np
 from . import plan as planmod
 from . import utils
 from .adapters import one_electron_ints, problem_from_mf
-from .drivers_common import TimeCounter, make_engine, solve
+from .drivers_common import TimeCounter, solve, timed_engine
 
 au2ev = utils.au2ev_xsf
 
@@ -44,7 +44,7 @@ class XSF_TDA:
                 self._engine.close()
             self.plan = planmod.build_sf_plan(self.problem, isf=-1, method=self.method, sa=self.SA, layout=planmod.LAYOUT_BLOCK,
                                               remove=self.re, foo=foo, fglobal=fglobal, hdiag_kind="xsf")
-            self._engine = make_engine(self.plan, self.problem, max_nvec=40)
+            self._engine = timed_engine(self.tc, self.plan, self.problem, max_nvec=40)
             self._engine_key = key
         return self._engine
 

@@ -9,7 +9,7 @@ import numpy as np
 from . import plan as planmod
 from . import utils
 from .adapters import one_electron_ints, problem_from_mf
-from .drivers_common import TimeCounter, make_engine, solve
+from .drivers_common import TimeCounter, solve, timed_engine
 
 
 class XSF_TDA_GPU:
@@ -48,7 +48,7 @@ class XSF_TDA_GPU:
             else:
                 self.plan = planmod.build_sf_plan(self.problem, isf=-1, method=self.method, sa=self.X, layout=planmod.LAYOUT_PYSCF,
                                                   remove=self.re, foo=self.foo, fglobal=self.fglobal, hdiag_kind="gpu")
-            self._engine = make_engine(self.plan, self.problem, max_nvec=40)
+            self._engine = timed_engine(self.tc, self.plan, self.problem, max_nvec=40)
         return self._engine
 
     def gen_vind(self):

@@ -13,7 +13,7 @@ import numpy as np
 from . import plan as planmod
 from . import utils
 from .adapters import is_chiral, one_electron_ints, problem_from_mf
-from .drivers_common import TimeCounter, make_engine, solve
+from .drivers_common import TimeCounter, solve, timed_engine
 
 
 class XTDA:
@@ -36,7 +36,7 @@ class XTDA:
     def _get_engine(self):
         if self._engine is None:
             self.plan = planmod.build_xtda_plan(self.problem)
-            self._engine = make_engine(self.plan, self.problem, max_nvec=40)
+            self._engine = timed_engine(self.tc, self.plan, self.problem, max_nvec=40)
         return self._engine
 
     def gen_vind(self, mf=None):

@@ -314,7 +314,11 @@ class SigmaEngine:
                 ptr, n = C.c_void_p(), C.c_long()
                 _lib.check(self.lib.xtd_partial_buffer(self._h, x1 - x0, C.byref(ptr), C.byref(n)), "xtd_partial_buffer")
                 part = _as_tensor(torch, ptr.value, n.value, self.device)
+                ev = self._ar_events()
+                ev[0].record()
                 self.reducer.allreduce_(part)          # one all-reduce(sum, fp64) of the MO-space partial per call
+                ev[1].record()
+                self._ar_pending.append(ev)
                 _lib.check(self.lib.xtd_sigma_finish(self._h, x1 - x0, _ptr(oo)), "xtd_sigma_finish")
         return out
 
@@ -339,11 +343,29 @@ class SigmaEngine:
             return self.sigma_host(np.asarray(zs, dtype=np.float64).reshape(-1, self.ext_dim))
         return vind
 
+    def _ar_events(self):
+        """A pair of CUDA events around the all-reduce of one call (device time of the collective as this rank sees it,
+        waiting for the slowest rank included)."""
+        if not hasattr(self, "_ar_pool"):
+            self._ar_pool, self._ar_pending = [], []
+        if self._ar_pool:
+            return self._ar_pool.pop()
+        return (self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True))
+
     def stats(self) -> dict:
+        """Per-phase device times (ms) and GEMM flops of the LAST sigma call; `allreduce` = the NCCL all-reduce of every
+        partial-sigma block since the previous stats() call."""
         st = _lib.XtdStats()
         _lib.check(self.lib.xtd_get_stats(self._h, C.byref(st)), "xtd_get_stats")
-        return dict(flops_gemm=st.flops_gemm, launches=int(st.launches), ms={n: st.ms[i] for i, n in enumerate(_lib.T_NAMES)},
-                    flops={n: st.flops[i] for i, n in enumerate(_lib.T_NAMES)})
+        ms = {n: st.ms[i] for i, n in enumerate(_lib.T_NAMES)}
+        ar = 0.0
+        for ev in getattr(self, "_ar_pending", []):
+            ar += ev[0].elapsed_time(ev[1])         # xtd_get_stats synchronised the stream
+            self._ar_pool.append(ev)
+        if hasattr(self, "_ar_pending"):
+            self._ar_pending = []
+        ms["allreduce"] = ar
+        return dict(flops_gemm=st.flops_gemm, launches=int(st.launches), ms=ms, flops={n: st.flops[i] for i, n in enumerate(_lib.T_NAMES)})
 
     def last_chunks(self):
         """(aux chunks, grid chunks) the last eager sigma call looped over."""
