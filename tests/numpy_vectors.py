@@ -37,3 +37,8 @@ class NumpyVectors:
 
     def scale(self, x, s):
         x *= np.asarray(s)[:, None]
+
+    def transform(self, work, n_in, t):
+        n_out = t.shape[0]
+        if n_out:
+            work[:n_out] = t @ work[:n_in]

@@ -207,3 +207,31 @@ def test_engine_emulated_grid_path(torch_cuda, monkeypatch, method, xct):
     err = float(np.abs(got - ref).max() / max(1.0, np.abs(ref).max()))
     assert err < 1e-11, err
     eng.close()
+
+
+@pytest.mark.parametrize("nc,no,nv", [(140, 3, 150), (40, 4, 90), (20, 2, 200)])
+@pytest.mark.parametrize("sa,remove", [(3, True), (2, False), (1, True)])
+def test_engine_emulated_block_weighted_exchange(torch_cuda, monkeypatch, nc, no, nv, sa, remove):
+    """XSF-TDA Delta A (block-weighted exchange images): the narrow open-shell output columns keep their DMMA pass, the wide
+    virtual block is emulated -- one fused half-transform per occupied row block (closed rows spanning two 128-row tiles, the
+    open rows inside a tile), one contraction against the planes of Lvv[v2off:, :].  Several aux chunks, odd / even open-shell
+    counts, removed OO vector."""
+    from oracle import sigma as osig
+    from xtddft_b200 import plan as planmod
+    from xtddft_b200.engine import SigmaEngine
+    from xtddft_b200.synth import make_problem
+    monkeypatch.setenv("XTD_CHUNK_AUX", "8")
+    p = make_problem(nc + no + nv, nc, no, nv, 19, 200, xctype="LDA", hyb=0.3, seed=420 + no)
+    vind, hd = osig.xsf_gen_vind(p, sa=sa, method=0, remove=remove, foo=0.8, fglobal=0.7)
+    plan = planmod.build_sf_plan(p, isf=-1, method=0, sa=sa, layout=planmod.LAYOUT_BLOCK, remove=remove, foo=0.8, fglobal=0.7, hdiag_kind="xsf")
+    z = np.random.default_rng(7).standard_normal((3, hd.size))
+    ref = vind(z)
+    eng = SigmaEngine.from_problem(plan, p, workspace_bytes=512 << 20, max_nvec=4, exchange_slices=7, df_chunk=12)
+    got = eng.sigma(torch_cuda.from_numpy(z).cuda()).cpu().numpy()
+    assert eng.last_chunks()[0] == 3
+    st = eng.stats()
+    assert st["ms"]["k2_slice"] > 0, "the emulated path was not taken"
+    err = float(np.abs(got - ref).max() / max(1.0, np.abs(ref).max()))
+    assert err < 1e-11, err
+    assert np.abs(eng.hdiag() - hd).max() < 1e-10
+    eng.close()

@@ -420,7 +420,9 @@ struct OzK1Params {
   const double* so;   // [groups][Mpad2]      output row scales (2^(e-6), |U| < 2^e guaranteed by the bound)
   int8_t* out;        // [np][nmt2][nkb2][S][128 x 32]
   int np, nit, nbt, nkb1, nvec, no, group, nmt2, nkb2, Mpad2;
-  long ntiles;
+  int it0, nit_run;   // row tiles [it0, it0 + nit_run) of every aux function are computed ...
+  int i_lo, i_hi;     // ... and only rows i in [i_lo, i_hi) are written (a row block of a block-weighted term)
+  long ntiles;        // np * nit_run * nvec * nbt
 };
 
 template <int S>
@@ -453,7 +455,7 @@ __global__ void __launch_bounds__(OZ_K1_THREADS, 1) oz_k1_kernel(const OzK1Param
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
-  const long per_p = (long)p.nit * p.nvec * p.nbt, per_it = (long)p.nvec * p.nbt;
+  const long per_p = (long)p.nit_run * p.nvec * p.nbt, per_it = (long)p.nvec * p.nbt;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -464,7 +466,7 @@ __global__ void __launch_bounds__(OZ_K1_THREADS, 1) oz_k1_kernel(const OzK1Param
         const int itile = (int)(r0 / per_it);
         const long r1 = r0 - (long)itile * per_it;
         const int x = (int)(r1 / p.nbt), bt = (int)(r1 - (long)x * p.nbt);
-        const int8_t* a = p.A + (((long)P * p.nit + itile) * p.nkb1) * A_BYTES;
+        const int8_t* a = p.A + (((long)P * p.nit + p.it0 + itile) * p.nkb1) * A_BYTES;
         const int8_t* b = p.B + (((long)x * p.nbt + bt) * p.nkb1) * B_BYTES;
         for (int kb = 0; kb < p.nkb1; ++kb, ++it) {
           const int s = (int)(it % OZ_STAGES);
@@ -519,11 +521,11 @@ __global__ void __launch_bounds__(OZ_K1_THREADS, 1) oz_k1_kernel(const OzK1Param
     for (long t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++n) {
       const int P = (int)(t / per_p);
       const long r0 = t - (long)P * per_p;
-      const int itile = (int)(r0 / per_it);
-      const long r1 = r0 - (long)itile * per_it;
+      const int itile = p.it0 + (int)(r0 / per_it);
+      const long r1 = r0 - (long)(itile - p.it0) * per_it;
       const int x = (int)(r1 / p.nbt), bt = (int)(r1 - (long)x * p.nbt);
       const int i = itile * OZ_BM + row;
-      const bool valid = i < p.no;
+      const bool valid = i >= p.i_lo && i < p.i_hi;
       const int m = x * p.no + i;
       const double sa = valid ? p.sa[(long)P * rowsA + i] : 0.0;
       const double so = valid ? p.so[(long)(P / p.group) * p.Mpad2 + m] : 0.0;
@@ -627,17 +629,21 @@ __global__ void oz_colmax_kernel(double* __restrict__ zmax, const double* __rest
 }
 // so[g][m = x no + i] = scale of the bound  zmax[x] * max_{P in group g} |Loo[P][i][:]|   (1 + 1e-9 covers rounding of the norms and
 // the emulation error of U itself)
+// Only rows with i in [i_lo, i_hi) are written (plus the padding rows m >= nvec no when i_lo == 0).
 __global__ void oz_bound_scale_kernel(double* __restrict__ so, int Mpad2, const double* __restrict__ loo_norm, int rowsA, const double* __restrict__ zmax,
-                                      int np, int group, int nvec, int no) {
+                                      int np, int group, int nvec, int no, int i_lo, int i_hi) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x, g = blockIdx.y;
   if (m >= Mpad2) return;
   double s = 0.0;
   if (m < nvec * no) {
     const int x = m / no, i = m - x * no;
+    if (i < i_lo || i >= i_hi) return;
     double nl = 0.0;
     const int p1 = min(np, (g + 1) * group);
     for (int P = g * group; P < p1; ++P) nl = fmax(nl, loo_norm[(long)P * rowsA + i]);
     s = oz_scale_of(nl * zmax[x] * (1.0 + 1e-9));
+  } else if (i_lo != 0) {
+    return;
   }
   so[(long)g * Mpad2 + m] = s;
 }

@@ -67,6 +67,8 @@ struct Channel {
   double* LvvScale[2] = {nullptr, nullptr}; // [groups][rows_pad]
   OzShape ozB;
   int oz_group = 0;
+  int oz_col0[2] = {0, 0};                  // first output column of the emulated block: 0, or the start of the second virtual
+                                            // block for block-weighted terms (the narrow first block keeps its DMMA pass)
   // ... and the occupied-occupied block as the A operand of the fused half-transform (oz_k1_kernel): planes, row scales, row 2-norms
   int8_t* LooS[2] = {nullptr, nullptr};
   double *LooScale[2] = {nullptr, nullptr}, *LooNorm[2] = {nullptr, nullptr};
@@ -607,16 +609,23 @@ int xtd_df_begin(xtd_handle h, int tensor, long naux_local) {
   for (auto* c : h->ch) {
     if (!c->need_k[tensor]) continue;
     XTD_TRY(c->Loo[tensor].alloc((size_t)naux_local * c->no * c->ldoo, h->stream));
-    // emulated path: every exchange term on this (tensor, channel) has uniform weights (no block-weighted pass reads fp64 Lvv)
+    // emulated path: uniform-weight terms, or block-weighted terms whose first virtual block is narrow (it keeps its DMMA pass;
+    // the wide second block is emulated with one half-transform per occupied row block).  Mixed term lists stay on DMMA.
     c->use_oz[tensor] = false;
+    c->oz_col0[tensor] = 0;
     if (h->oz_slices > 0 && oz_max_group(c->nv, h->oz_slices) >= 1) {
-      bool all_uniform = true;
+      int n_uni = 0, n_blk = 0;
       for (const KTermRec& k : h->kterms)
-        if (k.tensor == tensor && h->ch[k.ch] == c && !k.uniform) all_uniform = false;
-      c->use_oz[tensor] = all_uniform;
+        if (k.tensor == tensor && h->ch[k.ch] == c) (k.uniform ? n_uni : n_blk)++;
+      if (n_blk == 0) c->use_oz[tensor] = n_uni > 0;
+      else if (n_uni == 0 && !(getenv("XTD_OZ_BLOCKED") && atoi(getenv("XTD_OZ_BLOCKED")) == 0)) {
+        if (c->v_blocks.size() == 1) c->use_oz[tensor] = true;
+        else if (c->need_narrow[tensor]) { c->use_oz[tensor] = true; c->oz_col0[tensor] = c->v_blocks[1].first; }
+      }
+      if (c->use_oz[tensor]) c->tail_w = 0;           // no short-tail pass: the emulated block pads to 64-column tiles anyway
     }
     if (c->use_oz[tensor]) {
-      c->ozB.set(c->nv, OZ_BN, c->nv);
+      c->ozB.set(c->nv - c->oz_col0[tensor], OZ_BN, c->nv);
       c->oz_group = std::min(4, oz_max_group(c->nv, h->oz_slices));
       if (c->LvvS[tensor]) cudaFree(c->LvvS[tensor]);
       if (c->LvvScale[tensor]) cudaFree(c->LvvScale[tensor]);
@@ -777,17 +786,17 @@ int xtd_df_add(xtd_handle h, int tensor, const double* l_dev, long np, long ld_r
         XTD_TRY(gemm(h->gemm, e, s));
         if (c->use_oz[tensor])
           XTD_TRY(oz_slice(h->oz_slices, c->LvvS[tensor] + c->ozB.slice_bytes(P0, h->oz_slices),
-                           c->LvvScale[tensor] + (size_t)(P0 / c->oz_group) * c->ozB.rows_pad, c->ozB, lvv_tmp, c->ldvv, (long)c->nv * c->ldvv, pn,
-                           c->oz_group, s));
+                           c->LvvScale[tensor] + (size_t)(P0 / c->oz_group) * c->ozB.rows_pad, c->ozB,
+                           lvv_tmp + (long)c->oz_col0[tensor] * c->ldvv, c->ldvv, (long)c->nv * c->ldvv, pn, c->oz_group, s));
         if (c->need_narrow[tensor]) {
           const size_t v2 = (size_t)c->v_blocks[1].first;
-          XTD_CUDA(cudaMemcpy2DAsync(c->Lvo[tensor].p + P0 * v2 * c->ldvv, v2 * c->ldvv * 8, c->Lvv[tensor].p + P0 * c->nv * c->ldvv,
-                                     (size_t)c->nv * c->ldvv * 8, v2 * c->ldvv * 8, pn, cudaMemcpyDeviceToDevice, s));
+          const double* lsrc = c->use_oz[tensor] ? lvv_tmp : c->Lvv[tensor].p + P0 * c->nv * c->ldvv;     // this chunk's [pn][nv][ldvv]
+          XTD_CUDA(cudaMemcpy2DAsync(c->Lvo[tensor].p + P0 * v2 * c->ldvv, v2 * c->ldvv * 8, lsrc, (size_t)c->nv * c->ldvv * 8,
+                                     v2 * c->ldvv * 8, pn, cudaMemcpyDeviceToDevice, s));
           if (c->tail_w > 0) {
             const size_t tw = (size_t)c->tail_w;
-            XTD_CUDA(cudaMemcpy2DAsync(c->Lvt[tensor].p + P0 * tw * c->ldvv, tw * c->ldvv * 8,
-                                       c->Lvv[tensor].p + (P0 * c->nv + c->tail_start) * c->ldvv, (size_t)c->nv * c->ldvv * 8,
-                                       tw * c->ldvv * 8, pn, cudaMemcpyDeviceToDevice, s));
+            XTD_CUDA(cudaMemcpy2DAsync(c->Lvt[tensor].p + P0 * tw * c->ldvv, tw * c->ldvv * 8, lsrc + (size_t)c->tail_start * c->ldvv,
+                                       (size_t)c->nv * c->ldvv * 8, tw * c->ldvv * 8, pn, cudaMemcpyDeviceToDevice, s));
           }
         }
       }
@@ -1252,12 +1261,36 @@ static int run_xc(xtd_engine* h, int nvec) {
 //   K1 (DMMA)   U[P][(i,x)][b] = sum_j Loo[(P,i)][j] zt[x][b][j]            as in run_k
 //   slice       U -> S int8 digit planes + one power-of-two scale per (row, group of aux functions)
 //   K2 (tcgen05.mma kind::i8, TMEM)   SIG[x][i][a] += w sum_P sum_b U[P][(i,x)][b] Lvv[P][a][b]   against the int8 planes of Lvv
-// ... with the half-transform fused (oz_k1_kernel): U never exists in fp64; the A planes of the contraction are written directly
+// ... with the half-transform fused (oz_k1_kernel): U never exists in fp64; the A planes of the contraction are written directly.
+// Block-weighted terms (XSF Delta A): the wide second virtual block [col0, nv) is emulated -- one half-transform per occupied
+// row block ib with the trial vectors scaled by w(ib, 1, :, :), each filling its rows of the A planes, then ONE contraction
+// against the planes of Lvv[col0:, :]; the narrow first block was done by the DMMA narrow pass of run_k.
 static int run_k_fused(xtd_engine* h, const KTermRec& k, int nvec) {
   cudaStream_t s = h->stream;
   Channel* ch = h->ch[k.ch];
   const long naux = h->naux[k.tensor];
   const int S = h->oz_slices, G = ch->oz_group;
+  const int col0 = ch->oz_col0[k.tensor];
+  struct RowPass { int i_lo, i_hi; BlockSplit bs; };
+  std::vector<RowPass> passes;
+  if (k.uniform) {
+    passes.push_back({0, ch->no, BlockSplit()});
+  } else {
+    const int o2off = ch->o_blocks.size() > 1 ? ch->o_blocks[1].first : ch->no;
+    const int v2off = ch->v_blocks.size() > 1 ? ch->v_blocks[1].first : ch->nv;
+    const int ab = col0 > 0 ? 1 : 0;
+    const int nib = ch->o_blocks.size() > 1 ? 2 : 1;
+    for (int ib = 0; ib < nib; ++ib) {
+      RowPass rp;
+      rp.i_lo = ib == 0 ? 0 : o2off;
+      rp.i_hi = (ib == 0 && nib == 2) ? o2off : ch->no;
+      rp.bs.o2off = o2off; rp.bs.v2off = v2off;       // scale_blocks_kernel on the transposed vectors zt[x][b][j], as in run_k
+      for (int j = 0; j < 2; ++j)
+        for (int b = 0; b < 2; ++b) rp.bs.w[j][b] = k.w[ib][ab][j < k.nob ? j : 0][b < k.nvb ? b : 0];
+      passes.push_back(rp);
+    }
+  }
+  const int npass = (int)passes.size();
   OzShape shA, shZt;
   shA.set(nvec * ch->no, OZ_BM, ch->nv);          // rows m = x no + i of the contraction's A operand
   shZt.set(ch->nv, OZ_BN, ch->no);                // zt[x][b][j]: one q-slice per trial vector
@@ -1266,7 +1299,8 @@ static int run_k_fused(xtd_engine* h, const KTermRec& k, int nvec) {
   int splits_max = std::min<long>(64, std::max<long>(1, cdiv(naux, G)));
   size_t w_doubles = (size_t)splits_max * shA.rows_pad * shB.rows_pad;
   while (splits_max > 1 && w_doubles * 4 > h->scratch_doubles) { splits_max /= 2; w_doubles = (size_t)splits_max * shA.rows_pad * shB.rows_pad; }
-  const size_t zt_doubles = shZt.slice_bytes(nvec, S) / 8 + 2 * (size_t)nvec * shZt.rows_pad + nvec + 256;
+  const size_t zt_one = shZt.slice_bytes(nvec, S) / 8 + (size_t)nvec * shZt.rows_pad + nvec + 128;
+  const size_t zt_doubles = npass * zt_one + (size_t)nvec * shZt.rows_pad + (k.uniform ? 0 : (size_t)nvec * ch->nv * ch->ldzt) + 256;
   const size_t a_per_p = shA.slice_bytes(1, S) / 8;
   const size_t per_p = a_per_p + (size_t)cdiv(shA.rows_pad, G) + 1;
   XTD_REQUIRE(h->scratch_doubles > w_doubles + zt_doubles + (size_t)G * per_p + 4096, XTD_ERR_NOMEM,
@@ -1280,36 +1314,54 @@ static int run_k_fused(xtd_engine* h, const KTermRec& k, int nvec) {
   double* cur = h->scratch;
   auto take = [&](size_t n) { double* p = cur; cur += (n + 31) & ~(size_t)31; return p; };
   double* W = take(w_doubles);
-  int8_t* ztS = reinterpret_cast<int8_t*>(take(shZt.slice_bytes(nvec, S) / 8));
-  double* ztScale = take((size_t)nvec * shZt.rows_pad);
   double* ztNorm = take((size_t)nvec * shZt.rows_pad);
-  double* zmax = take(nvec);
+  double* zts_tmp = k.uniform ? nullptr : take((size_t)nvec * ch->nv * ch->ldzt);
+  int8_t* ztS[2]; double* ztScale[2]; double* zmax[2];
+  for (int ip = 0; ip < npass; ++ip) {
+    ztS[ip] = reinterpret_cast<int8_t*>(take(shZt.slice_bytes(nvec, S) / 8));
+    ztScale[ip] = take((size_t)nvec * shZt.rows_pad);
+    zmax[ip] = take(nvec);
+  }
   int8_t* As = reinterpret_cast<int8_t*>(take((size_t)pc * a_per_p));
   double* so = take((size_t)cdiv(pc, G) * shA.rows_pad);
   {
     PhaseTimer t(h, XTD_T_K2_SLICE);
-    XTD_TRY(oz_slice(S, ztS, ztScale, shZt, h->ZT[k.ch], ch->ldzt, (long)ch->nv * ch->ldzt, nvec, 1, s));
-    oz_rownorm_kernel<<<dim3(shZt.rows_pad, nvec), 128, 0, s>>>(ztNorm, shZt.rows_pad, h->ZT[k.ch], ch->ldzt, (long)ch->nv * ch->ldzt, ch->nv, ch->no);
-    LAUNCH_CHECK();
-    oz_colmax_kernel<<<nvec, 256, 0, s>>>(zmax, ztNorm, shZt.rows_pad, ch->nv);
-    LAUNCH_CHECK();
+    for (int ip = 0; ip < npass; ++ip) {
+      const double* zt = h->ZT[k.ch];
+      if (!k.uniform) {
+        scale_blocks_kernel<<<dim3((unsigned)cdiv(ch->no, 128), ch->nv, nvec), 128, 0, s>>>(zts_tmp, h->ZT[k.ch], ch->ldzt, (long)ch->nv * ch->ldzt,
+                                                                                          ch->nv, ch->no, passes[ip].bs);
+        LAUNCH_CHECK();
+        zt = zts_tmp;
+      }
+      XTD_TRY(oz_slice(S, ztS[ip], ztScale[ip], shZt, zt, ch->ldzt, (long)ch->nv * ch->ldzt, nvec, 1, s));
+      oz_rownorm_kernel<<<dim3(shZt.rows_pad, nvec), 128, 0, s>>>(ztNorm, shZt.rows_pad, zt, ch->ldzt, (long)ch->nv * ch->ldzt, ch->nv, ch->no);
+      LAUNCH_CHECK();
+      oz_colmax_kernel<<<nvec, 256, 0, s>>>(zmax[ip], ztNorm, shZt.rows_pad, ch->nv);
+      LAUNCH_CHECK();
+    }
   }
   for (long P0 = 0; P0 < naux; P0 += pc) {
     const int pn = (int)std::min<long>(pc, naux - P0);
     const int ng = (int)cdiv(pn, G);
     {
       PhaseTimer t(h, XTD_T_K1);
-      oz_bound_scale_kernel<<<dim3((unsigned)cdiv(shA.rows_pad, 256), ng), 256, 0, s>>>(so, shA.rows_pad, ch->LooNorm[k.tensor] + (size_t)P0 * shL.rows_pad,
-                                                                                        shL.rows_pad, zmax, pn, G, nvec, ch->no);
-      LAUNCH_CHECK();
-      OzK1Params q;
-      q.A = ch->LooS[k.tensor] + shL.slice_bytes(P0, S); q.B = ztS;
-      q.sa = ch->LooScale[k.tensor] + (size_t)P0 * shL.rows_pad; q.sb = ztScale; q.so = so; q.out = As;
-      q.np = pn; q.nit = shL.nrt; q.nbt = shZt.nrt; q.nkb1 = shL.nkb; q.nvec = nvec; q.no = ch->no; q.group = G;
-      q.nmt2 = shA.nrt; q.nkb2 = shA.nkb; q.Mpad2 = shA.rows_pad;
-      q.ntiles = (long)pn * q.nit * nvec * q.nbt;
-      XTD_TRY(oz_k1(S, q, h->gemm.num_sms, s));
-      h->gemm.flops += 2.0 * pn * (double)ch->no * ch->no * ch->nv * nvec;
+      for (int ip = 0; ip < npass; ++ip) {
+        const RowPass& rp = passes[ip];
+        oz_bound_scale_kernel<<<dim3((unsigned)cdiv(shA.rows_pad, 256), ng), 256, 0, s>>>(so, shA.rows_pad, ch->LooNorm[k.tensor] + (size_t)P0 * shL.rows_pad,
+                                                                                          shL.rows_pad, zmax[ip], pn, G, nvec, ch->no, rp.i_lo, rp.i_hi);
+        LAUNCH_CHECK();
+        OzK1Params q;
+        q.A = ch->LooS[k.tensor] + shL.slice_bytes(P0, S); q.B = ztS[ip];
+        q.sa = ch->LooScale[k.tensor] + (size_t)P0 * shL.rows_pad; q.sb = ztScale[ip]; q.so = so; q.out = As;
+        q.np = pn; q.nit = shL.nrt; q.nbt = shZt.nrt; q.nkb1 = shL.nkb; q.nvec = nvec; q.no = ch->no; q.group = G;
+        q.nmt2 = shA.nrt; q.nkb2 = shA.nkb; q.Mpad2 = shA.rows_pad;
+        q.i_lo = rp.i_lo; q.i_hi = rp.i_hi;
+        q.it0 = rp.i_lo / OZ_BM; q.nit_run = (rp.i_hi - 1) / OZ_BM - q.it0 + 1;
+        q.ntiles = (long)pn * q.nit_run * nvec * q.nbt;
+        XTD_TRY(oz_k1(S, q, h->gemm.num_sms, s));
+        h->gemm.flops += 2.0 * pn * (double)(rp.i_hi - rp.i_lo) * ch->no * ch->nv * nvec;
+      }
     }
     {
       PhaseTimer t(h, XTD_T_K2);
@@ -1318,12 +1370,12 @@ static int run_k_fused(xtd_engine* h, const KTermRec& k, int nvec) {
       p.nmt = shA.nrt; p.nnt = shB.nrt; p.nkb = shA.nkb; p.nq = pn; p.group = G; p.b_q0 = (int)P0;
       p.Mpad = shA.rows_pad; p.Npad = shB.rows_pad;
       p.splits = std::min(splits_max, oz_choose_splits(tiles, ng, h->gemm.num_sms));
-      p.W = W; p.alpha = k.w[0][0][0][0];
+      p.W = W; p.alpha = k.uniform ? k.w[0][0][0][0] : 1.0;
       XTD_TRY(oz_gemm(S, p, s));
-      const int M = nvec * ch->no, N = ch->nv;
+      const int M = nvec * ch->no, N = ch->nv - col0;
       const long nblk = cdiv((long)M * N, 256);
       reduce_splits_kernel<<<dim3((unsigned)(nblk > 4096 ? 4096 : nblk), 1), 256, 0, s>>>(
-          h->SIG + h->sig_base[k.ch], ch->ldz, 0, W, shB.rows_pad, 0, (long)shA.rows_pad * shB.rows_pad, p.splits, M, N, 1, 0, 0, 0);
+          h->SIG + h->sig_base[k.ch] + col0, ch->ldz, 0, W, shB.rows_pad, 0, (long)shA.rows_pad * shB.rows_pad, p.splits, M, N, 1, 0, 0, 0);
       LAUNCH_CHECK();
       h->gemm.flops += 2.0 * M * N * (double)ch->nv * pn;
     }
@@ -1332,7 +1384,7 @@ static int run_k_fused(xtd_engine* h, const KTermRec& k, int nvec) {
 }
 
 static int run_k_emulated(xtd_engine* h, const KTermRec& k, int nvec) {
-  if (h->oz_fuse) return run_k_fused(h, k, nvec);
+  if (h->oz_fuse || !k.uniform) return run_k_fused(h, k, nvec);
   cudaStream_t s = h->stream;
   Channel* ch = h->ch[k.ch];
   const long naux = h->naux[k.tensor];
@@ -1407,7 +1459,7 @@ static int run_k(xtd_engine* h, int nvec) {
     if (naux == 0) continue;
     const double* Loo = ch->Loo[k.tensor].p;
     const double* Lvv = ch->Lvv[k.tensor].p;
-    if (ch->use_oz[k.tensor]) {
+    if (ch->use_oz[k.tensor] && k.uniform) {
       XTD_TRY(run_k_emulated(h, k, nvec));
       continue;
     }
@@ -1476,6 +1528,13 @@ static int run_k(xtd_engine* h, int nvec) {
         }
       ab_first = 1;
       if (ch->tail_w > 0) ablks[1].second = ch->tail_start - v2off;     // the general pass stops at the last full 128-column tile
+    }
+    if (ch->use_oz[k.tensor]) {
+      // block weights on the emulated path: the narrow first block is done (or there is none); the wide block is emulated
+      XTD_REQUIRE(ab_first == (size_t)(ch->oz_col0[k.tensor] > 0 ? 1 : 0), XTD_ERR_NOMEM,
+                  "workspace too small for the narrow-output exchange pass that the emulated path relies on");
+      XTD_TRY(run_k_emulated(h, k, nvec));
+      continue;
     }
     for (size_t ab = ab_first; ab < ablks.size(); ++ab) {
       for (long P0 = 0; P0 < naux; P0 += pc) {

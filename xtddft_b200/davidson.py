@@ -107,27 +107,75 @@ class CudaVectors:
         _lib.check(self.lib.xtd_vec_scale(self._stream(), C.c_void_p(x.data_ptr()), x.stride(0), C.c_void_p(sd.data_ptr()), k, self.dim),
                    "xtd_vec_scale")
 
+    # ---- the same operations with the small coefficient arrays left on the device (no host round trip) -------------------
+    def precond_normalise(self, x, hdiag, shift: np.ndarray):
+        """x <- normalised (x / (hdiag - shift)): the squared norms never leave the device."""
+        k = len(shift)
+        sd = self._small(shift)
+        nrm = self.torch.empty(k, dtype=self.torch.float64, device=self.device)
+        _lib.check(self.lib.xtd_vec_precond(self._stream(), C.c_void_p(x.data_ptr()), x.stride(0), C.c_void_p(hdiag.data_ptr()),
+                                            C.c_void_p(sd.data_ptr()), C.c_void_p(nrm.data_ptr()), k, self.dim), "xtd_vec_precond")
+        inv = self.torch.rsqrt(self.torch.clamp_min(nrm, 1e-300))
+        _lib.check(self.lib.xtd_vec_scale(self._stream(), C.c_void_p(x.data_ptr()), x.stride(0), C.c_void_p(inv.data_ptr()), k, self.dim),
+                   "xtd_vec_scale")
+
+    def project_out(self, y, x):
+        """y <- y - (y x^T) x for orthonormal rows x: Gram block and update both on the device."""
+        m, k = y.shape[0], x.shape[0]
+        if m == 0 or k == 0:
+            return
+        g = self.torch.empty((m, k), dtype=self.torch.float64, device=self.device)
+        _lib.check(self.lib.xtd_vec_dots(self._stream(), C.c_void_p(g.data_ptr()), k, C.c_void_p(y.data_ptr()), y.stride(0), m,
+                                         C.c_void_p(x.data_ptr()), x.stride(0), k, self.dim), "xtd_vec_dots")
+        g.neg_()
+        _lib.check(self.lib.xtd_vec_lincomb(self._stream(), C.c_void_p(y.data_ptr()), y.stride(0), C.c_void_p(x.data_ptr()), x.stride(0),
+                                            C.c_void_p(g.data_ptr()), k, m, k, self.dim, 1.0), "xtd_vec_lincomb")
+
+    def transform(self, work, n_in: int, t: np.ndarray):
+        """work[:n_out] <- t[n_out, n_in] work[:n_in]  (through a scratch block: the kernel must not alias input and output)."""
+        n_out = t.shape[0]
+        if n_out == 0:
+            return
+        tmp = getattr(self, "_tmp", None)
+        if tmp is None or tmp.shape[0] < n_out:
+            tmp = self._tmp = self.alloc(max(n_out, 40))
+        self.lincomb(tmp[:n_out], work[:n_in], np.ascontiguousarray(t), 0.0)
+        work[:n_out].copy_(tmp[:n_out])
+
 
 # --------------------------------------------------------------------------------------------------------
 # helpers on the backend
 # --------------------------------------------------------------------------------------------------------
-def _orthonormalise(vb, work, n_in: int, lindep: float) -> int:
-    """Gram-Schmidt of work[:n_in] in place (classical, applied twice per vector: as stable as the reference's
-    modified Gram-Schmidt `_qr`); vectors whose remaining squared norm is <= lindep are dropped.  Returns the
-    number kept, compacted to the front of `work`."""
-    nv = 0
-    for i in range(n_in):
-        xi = work[i:i + 1]
-        if nv:
-            for _ in range(2):
-                d = vb.dots(xi, work[:nv])                  # [1, nv]
-                vb.lincomb(xi, work[:nv], -d, beta=1.0)
-        nrm2 = float(vb.dots(xi, xi)[0, 0])
+def _gs_coefficients(g: np.ndarray, lindep: float) -> np.ndarray:
+    """Gram-Schmidt carried out on the Gram matrix g = W W^T: rows t of the result give orthonormal vectors t W, taken in
+    order; a vector whose squared norm after projecting out the kept ones is <= lindep is dropped -- the criterion of the
+    reference's `_qr` (pyscf.lib.linalg_helper), evaluated on the host from ONE device Gram product."""
+    n = g.shape[0]
+    rows = []
+    for i in range(n):
+        c = np.zeros(n)
+        c[i] = 1.0
+        for t in rows:
+            c -= (c @ g @ t) * t
+        nrm2 = float(c @ g @ c)
         if nrm2 > lindep:
-            vb.scale(xi, np.array([1.0 / np.sqrt(nrm2)]))
-            if nv != i:
-                vb.copy(work[nv:nv + 1], xi)
-            nv += 1
+            rows.append(c / np.sqrt(nrm2))
+    return np.array(rows).reshape(len(rows), n)
+
+
+def _orthonormalise(vb, work, n_in: int, lindep: float, gram: Optional[np.ndarray] = None) -> int:
+    """Orthonormalise work[:n_in] in place, dropping dependent vectors; returns the number kept (compacted to the front).
+    Block form: Gram matrix on the device, Gram-Schmidt coefficients on the host, one linear combination -- applied twice
+    (the second pass restores orthogonality to rounding level, as CholQR2 / CGS2 do), i.e. two host round trips per call
+    instead of five per vector.  `gram`: the Gram matrix of work[:n_in] if the caller already has it."""
+    nv = n_in
+    for it in range(2):
+        if nv == 0:
+            return 0
+        g = gram if (it == 0 and gram is not None) else vb.dots(work[:nv], work[:nv])
+        t = _gs_coefficients(g, lindep)
+        vb.transform(work, nv, t)
+        nv = t.shape[0]
     return nv
 
 
@@ -171,6 +219,7 @@ def davidson1(aop: Callable, x0, precond, tol: float = 1e-12, max_cycle: int = 5
 
     heff = np.zeros((cap, cap))
     fresh_start = True
+    xt_orthonormal = False
     e = v = None
     conv = np.zeros(nroots, dtype=bool)
     space = 0
@@ -185,9 +234,10 @@ def davidson1(aop: Callable, x0, precond, tol: float = 1e-12, max_cycle: int = 5
             if nt == 0:
                 raise LinearDependencyError("Initial guess is empty or zero" if icyc == 0 else
                                             "No more linearly independent basis were found.")
-        elif nt > 1:
+        elif nt > 1 and not xt_orthonormal:
             nt = _orthonormalise(vb, xt, nt, lindep)
             nt = min(nt, 40)
+        xt_orthonormal = False
         if nt == 0:
             raise LinearDependencyError("No linearly independent basis found by the diagonalization solver.")
         if timing is not None:
@@ -201,13 +251,14 @@ def davidson1(aop: Callable, x0, precond, tol: float = 1e-12, max_cycle: int = 5
         vb.copy(ax[head:space], axt)
         elast, vlast, conv_last = e, v, conv
         # projected matrix: new rows/columns only (reference `_fill_heff_hermitian`)
-        d_new = vb.dots(xs[head:space], ax[head:space])          # [nt, nt]
+        d_all = vb.dots(xs[head:space], ax[:space])              # [nt, space]: one Gram product, one host round trip
+        d_new = d_all[:, head:]
         for ip in range(nt):
             for jp in range(ip):
                 heff[head + ip, head + jp] = heff[head + jp, head + ip] = d_new[ip, jp]
             heff[head + ip, head + ip] = d_new[ip, ip]
         if head:
-            d_old = vb.dots(xs[head:space], ax[:head])            # [nt, head]
+            d_old = d_all[:, :head]                               # [nt, head]
             heff[head:space, :head] = d_old
             heff[:head, head:space] = d_old.T
         w, v = scipy.linalg.eigh(heff[:space, :space])
@@ -244,27 +295,51 @@ def davidson1(aop: Callable, x0, precond, tol: float = 1e-12, max_cycle: int = 5
                 vb.copy(xt[dst:dst + 1], xt[k:k + 1])
         nt = len(keep)
         if nt:
-            if hdiag_dev is not None:
-                n2 = vb.precond(xt[:nt], hdiag_dev, np.full(nt, e[0] - level_shift))
+            fused = hdiag_dev is not None and hasattr(vb, "project_out")
+            if fused:
+                # precondition + normalise, project against the subspace: coefficients stay on the device
+                vb.precond_normalise(xt[:nt], hdiag_dev, np.full(nt, e[0] - level_shift))
+                vb.project_out(xt[:nt], xs[:space])
             else:
-                host = vb.to_host(xt[:nt])
-                x_host = vb.to_host(ritz[:nritz])
-                for dst, k in enumerate(keep):
-                    host[dst] = precond(host[dst], e[0], x_host[k])
-                vb.copy(xt[:nt], vb.from_host(host))
-                n2 = np.einsum("ij,ij->i", host, host)
-            vb.scale(xt[:nt], 1.0 / np.sqrt(n2))
-            # reference `_normalize_xt_`: subtract projections on all xs, keep if norm^2 > lindep, normalise
-            d = vb.dots(xt[:nt], xs[:space])
-            vb.lincomb(xt[:nt], xs[:space], -d, beta=1.0)
-            n2 = np.diag(vb.dots(xt[:nt], xt[:nt])).copy()
+                if hdiag_dev is not None:
+                    n2 = vb.precond(xt[:nt], hdiag_dev, np.full(nt, e[0] - level_shift))
+                else:
+                    host = vb.to_host(xt[:nt])
+                    x_host = vb.to_host(ritz[:nritz])
+                    for dst, k in enumerate(keep):
+                        host[dst] = precond(host[dst], e[0], x_host[k])
+                    vb.copy(xt[:nt], vb.from_host(host))
+                    n2 = np.einsum("ij,ij->i", host, host)
+                vb.scale(xt[:nt], 1.0 / np.sqrt(n2))
+                # reference `_normalize_xt_`: subtract projections on all xs, keep if norm^2 > lindep, normalise
+                d = vb.dots(xt[:nt], xs[:space])
+                vb.lincomb(xt[:nt], xs[:space], -d, beta=1.0)
+            # ONE Gram matrix serves the `_normalize_xt_` filter (its diagonal), the normalisation and the first
+            # Gram-Schmidt pass of the next cycle's `_qr` (rows / columns rescaled on the host)
+            gm = vb.dots(xt[:nt], xt[:nt])
+            n2 = np.diag(gm).copy()
             good = [k for k in range(nt) if n2[k] > lindep]
-            for dst, k in enumerate(good):
-                if dst != k:
-                    vb.copy(xt[dst:dst + 1], xt[k:k + 1])
-            nt = len(good)
-            if nt:
-                vb.scale(xt[:nt], 1.0 / np.sqrt(n2[good]))
+            if good:
+                inv = 1.0 / np.sqrt(n2[good])
+                sel = np.zeros((len(good), nt))
+                sel[np.arange(len(good)), good] = inv
+                if len(good) > 1 and not (space + nroots > max_space):
+                    gs = gm[np.ix_(good, good)] * inv[:, None] * inv[None, :]
+                    t1 = _gs_coefficients(gs, lindep)
+                    vb.transform(xt, nt, t1 @ sel)
+                    nt = t1.shape[0]
+                    if nt > 1:                                   # second pass (rounding-level orthogonality)
+                        g2 = vb.dots(xt[:nt], xt[:nt])
+                        t2 = _gs_coefficients(g2, lindep)
+                        vb.transform(xt, nt, t2)
+                        nt = t2.shape[0]
+                    nt = min(nt, 40)
+                    xt_orthonormal = True
+                else:
+                    vb.transform(xt, nt, sel)
+                    nt = len(good)
+            else:
+                nt = 0
         if nt == 0:
             conv = dx_norm < toloose
             break
