@@ -235,3 +235,33 @@ def test_engine_emulated_block_weighted_exchange(torch_cuda, monkeypatch, nc, no
     assert err < 1e-11, err
     assert np.abs(eng.hdiag() - hd).max() < 1e-10
     eng.close()
+
+
+@pytest.mark.parametrize("method", ["xtda", "sf_mcol"])
+@pytest.mark.parametrize("restricted", [True, False])
+def test_engine_emulated_split_gradient_grid_path(torch_cuda, monkeypatch, method, restricted):
+    """Value + gradient kernels (UKS GGA of X-TDA on two channels, multicollinear GGA spin flip) in the split-gradient form with
+    its four value GEMMs on the INT8 tensor cores (two of them batched over the trial vectors), two grid chunks with a ragged
+    last block; the streaming kernel between them is the fp64 one."""
+    from oracle import sigma as osig
+    from xtddft_b200 import plan as planmod
+    from xtddft_b200.engine import SigmaEngine
+    from xtddft_b200.synth import make_problem
+    monkeypatch.setenv("XTD_CHUNK_GRID", "16384")
+    p = make_problem(60, 10, 2, 48, 12, 20000, xctype="GGA", hyb=0.4, restricted=restricted, seed=430)
+    if method == "xtda":
+        vind, hd = osig.xtda_gen_vind(p)
+        plan = planmod.build_xtda_plan(p)
+    else:
+        vind, hd = osig.sf_gen_vind(p, -1, 1)
+        plan = planmod.build_sf_plan(p, isf=-1, method=1)
+    z = np.random.default_rng(4).standard_normal((3, hd.size))
+    ref = vind(z)
+    eng = SigmaEngine.from_problem(plan, p, workspace_bytes=1 << 30, max_nvec=4, exchange_slices=7)
+    got = eng.sigma(torch_cuda.from_numpy(z).cuda()).cpu().numpy()
+    st = eng.stats()
+    assert st["ms"]["xc_slice"] > 0, "the emulated grid path was not taken"
+    assert eng.last_chunks()[1] == 2
+    err = float(np.abs(got - ref).max() / max(1.0, np.abs(ref).max()))
+    assert err < 1e-11, err
+    eng.close()

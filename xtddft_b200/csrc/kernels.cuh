@@ -316,8 +316,9 @@ struct XcArgs2 {
   long g0;
   double* Y[2];            // [gb][ldY]          Y0 in, A out
   long ldY[2];
-  double* T[2];            // [nvec][gb][ldT]    T in, B out
+  double* T[2];            // [nvec][t_rows][ldT]    T in, B out   (t_rows >= gb: rows per trial vector, 0 = gb)
   long ldT[2];
+  long t_rows = 0;
   const double* phi[2];    // [4][ng][ldphi]
   long ldphi[2], phi_comp[2];
   const double* phiv[2];   // [4][ng][ldphiv]
@@ -395,7 +396,7 @@ __global__ void __launch_bounds__(512, 2) xc_weight_split_kernel(const XcArgs2 a
 #pragma unroll
           for (int k = 0; k < NVAR; ++k) rho[s * NVAR + k] += y.v[e] * sphi[s][k * nop[s] + o + e];
       }
-      const double* tb = a.T[s] + ((long)x * a.gb + g) * a.ldT[s];
+      const double* tb = a.T[s] + ((long)x * (a.t_rows ? a.t_rows : a.gb) + g) * a.ldT[s];
 #pragma unroll 2
       for (int v = lane * 2; v < nv; v += 64) {
         XcVec<2> t;
@@ -435,7 +436,7 @@ __global__ void __launch_bounds__(512, 2) xc_weight_split_kernel(const XcArgs2 a
         }
         out.store(yb + o);
       }
-      double* tb = a.T[s] + ((long)x * a.gb + g) * a.ldT[s];
+      double* tb = a.T[s] + ((long)x * (a.t_rows ? a.t_rows : a.gb) + g) * a.ldT[s];
 #pragma unroll 2
       for (int v = lane * 2; v < nv; v += 64) {
         double2 acc = make_double2(0.0, 0.0);

@@ -177,6 +177,9 @@ struct OzGemmParams {
   int Mpad, Npad, splits;
   double* W;            // partial tiles [splits][Mpad][Npad]
   double alpha;
+  // independent problems in one launch (blockIdx.y): per-batch offsets of the operands (bytes), scales and output (doubles)
+  int batches = 1;
+  long a_bstride = 0, b_bstride = 0, sa_bstride = 0, sb_bstride = 0, w_bstride = 0;
 };
 
 __device__ __forceinline__ void oz_mbar_init(uint64_t* bar, uint32_t count) {
@@ -268,6 +271,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const OzGemmPara
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int item = blockIdx.x;
+  const long zb = blockIdx.y;
   const int nt = item % p.nnt, mt = (item / p.nnt) % p.nmt, sp = item / (p.nnt * p.nmt);
   const int ngroups = (p.nq + p.group - 1) / p.group;
   const int g0 = (int)((long)ngroups * sp / p.splits), g1 = (int)((long)ngroups * (sp + 1) / p.splits);
@@ -301,8 +305,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const OzGemmPara
       for (int g = g0; g < g1; ++g) {
         const int q1 = min(p.nq, (g + 1) * p.group);
         for (int q = g * p.group; q < q1; ++q) {
-          const int8_t* a = p.A + (((long)q * p.nmt + mt) * p.nkb) * A_BYTES;
-          const int8_t* b = p.B + (((long)(q + p.b_q0) * p.nnt + nt) * p.nkb) * B_BYTES;
+          const int8_t* a = p.A + zb * p.a_bstride + (((long)q * p.nmt + mt) * p.nkb) * A_BYTES;
+          const int8_t* b = p.B + zb * p.b_bstride + (((long)(q + p.b_q0) * p.nnt + nt) * p.nkb) * B_BYTES;
           for (int kb = 0; kb < p.nkb; ++kb, ++it) {
             const int s = (int)(it % OZ_STAGES);
             const uint32_t ph = (uint32_t)((it / OZ_STAGES) & 1);
@@ -368,8 +372,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const OzGemmPara
     for (int g = g0; g < g1; ++g) {
       oz_mbar_wait(tmem_full, (uint32_t)((g - g0) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const double sa = p.sa[(long)g * p.Mpad + mt * OZ_BM + row];
-      const double* sb = p.sb + (long)(g + p.b_q0 / p.group) * p.Npad + nt * OZ_BN;
+      const double sa = p.sa[zb * p.sa_bstride + (long)g * p.Mpad + mt * OZ_BM + row];
+      const double* sb = p.sb + zb * p.sb_bstride + (long)(g + p.b_q0 / p.group) * p.Npad + nt * OZ_BN;
 #pragma unroll
       for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
         double v[16];
@@ -389,7 +393,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const OzGemmPara
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       oz_mbar_arrive(tmem_empty);
     }
-    double* w = p.W + ((long)sp * p.Mpad + mt * OZ_BM + row) * p.Npad + nt * OZ_BN;
+    double* w = p.W + zb * p.w_bstride + ((long)sp * p.Mpad + mt * OZ_BM + row) * p.Npad + nt * OZ_BN;
 #pragma unroll
     for (int c = 0; c < OZ_BN; c += 2) *reinterpret_cast<double2*>(w + c) = make_double2(p.alpha * acc[c], p.alpha * acc[c + 1]);
   }
@@ -752,7 +756,7 @@ inline int oz_gemm_launch_cn(const OzGemmParams& p, cudaStream_t st) {
     attr_set[dev & 63] = true;
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(p.nmt * p.nnt * p.splits));
+  cfg.gridDim = dim3((unsigned)(p.nmt * p.nnt * p.splits), (unsigned)p.batches);
   cfg.blockDim = dim3(OZ_THREADS);
   cfg.dynamicSmemBytes = oz_gemm_smem(S);
   cfg.stream = st;

@@ -80,6 +80,13 @@ struct Channel {
   int8_t *phivF = nullptr, *phivB = nullptr;
   double *phivFs = nullptr, *phivBs = nullptr;
   OzShape ozPF, ozPB;
+  // value + gradient kernels in the split-gradient form: the four value GEMMs are emulated (planes of the value component of phiv
+  // as above, and of the value component of phi: rows = grid points, K = occupied index / rows = occupied index, K = grid blocks);
+  // the fp64 arrays stay (the streaming kernel reads the gradient components)
+  bool xc_oz_split = false;
+  int8_t *phiF = nullptr, *phiB = nullptr;
+  double *phiFs = nullptr, *phiBs = nullptr;
+  OzShape ozOF, ozOB;
   DevBuf phi;                       // occupied values on the grid  [nvar_eff][ng][ldphi]
   long ldphi = 0;
   DevBuf phiv;                      // virtual values on the grid   [nvar_eff][ng][ldphiv]
@@ -90,6 +97,7 @@ struct Channel {
   long g_nnz = 0;
 };
 
+constexpr long XC_SPLIT_SMEM_MAX = 200 * 1024;   // shared memory of the split-gradient streaming kernel (MO values of one point)
 constexpr int OZ_XC_KQ = 8192;   // grid points per int32 accumulation group of the backward grid GEMM (8192 * S * 2^14 < 2^31)
 constexpr int NARROW_MAX = 16;   // widest first virtual block that takes the narrow-output exchange pass
 
@@ -363,8 +371,14 @@ int grid_commit(xtd_engine* h) {
       e.N = c->nv;
       e.C = c->phiv.p; e.ldc = c->ldphiv; e.c_batch_stride = h->ng * c->ldphiv;
       XTD_TRY(gemm(h->gemm, e, s));
-      if (h->oz_slices > 0 && h->nvar_eff == 1) {
-        // both operand roles of phiv as int8 planes; the fp64 array is dropped
+      bool split_oz = false;
+      if (h->oz_slices > 0 && h->nvar_eff == 4 && !h->tau && !(getenv("XTD_XC_SPLIT") && atoi(getenv("XTD_XC_SPLIT")) == 0)) {
+        int no2[2] = {0, 0}, nv2[2] = {0, 0};
+        for (size_t k = 0; k < h->ch.size(); ++k) { no2[k] = h->ch[k]->no; nv2[k] = h->ch[k]->nv; }
+        split_oz = xc_split_smem_doubles((int)h->ch.size(), no2, nv2) * 8 <= XC_SPLIT_SMEM_MAX;
+      }
+      if (h->oz_slices > 0 && (h->nvar_eff == 1 || split_oz)) {
+        // both operand roles of (the value component of) phiv as int8 planes
         const int S = h->oz_slices;
         c->ozPF.set((int)h->ng, OZ_BM, c->nv);
         c->ozPB.set(c->nv, OZ_BN, OZ_XC_KQ);
@@ -376,9 +390,24 @@ int grid_commit(xtd_engine* h) {
         XTD_CUDA(cudaMalloc((void**)&c->phivBs, c->ozPB.scale_doubles(nqg, 1) * 8));
         XTD_TRY(oz_slice(S, c->phivF, c->phivFs, c->ozPF, c->phiv.p, c->ldphiv, 0, 1, 1, s));
         XTD_TRY(oz_slice(S, c->phivB, c->phivBs, c->ozPB, c->phiv.p, c->ldphiv, (long)OZ_XC_KQ * c->ldphiv, (int)nqg, 1, s, true, h->ng));
+        if (split_oz) {
+          // ... and of the value component of phi (occupied side of the split-gradient form)
+          c->ozOF.set((int)h->ng, OZ_BM, c->no);
+          c->ozOB.set(c->no, OZ_BM, OZ_XC_KQ);
+          XTD_CUDA(cudaMalloc((void**)&c->phiF, c->ozOF.slice_bytes(1, S)));
+          XTD_CUDA(cudaMalloc((void**)&c->phiFs, c->ozOF.scale_doubles(1, 1) * 8));
+          XTD_CUDA(cudaMalloc((void**)&c->phiB, c->ozOB.slice_bytes(nqg, S)));
+          XTD_CUDA(cudaMalloc((void**)&c->phiBs, c->ozOB.scale_doubles(nqg, 1) * 8));
+          XTD_TRY(oz_slice(S, c->phiF, c->phiFs, c->ozOF, c->phi.p, c->ldphi, 0, 1, 1, s));
+          XTD_TRY(oz_slice(S, c->phiB, c->phiBs, c->ozOB, c->phi.p, c->ldphi, (long)OZ_XC_KQ * c->ldphi, (int)nqg, 1, s, true, h->ng));
+        }
         XTD_CUDA(cudaStreamSynchronize(s));
-        c->phiv.release();
-        c->xc_oz = true;
+        if (split_oz) {
+          c->xc_oz_split = true;
+        } else {
+          c->phiv.release();                 // one component: the fp64 array is not read again
+          c->xc_oz = true;
+        }
       }
     }
     if (h->tau) XTD_REQUIRE(h->nvar == 4, XTD_ERR_ARG, "meta-GGA kernels need value + gradient AO components (nvar = 4)");
@@ -459,6 +488,10 @@ int xtd_destroy(xtd_handle h) {
       if (c->LooScale[t]) cudaFree(c->LooScale[t]);
       if (c->LooNorm[t]) cudaFree(c->LooNorm[t]);
     }
+    if (c->phiF) cudaFree(c->phiF);
+    if (c->phiB) cudaFree(c->phiB);
+    if (c->phiFs) cudaFree(c->phiFs);
+    if (c->phiBs) cudaFree(c->phiBs);
     if (c->phivF) cudaFree(c->phivF);
     if (c->phivB) cudaFree(c->phivB);
     if (c->phivFs) cudaFree(c->phivFs);
@@ -981,7 +1014,6 @@ static void launch_xc(const XcArgs& a, cudaStream_t s) {
   else xc_weight_kernel<NVAR, KIND, XU, 1, TAU><<<grid, 256, 0, s>>>(a);
 }
 
-constexpr long XC_SPLIT_SMEM_MAX = 200 * 1024;
 
 template <int KIND>
 static int launch_xc_split(const XcArgs2& a, cudaStream_t s) {
@@ -1011,6 +1043,7 @@ static int launch_xc_split(const XcArgs2& a, cudaStream_t s) {
 // a tile or the problem is tiny.
 static bool xc_use_split(const xtd_engine* h, int nvec) {
   if (h->nvar_eff != 4 || h->tau) return false;      // tau needs the gradient of both orbitals: four-component form
+  if (!h->ch.empty() && h->ch[0]->xc_oz_split) return true;     // the emulated grid path always takes the split-gradient form
   {
     int no[2] = {0, 0}, nv[2] = {0, 0};
     for (size_t c = 0; c < h->ch.size(); ++c) { no[c] = h->ch[c]->no; nv[c] = h->ch[c]->nv; }
@@ -1133,8 +1166,161 @@ static int run_xc_emulated(xtd_engine* h, int nvec) {
   return XTD_OK;
 }
 
+// Value + gradient kernels (UKS GGA of X-TDA, multicollinear GGA) in the split-gradient form with its four value GEMMs emulated:
+//   F1  Y0[g][(x,o)] = sum_v phiv0[g][v] Z[(x,o)][v]            F2  T[x][g][v] = sum_o phi0[g][o] Z[x][o][v]      (batched over x)
+//   streaming kernel (unchanged): rho from Y0, T and the gradient components; A -> Y0, B -> T in place
+//   B1  SIG[(x,o)][v] += sum_g A[g][(x,o)] phiv0[g][v]           B2  SIG[x][o][v] += sum_g phi0[g][o] B[x][g][v]   (batched over x)
+static int run_xc_split_emulated(xtd_engine* h, int nvec) {
+  cudaStream_t s = h->stream;
+  const int nch = (int)h->ch.size();
+  const int S = h->oz_slices;
+  OzShape shZ[2], shA[2], shZt[2], shBt[2];
+  size_t per_g = 0, fixed = 0, w_doubles = 0;
+  const int splits_max = 8;
+  for (int c = 0; c < nch; ++c) {
+    Channel* ch = h->ch[c];
+    shZ[c].set(nvec * ch->no, OZ_BN, ch->nv);        // F1 B operand: rows (x,o), K = v
+    shA[c].set(nvec * ch->no, OZ_BM, OZ_XC_KQ);      // B1 A operand: rows (x,o), K = grid block
+    shZt[c].set(ch->nv, OZ_BN, ch->no);              // F2 B operand: rows v, K = o, one q-slice (batch) per x
+    shBt[c].set(ch->nv, OZ_BN, OZ_XC_KQ);            // B2 B operand: rows v, K = grid block, one batch per x
+    per_g += (size_t)shZ[c].rows_pad + (size_t)nvec * shZt[c].rows_pad + (size_t)shA[c].rows_pad * S / 8 + (size_t)nvec * shBt[c].rows_pad * S / 8 + 2;
+    fixed += shZ[c].slice_bytes(1, S) / 8 + shZ[c].rows_pad + shZt[c].slice_bytes(nvec, S) / 8 + (size_t)nvec * shZt[c].rows_pad + 256;
+    fixed += (size_t)(65536 / OZ_XC_KQ) * ((size_t)shA[c].rows_pad + (size_t)nvec * shBt[c].rows_pad) + 256;
+    w_doubles = std::max(w_doubles, (size_t)splits_max * shA[c].rows_pad * ch->ozPB.rows_pad);
+    w_doubles = std::max(w_doubles, (size_t)splits_max * nvec * ch->ozOB.rows_pad * shBt[c].rows_pad);
+  }
+  fixed += w_doubles + 8192;
+  XTD_REQUIRE(h->scratch_doubles > fixed + per_g * (OZ_XC_KQ + 128), XTD_ERR_NOMEM, "workspace too small for one block of the emulated grid path");
+  long GB = (long)((h->scratch_doubles - fixed) / per_g) - 128;
+  GB = std::min<long>(GB, 1 << 16);
+  if (h->max_gb > 0) GB = std::min<long>(GB, std::max<long>(h->max_gb, OZ_XC_KQ));
+  GB = GB / OZ_XC_KQ * OZ_XC_KQ;
+  h->last_grid_chunks = cdiv(h->ng, GB);
+  double* cur = h->scratch;
+  auto take = [&](size_t n) { double* p = cur; cur += (n + 31) & ~(size_t)31; return p; };
+  double* W = take(w_doubles);
+  const long gbmax = round_up(std::min<long>(GB, h->ng), 128);
+  const long nqmax = cdiv(gbmax, OZ_XC_KQ);
+  int8_t *zS[2], *ztS[2], *aS[2], *bS[2];
+  double *zsc[2], *ztsc[2], *Y[2], *T[2], *asc[2], *bsc[2];
+  for (int c = 0; c < nch; ++c) {
+    zS[c] = reinterpret_cast<int8_t*>(take(shZ[c].slice_bytes(1, S) / 8));
+    zsc[c] = take(shZ[c].rows_pad);
+    ztS[c] = reinterpret_cast<int8_t*>(take(shZt[c].slice_bytes(nvec, S) / 8));
+    ztsc[c] = take((size_t)nvec * shZt[c].rows_pad);
+    Y[c] = take((size_t)gbmax * shZ[c].rows_pad);
+    T[c] = take((size_t)nvec * gbmax * shZt[c].rows_pad);
+    aS[c] = reinterpret_cast<int8_t*>(take((size_t)nqmax * shA[c].slice_bytes(1, S) / 8));
+    asc[c] = take((size_t)nqmax * shA[c].rows_pad);
+    bS[c] = reinterpret_cast<int8_t*>(take((size_t)nvec * nqmax * shBt[c].slice_bytes(1, S) / 8));
+    bsc[c] = take((size_t)nvec * nqmax * shBt[c].rows_pad);
+  }
+  {
+    PhaseTimer t(h, XTD_T_XC_SLICE);
+    for (int c = 0; c < nch; ++c) {
+      Channel* ch = h->ch[c];
+      XTD_TRY(oz_slice(S, zS[c], zsc[c], shZ[c], h->Z[c], ch->ldz, 0, 1, 1, s));
+      XTD_TRY(oz_slice(S, ztS[c], ztsc[c], shZt[c], h->ZT[c], ch->ldzt, (long)ch->nv * ch->ldzt, nvec, 1, s));
+    }
+  }
+  for (long g0 = 0; g0 < h->ng; g0 += GB) {
+    const int gb = (int)std::min<long>(GB, h->ng - g0);
+    const int nmt_g = (int)cdiv(gb, OZ_BM);
+    const long mpad_g = (long)nmt_g * OZ_BM;
+    const int nqc = (int)cdiv(gb, OZ_XC_KQ);
+    {
+      PhaseTimer t(h, XTD_T_XC_GEMM);
+      for (int c = 0; c < nch; ++c) {
+        Channel* ch = h->ch[c];
+        OzGemmParams p;                       // F1
+        p.A = ch->phivF + (size_t)(g0 / OZ_BM) * ch->ozPF.nkb * S * (OZ_BM * OZ_KB);
+        p.B = zS[c]; p.sa = ch->phivFs + g0; p.sb = zsc[c];
+        p.nmt = nmt_g; p.nnt = shZ[c].nrt; p.nkb = ch->ozPF.nkb; p.nq = 1; p.group = 1; p.b_q0 = 0;
+        p.Mpad = (int)mpad_g; p.Npad = shZ[c].rows_pad; p.splits = 1; p.W = Y[c]; p.alpha = 1.0;
+        XTD_TRY(oz_gemm(S, p, s));
+        OzGemmParams q;                       // F2, one batch per trial vector
+        q.A = ch->phiF + (size_t)(g0 / OZ_BM) * ch->ozOF.nkb * S * (OZ_BM * OZ_KB);
+        q.B = ztS[c]; q.sa = ch->phiFs + g0; q.sb = ztsc[c];
+        q.nmt = nmt_g; q.nnt = shZt[c].nrt; q.nkb = ch->ozOF.nkb; q.nq = 1; q.group = 1; q.b_q0 = 0;
+        q.Mpad = (int)mpad_g; q.Npad = shZt[c].rows_pad; q.splits = 1; q.W = T[c]; q.alpha = 1.0;
+        q.batches = nvec; q.b_bstride = (long)shZt[c].slice_bytes(1, S); q.sb_bstride = shZt[c].rows_pad;
+        q.w_bstride = mpad_g * shZt[c].rows_pad;
+        XTD_TRY(oz_gemm(S, q, s));
+        h->gemm.flops += 4.0 * gb * (double)(nvec * ch->no) * ch->nv;
+      }
+    }
+    {
+      PhaseTimer t(h, XTD_T_XC_STREAM);
+      XcArgs2 a;
+      a.nch = nch; a.nvec = nvec; a.gb = gb; a.g0 = g0; a.t_rows = mpad_g;
+      for (int c = 0; c < 2; ++c) {
+        const bool on = c < nch;
+        Channel* ch = on ? h->ch[c] : nullptr;
+        a.Y[c] = on ? Y[c] : nullptr; a.ldY[c] = on ? shZ[c].rows_pad : 0;
+        a.T[c] = on ? T[c] : nullptr; a.ldT[c] = on ? shZt[c].rows_pad : 0;
+        a.phi[c] = on ? ch->phi.p : nullptr; a.ldphi[c] = on ? ch->ldphi : 0; a.phi_comp[c] = on ? h->ng * ch->ldphi : 0;
+        a.phiv[c] = on ? ch->phiv.p : nullptr; a.ldphiv[c] = on ? ch->ldphiv : 0; a.phiv_comp[c] = on ? h->ng * ch->ldphiv : 0;
+        a.no[c] = on ? ch->no : 0; a.nv[c] = on ? ch->nv : 0;
+      }
+      a.wf = h->wf.p;
+      if (h->fxc_kind == XTD_FXC_UKS) XTD_TRY(launch_xc_split<XC_KIND_UKS>(a, s));
+      else XTD_TRY(launch_xc_split<XC_KIND_MCOL>(a, s));
+      LAUNCH_CHECK();
+    }
+    {
+      PhaseTimer t(h, XTD_T_XC_SLICE);
+      for (int c = 0; c < nch; ++c) {
+        // A planes of B1 from Y (now holding A[g][(x,o)]); B planes of B2 from T (now holding B[x][g][v]), one batch per x
+        XTD_TRY(oz_slice(S, aS[c], asc[c], shA[c], Y[c], shZ[c].rows_pad, (long)OZ_XC_KQ * shZ[c].rows_pad, nqc, 1, s, true, gb));
+        for (int x = 0; x < nvec; ++x)
+          XTD_TRY(oz_slice(S, bS[c] + (size_t)x * nqmax * shBt[c].slice_bytes(1, S), bsc[c] + (size_t)x * nqmax * shBt[c].rows_pad, shBt[c],
+                           T[c] + (size_t)x * mpad_g * shZt[c].rows_pad, shZt[c].rows_pad, (long)OZ_XC_KQ * shZt[c].rows_pad, nqc, 1, s, true, gb));
+      }
+    }
+    {
+      PhaseTimer t(h, XTD_T_XC_GEMM);
+      for (int c = 0; c < nch; ++c) {
+        Channel* ch = h->ch[c];
+        const int M = nvec * ch->no, N = ch->nv;
+        OzGemmParams p;                       // B1
+        p.A = aS[c]; p.B = ch->phivB; p.sa = asc[c]; p.sb = ch->phivBs;
+        p.nmt = shA[c].nrt; p.nnt = ch->ozPB.nrt; p.nkb = shA[c].nkb; p.nq = nqc; p.group = 1; p.b_q0 = (int)(g0 / OZ_XC_KQ);
+        p.Mpad = shA[c].rows_pad; p.Npad = ch->ozPB.rows_pad;
+        p.splits = std::min(splits_max, oz_choose_splits(p.nmt * p.nnt, nqc, h->gemm.num_sms));
+        p.W = W; p.alpha = 1.0;
+        XTD_TRY(oz_gemm(S, p, s));
+        long nblk = cdiv((long)M * N, 256);
+        reduce_splits_kernel<<<dim3((unsigned)(nblk > 4096 ? 4096 : nblk), 1), 256, 0, s>>>(
+            h->SIG + h->sig_base[c], ch->ldz, 0, W, ch->ozPB.rows_pad, 0, (long)shA[c].rows_pad * ch->ozPB.rows_pad, p.splits, M, N, 1, 0, 0, 0);
+        LAUNCH_CHECK();
+        OzGemmParams q;                       // B2, one batch per trial vector: A = planes of phi0^T (shared), B = planes of B[x]^T
+        q.A = ch->phiB; q.B = bS[c]; q.sa = ch->phiBs; q.sb = bsc[c];
+        q.nmt = ch->ozOB.nrt; q.nnt = shBt[c].nrt; q.nkb = shBt[c].nkb; q.nq = nqc; q.group = 1; q.b_q0 = 0;
+        q.Mpad = ch->ozOB.rows_pad; q.Npad = shBt[c].rows_pad;
+        q.splits = std::min(splits_max, oz_choose_splits(q.nmt * q.nnt * nvec, nqc, h->gemm.num_sms));
+        q.W = W; q.alpha = 1.0;
+        q.batches = nvec;
+        q.b_bstride = (long)nqmax * shBt[c].slice_bytes(1, S); q.sb_bstride = (long)nqmax * shBt[c].rows_pad;
+        q.w_bstride = (long)q.splits * q.Mpad * q.Npad;
+        // the A operand / its scales start at this chunk's first grid block for every batch
+        q.A = ch->phiB + (size_t)(g0 / OZ_XC_KQ) * ch->ozOB.slice_bytes(1, S);
+        q.sa = ch->phiBs + (size_t)(g0 / OZ_XC_KQ) * ch->ozOB.rows_pad;
+        XTD_TRY(oz_gemm(S, q, s));
+        nblk = cdiv((long)ch->no * N, 256);
+        reduce_splits_kernel<<<dim3((unsigned)(nblk > 4096 ? 4096 : nblk), nvec), 256, 0, s>>>(
+            h->SIG + h->sig_base[c], ch->ldz, (long)ch->no * ch->ldz, W, shBt[c].rows_pad, q.w_bstride, (long)q.Mpad * q.Npad, q.splits, ch->no, N,
+            1, 0, 0, 0);
+        LAUNCH_CHECK();
+        h->gemm.flops += 4.0 * gb * (double)M * N;
+      }
+    }
+  }
+  return XTD_OK;
+}
+
 static int run_xc(xtd_engine* h, int nvec) {
   if (h->ch[0]->xc_oz) return run_xc_emulated(h, nvec);
+  if (h->ch[0]->xc_oz_split) return run_xc_split_emulated(h, nvec);
   cudaStream_t s = h->stream;
   const int nch = (int)h->ch.size();
   const int nve = h->nvar_eff;
@@ -1734,7 +1920,7 @@ int xtd_sigma_partial(xtd_handle h, int nvec, const double* z_dev) {
       pack_kernel<<<dim3((unsigned)cdiv(nrows, 256), nvec), 256, 0, s>>>(h->Z[c], ch->ldz, (long)ch->no * ch->ldz, ch->nv, nrows, ch->g_indptr,
                                                                          ch->g_cols, ch->g_vals, z_dev, h->ext_dim, nvec);
       LAUNCH_CHECK();
-      if (!h->kterms.empty()) {
+      if (!h->kterms.empty() || ch->xc_oz_split) {
         XTD_CUDA(cudaMemsetAsync(h->ZT[c], 0, (size_t)nvec * ch->nv * ch->ldzt * 8, s));
         transpose_kernel<<<dim3((unsigned)cdiv(ch->nv, 32), (unsigned)cdiv(ch->no, 32), nvec), dim3(32, 8), 0, s>>>(
             h->ZT[c], ch->ldzt, (long)ch->nv * ch->ldzt, h->Z[c], ch->ldz, (long)ch->no * ch->ldz, ch->no, ch->nv);
