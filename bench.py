@@ -295,10 +295,14 @@ def compact_config_record(cfg: int, steps: int = 2, warmup: int = 3, cpu_budget_
             rec["dominant_phase_share"] = phase[top] / max(sum(phase.values()), 1e-12)
             if pflops.get(top, 0.0) > 0:
                 rec["dominant_phase_fp64_equiv_tflops"] = pflops[top] / (phase[top] * 1e-3) / 1e12
+        warm = eng.ext_dim < 50000
+        if warm:          # small problems: one untimed solve first (module loading, graph capture of every call shape)
+            davidson_for_engine(eng, dp.nroots, dp.method)
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
         conv, e, x, info = davidson_for_engine(eng, dp.nroots, dp.method)
         torch.cuda.synchronize()
-        rec["davidson"] = {"time_to_roots_s": time.perf_counter() - t0, "nroots": dp.nroots, "converged": bool(np.all(conv)),
+        rec["davidson"] = {"time_to_roots_s": time.perf_counter() - t0, "nroots": dp.nroots, "converged": bool(np.all(conv)), "warm": warm,
                            "cycles": int(info[0]), "sigma_vectors": int(info[1]), "lowest_root_ha": float(e[0])}
     finally:
         eng.close()
@@ -430,14 +434,17 @@ def main():
     if args.davidson:
         try:
             from xtddft_b200.davidson import davidson_for_engine
+            warm = dim < 50000
+            if warm:      # small problems: the first solve pays one-off costs (CUDA module loading, graph capture of every call shape)
+                davidson_for_engine(eng, dp.nroots, dp.method)
             barrier()
             t0 = time.perf_counter()
             tm = {}
-            conv, e, x, info = davidson_for_engine(eng, dp.nroots, dp.method, timing=tm)
+            conv, e, x, info = davidson_for_engine(eng, dp.nroots, dp.method, timing=None if warm else tm)
             torch.cuda.synchronize()
             dav = {"time_to_roots_s": time.perf_counter() - t0, "nroots": dp.nroots, "converged": bool(np.all(conv)),
                    "cycles": int(info[0]), "sigma_vectors": int(info[1]), "lowest_root_ha": float(e[0]),
-                   "seconds_in_sigma": tm.get("sigma_s"), "tolerances": "reference SF_TDA.py:392-395 / XTDA.py:775-777 / XSF_TDA.py:1467-1470"}
+                   "seconds_in_sigma": tm.get("sigma_s"), "warm": warm, "tolerances": "reference SF_TDA.py:392-395 / XTDA.py:775-777 / XSF_TDA.py:1467-1470"}
         except ImportError:
             dav = None
 

@@ -69,6 +69,12 @@ int xtd_set_jmix(xtd_handle h, const double* mix_host, int n);
  * planes only.  Call before xtd_df_begin; with it every xtd_df_add chunk but the last must hold a multiple of the scale group
  * (at most 4 aux functions; the Python engine carries ragged remainders over). */
 int xtd_set_exchange_emulation(xtd_handle h, int slices);
+/* ROHF-form Fock matrices of the spin-adaptation terms (XTDA.py:607-613, XSF_TDA.py:1103-1111: `scf.ROHF(mol).get_veff(dm)`): only
+ * their spin difference F_beta - F_alpha = K[D_open] enters the sigma build (h and J cancel).  Declare the open-shell MOs of `spin`
+ * before streaming tensor 0; every xtd_df_add then accumulates kopen[p][q] += sum_P sum_u L^P_pu L^P_qu (MO basis, all nmo x nmo,
+ * this rank's aux functions; sum over ranks with one all-reduce).  xtd_get_kopen copies it to out_dev[nmo][ld]. */
+int xtd_set_open_orbitals(xtd_handle h, int spin, const int* open_idx_host, int n_open);
+int xtd_get_kopen(xtd_handle h, double* out_dev, long ld);
 int xtd_df_begin(xtd_handle h, int tensor, long naux_local);
 int xtd_df_add(xtd_handle h, int tensor, const double* l_dev, long np, long ld_row, long stride_p, int packed);
 int xtd_jblock_diag(xtd_handle h, int jb, double* out_dev);   /* out[nr*nc] = sum_P L_ia^2 */

@@ -41,3 +41,12 @@ def mo_eri(cderi, c1, c2, c3, c4):
     l12 = np.einsum("Pij,ip,jq->Ppq", cderi, c1, c2, optimize=True)
     l34 = np.einsum("Pij,ip,jq->Ppq", cderi, c3, c4, optimize=True)
     return np.einsum("Ppq,Prs->pqrs", l12, l34, optimize=True)
+
+
+def rohf_fock_difference(cderi, mo_coeff, open_idx):
+    """F_beta - F_alpha of the ROHF-form Fock matrices in the MO basis.  The reference builds both with
+    `scf.ROHF(mol).get_veff(mol, dm)` (xtddft/XTDA.py:607-613, xtddft/XSF_TDA.py:1103-1111) and uses only their difference:
+    h and J[D_alpha + D_beta] cancel, -K[D_beta] + K[D_alpha] = K[D_open], K[D]_pq = sum_P sum_u L^P_pu L^P_qu."""
+    c = np.asarray(mo_coeff)
+    d_open = c[:, open_idx] @ c[:, open_idx].T
+    return c.T @ get_k(cderi, d_open) @ c

@@ -182,3 +182,36 @@ def test_mcol_contraction_fixture(torch_cuda, golden_dir, name, xct, seed):
     assert _rel(got, grid_ref) < RTOL
     full.close()
     nogrid.close()
+
+
+def test_rohf_fock_difference_on_device(torch_cuda):
+    """Setup-stage piece: F_beta^HF - F_alpha^HF = K[D_open] accumulated from the streamed tensor in the MO
+    basis, against the oracle's `get_k` on the open-shell density; then the full flow -- a ROKS problem WITHOUT fock_hf gets its
+    spin-adaptation couplings from the device and must give the sigma vectors of the same problem with fock_hf = [0, K] supplied."""
+    from oracle import jk
+    from xtddft_b200.engine import SigmaEngine
+    p = make_problem(40, 8, 3, 29, 21, 200, xctype="LDA", hyb=0.3, seed=340)
+    kref = jk.rohf_fock_difference(p.cderi, p.mo_coeff[0], np.arange(p.nc, p.nc + p.no))
+    p.fock_hf = np.stack([np.zeros_like(kref), kref])
+    builder = lambda q: planmod.build_sf_plan(q, isf=-1, method=0, sa=3, layout=planmod.LAYOUT_BLOCK, remove=True, hdiag_kind="xsf")
+    vind, hd = osig.xsf_gen_vind(p, sa=3, method=0, remove=True)
+    z = np.random.default_rng(8).standard_normal((3, hd.size))
+    ref = vind(z)
+    import copy
+    q = copy.copy(p)
+    q.fock_hf = None
+    for world in (1, 2):
+        q.fock_hf = None
+        parts = []
+        for r in range(world):
+            eng = SigmaEngine.from_problem(builder(p), q if world == 1 else copy.copy(q), workspace_bytes=256 << 20, max_nvec=4, df_chunk=8,
+                                           plan_builder=builder, rank=r, world=world)
+            if world == 1:
+                assert np.abs(q.fock_hf[1] - kref).max() < 1e-11 * np.abs(kref).max()
+                assert _rel(eng.sigma_host(z), ref) < RTOL
+                assert np.abs(eng.hdiag() - hd).max() < 1e-10
+            else:
+                parts.append(eng.kopen())
+            eng.close()
+        if world == 2:          # aux shards of K[D_open] add up (the all-reduce of the real multi-rank run)
+            assert np.abs(parts[0] + parts[1] - kref).max() < 1e-11 * np.abs(kref).max()

@@ -41,9 +41,9 @@ class _SFBase:
 
     def _get_engine(self):
         if self._engine is None:
-            self.plan = planmod.build_sf_plan(self.problem, isf=self.isf, method=self.method, sa=0, layout=planmod.LAYOUT_PYSCF,
-                                              hdiag_kind="sf")
-            self._engine = timed_engine(self.tc, self.plan, self.problem, max_nvec=40)
+            builder = lambda p: planmod.build_sf_plan(p, isf=self.isf, method=self.method, sa=0, layout=planmod.LAYOUT_PYSCF, hdiag_kind="sf")
+            self._engine = timed_engine(self.tc, builder, self.problem, max_nvec=40)
+            self.plan = self._engine.plan
         return self._engine
 
     def gen_tda_operation_sf(self):

@@ -42,9 +42,10 @@ class XSF_TDA:
         if self._engine is None or self._engine_key != key:
             if self._engine is not None:
                 self._engine.close()
-            self.plan = planmod.build_sf_plan(self.problem, isf=-1, method=self.method, sa=self.SA, layout=planmod.LAYOUT_BLOCK,
-                                              remove=self.re, foo=foo, fglobal=fglobal, hdiag_kind="xsf")
-            self._engine = timed_engine(self.tc, self.plan, self.problem, max_nvec=40)
+            builder = lambda p: planmod.build_sf_plan(p, isf=-1, method=self.method, sa=self.SA, layout=planmod.LAYOUT_BLOCK, remove=self.re,
+                                                      foo=foo, fglobal=fglobal, hdiag_kind="xsf")
+            self._engine = timed_engine(self.tc, builder, self.problem, max_nvec=40)
+            self.plan = self._engine.plan
             self._engine_key = key
         return self._engine
 

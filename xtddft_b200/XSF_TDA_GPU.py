@@ -44,11 +44,12 @@ class XSF_TDA_GPU:
     def _get_engine(self):
         if self._engine is None:
             if self.extype == 0:
-                self.plan = planmod.build_sf_plan(self.problem, isf=1, method=self.method, hdiag_kind="gpu")
+                builder = lambda p: planmod.build_sf_plan(p, isf=1, method=self.method, hdiag_kind="gpu")
             else:
-                self.plan = planmod.build_sf_plan(self.problem, isf=-1, method=self.method, sa=self.X, layout=planmod.LAYOUT_PYSCF,
-                                                  remove=self.re, foo=self.foo, fglobal=self.fglobal, hdiag_kind="gpu")
-            self._engine = timed_engine(self.tc, self.plan, self.problem, max_nvec=40)
+                builder = lambda p: planmod.build_sf_plan(p, isf=-1, method=self.method, sa=self.X, layout=planmod.LAYOUT_PYSCF,
+                                                          remove=self.re, foo=self.foo, fglobal=self.fglobal, hdiag_kind="gpu")
+            self._engine = timed_engine(self.tc, builder, self.problem, max_nvec=40)
+            self.plan = self._engine.plan
         return self._engine
 
     def gen_vind(self):

@@ -35,8 +35,8 @@ class XTDA:
     # ---- operator interface (XTDA.py:694-698) ----------------------------------------------------------
     def _get_engine(self):
         if self._engine is None:
-            self.plan = planmod.build_xtda_plan(self.problem)
-            self._engine = timed_engine(self.tc, self.plan, self.problem, max_nvec=40)
+            self._engine = timed_engine(self.tc, planmod.build_xtda_plan, self.problem, max_nvec=40)
+            self.plan = self._engine.plan
         return self._engine
 
     def gen_vind(self, mf=None):

@@ -37,6 +37,8 @@ SIGNATURES = {
     "xtd_add_jblock": (_I, [_P, _I, _I, _I, _I, _I]),
     "xtd_set_jmix": (_I, [_P, _P, _I]),
     "xtd_set_exchange_emulation": (_I, [_P, _I]),
+    "xtd_set_open_orbitals": (_I, [_P, _I, _P, _I]),
+    "xtd_get_kopen": (_I, [_P, _P, _L]),
     "xtd_df_begin": (_I, [_P, _I, _L]),
     "xtd_df_add": (_I, [_P, _I, _P, _L, _L, _L, _I]),
     "xtd_jblock_diag": (_I, [_P, _I, _P]),

@@ -182,7 +182,7 @@ def _kernel_and_grid(mf, mol, kernel, mo_coeff, mo_occ2, restricted, collinear_s
     return xctype, ao, weights, fxc_uks, fxc_alda0, fxc_mcol
 
 
-def from_pyscf(mf, kernel: str = "uks", collinear_samples: int = 60, auxbasis=None, fxc_mcol=None) -> ProblemData:
+def from_pyscf(mf, kernel: str = "uks", collinear_samples: int = 60, auxbasis=None, fxc_mcol=None, rohf_fock: str = "pyscf") -> ProblemData:
     """Extract a ProblemData from a converged PySCF-style ROKS / UKS (ROHF / UHF) object -- exactly what the reference's
     `gen_vind()` closures capture (XTDA.py:558-613, SF_TDA.py:162-221, XSF_TDA.py:1029-1121).  kernel: 'uks' (X-TDA),
     'alda0', 'mcol', 'none'.
@@ -224,7 +224,7 @@ def from_pyscf(mf, kernel: str = "uks", collinear_samples: int = 60, auxbasis=No
     vhf = np.asarray(vhf)
     fock_ks = np.stack([mo_coeff[s].T @ (h1e + vhf[s]) @ mo_coeff[s] for s in (0, 1)])
     fock_hf = None
-    if restricted:
+    if restricted and rohf_fock != "device":
         import importlib
         try:
             scf = importlib.import_module("pyscf.scf")

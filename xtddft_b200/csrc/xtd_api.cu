@@ -159,6 +159,10 @@ struct xtd_engine {
   std::vector<JBlockRec*> jblocks;
   std::vector<double> jmix;
   DevBuf jmix_dev;
+  // ROHF-form Fock difference K[D_open] (xtd_set_open_orbitals): accumulated from the streamed tensor
+  int kopen_spin = -1, n_open = 0;
+  DevBuf CuT, CallT, kopen;    // [n_open][ldN], [nmo][ldN], [nmo][ld_mo]
+  long ld_mo = 0;
   long naux[2] = {0, 0};       // local aux count per tensor
   long naux_filled[2] = {0, 0};
   // grid
@@ -505,7 +509,7 @@ int xtd_destroy(xtd_handle h) {
   for (auto* l : h->lgemms) { l->M.release(); delete l; }
   for (auto* r : h->rank1s) { r->U.release(); r->V.release(); delete r; }
   for (auto* d : h->diags) { d->D.release(); delete d; }
-  h->jmix_dev.release(); h->wf.release();
+  h->jmix_dev.release(); h->wf.release(); h->CuT.release(); h->CallT.release(); h->kopen.release();
   if (h->s_indptr) cudaFree(h->s_indptr);
   if (h->s_offs) cudaFree(h->s_offs);
   if (h->s_chans) cudaFree(h->s_chans);
@@ -635,6 +639,49 @@ int xtd_set_exchange_emulation(xtd_handle h, int slices) {
   return XTD_OK;
 }
 
+int xtd_set_open_orbitals(xtd_handle h, int spin, const int* open_idx_host, int n_open) {
+  XTD_REQUIRE(h && !h->finalized && (spin == 0 || spin == 1) && open_idx_host && n_open >= 1 && n_open <= 64, XTD_ERR_ARG,
+              "xtd_set_open_orbitals: bad arguments");
+  XTD_REQUIRE(h->C[spin], XTD_ERR_STATE, "xtd_set_mo must precede xtd_set_open_orbitals");
+  XTD_REQUIRE(h->naux_filled[0] == 0, XTD_ERR_STATE, "xtd_set_open_orbitals must precede xtd_df_add");
+  const int N = h->nao, nmo = h->nmo[spin];
+  for (int i = 0; i < n_open; ++i) XTD_REQUIRE(open_idx_host[i] >= 0 && open_idx_host[i] < nmo, XTD_ERR_ARG, "open orbital index out of range");
+  cudaStream_t s = h->stream;
+  h->kopen_spin = spin; h->n_open = n_open; h->ld_mo = pad_ld(nmo);
+  DevBuf cu, call;
+  XTD_TRY(cu.alloc((size_t)N * pad_ld(n_open), s));
+  XTD_TRY(call.alloc((size_t)N * h->ld_mo, s));
+  XTD_TRY(h->CuT.alloc((size_t)n_open * h->ldN, s));
+  XTD_TRY(h->CallT.alloc((size_t)nmo * h->ldN, s));
+  XTD_TRY(h->kopen.alloc((size_t)nmo * h->ld_mo, s));
+  std::vector<int> all(nmo);
+  for (int i = 0; i < nmo; ++i) all[i] = i;
+  int *d_u = nullptr, *d_all = nullptr;
+  XTD_TRY(upload_array(&d_u, open_idx_host, (size_t)n_open, s));
+  XTD_TRY(upload_array(&d_all, all.data(), (size_t)nmo, s));
+  gather_cols_kernel<<<dim3((unsigned)cdiv(n_open, 128), N), 128, 0, s>>>(cu.p, pad_ld(n_open), h->C[spin], h->ldC[spin], N, d_u, n_open);
+  LAUNCH_CHECK();
+  gather_cols_kernel<<<dim3((unsigned)cdiv(nmo, 128), N), 128, 0, s>>>(call.p, h->ld_mo, h->C[spin], h->ldC[spin], N, d_all, nmo);
+  LAUNCH_CHECK();
+  dim3 tb(32, 8);
+  transpose_kernel<<<dim3((unsigned)cdiv(n_open, 32), (unsigned)cdiv(N, 32), 1), tb, 0, s>>>(h->CuT.p, h->ldN, 0, cu.p, pad_ld(n_open), 0, N, n_open);
+  LAUNCH_CHECK();
+  transpose_kernel<<<dim3((unsigned)cdiv(nmo, 32), (unsigned)cdiv(N, 32), 1), tb, 0, s>>>(h->CallT.p, h->ldN, 0, call.p, h->ld_mo, 0, N, nmo);
+  LAUNCH_CHECK();
+  XTD_CUDA(cudaStreamSynchronize(s));
+  cudaFree(d_u);
+  cudaFree(d_all);
+  return XTD_OK;
+}
+
+int xtd_get_kopen(xtd_handle h, double* out_dev, long ld) {
+  XTD_REQUIRE(h && out_dev && h->n_open > 0, XTD_ERR_STATE, "xtd_get_kopen: xtd_set_open_orbitals and the tensor come first");
+  const int nmo = h->nmo[h->kopen_spin];
+  XTD_REQUIRE(ld >= nmo, XTD_ERR_ARG, "xtd_get_kopen: ld < nmo");
+  XTD_CUDA(cudaMemcpy2DAsync(out_dev, (size_t)ld * 8, h->kopen.p, (size_t)h->ld_mo * 8, (size_t)nmo * 8, nmo, cudaMemcpyDeviceToDevice, h->stream));
+  return XTD_OK;
+}
+
 int xtd_df_begin(xtd_handle h, int tensor, long naux_local) {
   XTD_REQUIRE(h && (tensor == 0 || tensor == 1) && naux_local >= 0, XTD_ERR_ARG, "xtd_df_begin: bad arguments");
   h->naux[tensor] = naux_local;
@@ -707,6 +754,7 @@ int xtd_df_add(xtd_handle h, int tensor, const double* l_dev, long np, long ld_r
     if (need_o) max_n = std::max(max_n, c->no);
     if (c->need_k[tensor]) max_n = std::max(max_n, c->nv);
   }
+  if (tensor == 0 && h->n_open > 0) max_n = std::max(max_n, 1);
   if (max_n == 0) { h->naux_filled[tensor] += np; return XTD_OK; }
   h->arena.used = 0;
   size_t split_bytes = std::min<size_t>(h->arena.cap / 4, (size_t)1 << 30);
@@ -725,7 +773,8 @@ int xtd_df_add(xtd_handle h, int tensor, const double* l_dev, long np, long ld_r
                 "xtd_df_add: with the INT8-emulated exchange contraction every chunk but the last must hold a multiple of %ld aux functions",
                 oz_align);
   }
-  const size_t per_p = ((size_t)(direct ? 0 : N) + (size_t)max_n) * ldN + oz_tmp;
+  const size_t ko_tmp = (tensor == 0 && h->n_open > 0) ? (size_t)h->n_open * (ldN + h->ld_mo) : 0;   // Hu + Lu of K[D_open]
+  const size_t per_p = ((size_t)(direct ? 0 : N) + (size_t)max_n) * ldN + oz_tmp + ko_tmp;
   long pc = (long)(h->arena.left() / 8 / per_p);
   XTD_REQUIRE(pc >= oz_align, XTD_ERR_NOMEM, "xtd_df_add: workspace too small for %ld aux functions (%zu doubles each)", oz_align, per_p);
   pc = std::min<long>(pc, np);
@@ -733,7 +782,8 @@ int xtd_df_add(xtd_handle h, int tensor, const double* l_dev, long np, long ld_r
   double* stage = direct ? nullptr : h->arena.take((size_t)pc * N * ldN);
   double* half = h->arena.take((size_t)pc * max_n * ldN);
   double* lvv_tmp = oz_tmp ? h->arena.take((size_t)pc * oz_tmp) : nullptr;
-  XTD_REQUIRE(half && (direct || stage) && (!oz_tmp || lvv_tmp), XTD_ERR_NOMEM, "xtd_df_add: workspace exhausted");
+  double* ko_buf = ko_tmp ? h->arena.take((size_t)pc * ko_tmp) : nullptr;
+  XTD_REQUIRE(half && (direct || stage) && (!oz_tmp || lvv_tmp) && (!ko_tmp || ko_buf), XTD_ERR_NOMEM, "xtd_df_add: workspace exhausted");
 
   for (long p0 = 0; p0 < np; p0 += pc) {
     const int pn = (int)std::min<long>(pc, np - p0);
@@ -750,6 +800,28 @@ int xtd_df_add(xtd_handle h, int tensor, const double* l_dev, long np, long ld_r
       }
       LAUNCH_CHECK();
       Lv = view3d(stage, ldN, (long)N * ldN, pn, N, N);
+    }
+    if (ko_buf) {
+      // K[D_open][p][q] += sum_P sum_u L^P_pu L^P_qu:  Hu[P][u][mu] = sum_nu CuT[u][nu] L[P][mu][nu],  Lu[P][u][q] = sum_mu Hu C[mu][q]
+      const int nu_ = h->n_open, nmo = h->nmo[h->kopen_spin];
+      double* Hu = ko_buf;
+      double* Lu = ko_buf + (size_t)pc * nu_ * ldN;
+      GemmDesc d;
+      d.A = view2d(h->CuT.p, ldN, nu_, N); d.B = Lv; d.M = nu_; d.N = N; d.K = N;
+      d.batches = pn; d.z_div = 1; d.a_hi = 0; d.b_hi = 1;
+      d.C = Hu; d.ldc = ldN; d.c_batch_stride = (long)nu_ * ldN;
+      XTD_TRY(gemm(h->gemm, d, s));
+      GemmDesc e;
+      e.A = view3d(Hu, ldN, (long)nu_ * ldN, pn, nu_, N); e.B = view2d(h->CallT.p, ldN, nmo, N);
+      e.M = nu_; e.N = nmo; e.K = N; e.batches = pn; e.a_hi = 1; e.b_hi = 0;
+      e.C = Lu; e.ldc = h->ld_mo; e.c_batch_stride = (long)nu_ * h->ld_mo;
+      XTD_TRY(gemm(h->gemm, e, s));
+      GemmDesc f;
+      f.a_kc = false; f.b_kc = false;
+      f.A = view2d(Lu, h->ld_mo, pn * nu_, nmo); f.B = view2d(Lu, h->ld_mo, pn * nu_, nmo);
+      f.M = nmo; f.N = nmo; f.K = pn * nu_;
+      f.C = h->kopen.p; f.ldc = h->ld_mo; f.accumulate = true;
+      XTD_TRY(gemm(h->gemm, f, s));
     }
     for (size_t ci = 0; ci < h->ch.size(); ++ci) {
       Channel* c = h->ch[ci];

@@ -25,7 +25,12 @@ class TimeCounter:
 
 
 def make_engine(plan, p, max_nvec: int = 40, workspace_bytes: Optional[int] = None, distributed: bool = True) -> SigmaEngine:
+    """`plan`: a compiled Plan, or a callable `p -> Plan`.  With a callable, a ROKS problem that carries no ROHF-form Fock matrices
+    (`p.fock_hf is None`) gets their spin difference K[D_open] from the device while the tensor streams in (SigmaEngine.from_problem)."""
     import torch
+    builder = plan if callable(plan) else None
+    if builder is not None:
+        plan = None if (p.restricted and p.fock_hf is None) else builder(p)
     reducer = None
     rank, world = 0, 1
     if distributed and torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
@@ -34,7 +39,8 @@ def make_engine(plan, p, max_nvec: int = 40, workspace_bytes: Optional[int] = No
     if workspace_bytes is None:
         free, _ = torch.cuda.mem_get_info()
         workspace_bytes = int(min(8 << 30, max(256 << 20, free // 4)))
-    return SigmaEngine.from_problem(plan, p, max_nvec=max_nvec, workspace_bytes=workspace_bytes, reducer=reducer, rank=rank, world=world)
+    return SigmaEngine.from_problem(plan, p, max_nvec=max_nvec, workspace_bytes=workspace_bytes, reducer=reducer, rank=rank, world=world,
+                                    plan_builder=builder)
 
 
 def timed_engine(tc: Optional[TimeCounter], plan, p, **kw) -> SigmaEngine:

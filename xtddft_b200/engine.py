@@ -149,6 +149,25 @@ class SigmaEngine:
             _lib.check(self.lib.xtd_df_add(self._h, tensor, _ptr(chunk), chunk.shape[0], chunk.stride(1), chunk.stride(0), 0),
                        "xtd_df_add")
 
+    # ---- ROHF-form Fock difference (setup stage) ------------------------------------------------------
+    def set_open_orbitals(self, spin: int, open_idx):
+        """Declare the open-shell MOs before the tensor streams in: the library then accumulates K[D_open] in the MO basis."""
+        idx = np.ascontiguousarray(open_idx, dtype=np.int32)
+        _lib.check(self.lib.xtd_set_open_orbitals(self._h, int(spin), _np_ptr(idx), len(idx)), "xtd_set_open_orbitals")
+        self._kopen_nmo = int(self._keep[spin].shape[1])
+
+    def kopen(self) -> np.ndarray:
+        """K[D_open][p][q] = sum_P sum_u L^P_pu L^P_qu = F_beta^HF - F_alpha^HF of the ROHF-form Fock matrices (XTDA.py:607-613,
+        XSF_TDA.py:1103-1111), all-reduced over the aux shards."""
+        torch = self.torch
+        n = self._kopen_nmo
+        out = torch.zeros((n, n), dtype=torch.float64, device=self.device)
+        self._set_stream()
+        _lib.check(self.lib.xtd_get_kopen(self._h, _ptr(out), n), "xtd_get_kopen")
+        if self.reducer is not None:
+            self.reducer.allreduce_(out)
+        return out.cpu().numpy()
+
     def load_cderi(self, tensor: int, cderi: np.ndarray, chunk: int = 64):
         """Stream a host tensor [naux_local, nao, nao] through the device in aux chunks."""
         torch = self.torch
@@ -243,9 +262,18 @@ class SigmaEngine:
     @classmethod
     def from_problem(cls, plan: Plan, p: ProblemData, *, max_nvec: int = 40, workspace_bytes: int = 2 << 30, device=None,
                      reducer: Optional[SigmaReducer] = None, rank: int = 0, world: int = 1, df_chunk: int = 64,
-                     exchange_slices: Optional[int] = None) -> "SigmaEngine":
-        """Upload a host ProblemData; with world > 1 this rank keeps only its aux block and grid batch."""
+                     exchange_slices: Optional[int] = None, plan_builder=None) -> "SigmaEngine":
+        """Upload a host ProblemData; with world > 1 this rank keeps only its aux block and grid batch.
+
+        `plan_builder(p) -> Plan`: for a ROKS problem WITHOUT ROHF-form Fock matrices (`p.fock_hf is None`) the engine computes
+        their spin difference K[D_open] on the device while the tensor streams in, stores it as `p.fock_hf = [0, K]` (only the
+        difference enters the sigma build) and compiles the final plan with `plan_builder` before the local terms are uploaded;
+        `plan` then only has to carry the channels and exchange / Coulomb declarations (built from a zero placeholder)."""
         import torch
+        need_kopen = bool(p.restricted and p.fock_hf is None and plan_builder is not None)
+        if need_kopen:
+            p.fock_hf = np.zeros((2, p.nmo, p.nmo))
+            plan = plan_builder(p)
         eng = cls(plan, p.nao, p.mo_coeff, workspace_bytes=workspace_bytes, device=device, reducer=reducer, exchange_slices=exchange_slices)
         g0, g1 = split_range(p.ng, rank, world) if plan.xc_kind != "none" else (0, 0)
         if g1 > g0:                             # a rank whose grid batch is empty simply has no grid term
@@ -264,6 +292,10 @@ class SigmaEngine:
             del ao, w, f
             eng.grid_commit()                   # AO values are dropped before the tensor streams in
             torch.cuda.empty_cache()
+        if need_kopen:
+            if 0 not in eng.tensors_used:
+                raise _lib.XtdError("the ROHF-form Fock difference needs the density-fitting tensor, but this plan streams none")
+            eng.set_open_orbitals(0, np.arange(p.nc, p.nc + p.no))
         for t in eng.tensors_used:
             full = p.cderi if t == 0 else p.cderi_lr
             if full is None:                    # PySCF's packed storage: streamed block by block, never unpacked on the host
@@ -271,6 +303,9 @@ class SigmaEngine:
                 continue
             p0, p1 = split_range(full.shape[0], rank, world)
             eng.load_cderi(t, full[p0:p1], chunk=df_chunk)
+        if need_kopen:
+            p.fock_hf = np.stack([np.zeros((p.nmo, p.nmo)), eng.kopen()])
+            eng.plan = plan_builder(p)          # same channels / exchange declarations, local terms with the computed couplings
         eng.finalize(max_nvec)
         return eng
 
