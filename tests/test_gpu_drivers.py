@@ -163,3 +163,26 @@ def test_driver_property_pass(torch_cuda):
     tdm, osc = x.calculate_TDM(verbose=False)
     ref = oprop.tdm_r(np.asarray(x.v), ints_mo, p.nc, p.no, p.nv, 2, None)
     assert np.abs(tdm - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())
+
+
+def test_timing_categories_of_the_reference(torch_cuda):
+    """`tc` carries the reference's TimeCounter categories (XTDA_GPU.py:481-499) filled from the CUDA-event phase timers."""
+    from xtddft_b200.SF_TDA import SF_TDA
+    from xtddft_b200.synth import make_problem
+    p = make_problem(290, 40, 2, 248, 30, 3000, xctype="LDA", hyb=0.5, seed=77)       # dim 10 500 < 50 000: totals only
+    obj = SF_TDA(p, isf=-1)
+    obj.kernel(nstates=3)
+    assert obj.tc.Ap > 0 and obj.tc.dv > 0 and obj.tc.Adv == 0.0
+    p = make_problem(420, 120, 2, 298, 16, 2000, xctype="LDA", hyb=0.5, seed=78)      # dim 36 600 ... still small; force detail
+    obj = SF_TDA(p, isf=-1)
+    eng = obj._get_engine()
+    assert eng.ext_dim == 122 * 300
+    import xtddft_b200.drivers_common as dc
+    conv, e, v, cyc, hd = dc.solve(eng, 3, "sf_down", tc=obj.tc)
+    assert obj.tc.dv > 0
+    # the per-phase categories are collected from 50 000 unknowns on; check the accounting on this engine directly
+    import torch
+    z = torch.randn((3, eng.ext_dim), dtype=torch.float64, device="cuda")
+    eng.sigma(z)
+    ms = eng.stats()["ms"]
+    assert ms["k1"] > 0 and ms["k2"] > 0 and ms["xc_gemm"] > 0 and ms["allreduce"] == 0.0

@@ -49,6 +49,22 @@ __global__ void pack_kernel(double* __restrict__ Z, long ldz, long z_vec_stride,
   Z[(long)x * z_vec_stride + i * ldz + a] = acc;
 }
 
+// the same gather, also writing the transposed copy ZT[x][a][i] (small problems: one launch instead of pack + transpose)
+__global__ void pack_t_kernel(double* __restrict__ Z, long ldz, long z_vec_stride, double* __restrict__ ZT, long ldzt, long zt_vec_stride, int nv,
+                              long nrows, const long* __restrict__ indptr, const long* __restrict__ cols, const double* __restrict__ vals,
+                              const double* __restrict__ zext, long ext_dim, int nvec) {
+  const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int x = blockIdx.y;
+  if (r >= nrows || x >= nvec) return;
+  const long k0 = indptr[r], k1 = indptr[r + 1];
+  double acc = 0.0;
+  const double* zx = zext + (long)x * ext_dim;
+  for (long k = k0; k < k1; ++k) acc += vals[k] * zx[cols[k]];
+  const long i = r / nv, a = r - i * nv;
+  Z[(long)x * z_vec_stride + i * ldz + a] = acc;
+  ZT[(long)x * zt_vec_stride + a * ldzt + i] = acc;
+}
+
 // hz[x][e] = sum_k val[k] * SIG[ chan_base[ch[k]] + x*chan_vec_stride[ch[k]] + off[k] ]
 struct UnpackChan {
   long base[2];
@@ -586,6 +602,54 @@ __global__ void block_diag_kernel(double* __restrict__ S, const double* __restri
   const long i = e / nv, a = e - i * nv;
   const long o = (long)x * vec_stride + i * ld + a;
   S[o] += D[i * ld + a] * Z[o];
+}
+
+// All local GEMM terms and diagonal terms of a SMALL problem in ONE launch (launch-bound molecules: a dozen tiny GEMM launches
+// otherwise).  One thread per destination element (channel, vector, i, a): it walks the term list and adds every contribution
+// that covers its element -- deterministic, no atomics.
+struct LocalTermDev {
+  int side, dch, r0, nr, c0, nc, sch, sr0, sc0, k;   // k: contraction length
+  long ldm;
+  double alpha;
+  const double* M;
+};
+struct LocalSmallArgs {
+  const LocalTermDev* terms;
+  int nterms;
+  const LocalTermDev* diags;   // diagonal terms reuse the record: dch = channel, M = D[no][ld]
+  int ndiags;
+  double* sig;
+  const double* z[2];
+  long sig_base[2], ldz[2], vec_stride[2];
+  int no[2], nv[2];
+};
+__global__ void local_small_kernel(const LocalSmallArgs a) {
+  const int ch = blockIdx.z, x = blockIdx.y;
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long)a.no[ch] * a.nv[ch]) return;
+  const int i = (int)(e / a.nv[ch]), c = (int)(e - (long)i * a.nv[ch]);
+  double acc = 0.0;
+  for (int t = 0; t < a.nterms; ++t) {
+    const LocalTermDev& l = a.terms[t];
+    if (l.dch != ch || i < l.r0 || i >= l.r0 + l.nr || c < l.c0 || c >= l.c0 + l.nc) continue;
+    const double* src = a.z[l.sch] + (long)x * a.vec_stride[l.sch];
+    const long lds = a.ldz[l.sch];
+    double v = 0.0;
+    if (l.side == 0) {        // RIGHT: dst[r][c] += alpha sum_b src[sr0 + r][sc0 + b] M[b][c]
+      const double* sr = src + (long)(l.sr0 + i - l.r0) * lds + l.sc0;
+      const double* m = l.M + (c - l.c0);
+      for (int b = 0; b < l.k; ++b) v = fma(sr[b], m[(long)b * l.ldm], v);
+    } else {                  // LEFT: dst[r][c] += alpha sum_j M[r][j] src[sr0 + j][sc0 + c]
+      const double* m = l.M + (long)(i - l.r0) * l.ldm;
+      const double* sc = src + (long)l.sr0 * lds + l.sc0 + (c - l.c0);
+      for (int j = 0; j < l.k; ++j) v = fma(m[j], sc[(long)j * lds], v);
+    }
+    acc = fma(l.alpha, v, acc);
+  }
+  const long o = (long)x * a.vec_stride[ch] + (long)i * a.ldz[ch] + c;
+  for (int t = 0; t < a.ndiags; ++t)
+    if (a.diags[t].dch == ch) acc = fma(a.diags[t].M[(long)i * a.ldz[ch] + c], a.z[ch][o], acc);
+  a.sig[a.sig_base[ch] + o] += acc;
 }
 
 // ------------------------------------------------------------------------------------------------------

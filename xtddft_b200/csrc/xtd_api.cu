@@ -176,6 +176,8 @@ struct xtd_engine {
   DevBuf wf;
   bool grid_committed = false;
   // local terms
+  bool small_local = false;            // all local GEMM / diagonal terms in one launch (launch-bound molecules)
+  LocalTermDev *lt_dev = nullptr, *ld_dev = nullptr;
   std::vector<LocalGemmRec*> lgemms;
   std::vector<Rank1Rec*> rank1s;
   std::vector<DiagRec*> diags;
@@ -510,6 +512,8 @@ int xtd_destroy(xtd_handle h) {
   for (auto* r : h->rank1s) { r->U.release(); r->V.release(); delete r; }
   for (auto* d : h->diags) { d->D.release(); delete d; }
   h->jmix_dev.release(); h->wf.release(); h->CuT.release(); h->CallT.release(); h->kopen.release();
+  if (h->lt_dev) cudaFree(h->lt_dev);
+  if (h->ld_dev) cudaFree(h->ld_dev);
   if (h->s_indptr) cudaFree(h->s_indptr);
   if (h->s_offs) cudaFree(h->s_offs);
   if (h->s_chans) cudaFree(h->s_chans);
@@ -1034,6 +1038,27 @@ int xtd_finalize(xtd_handle h, int max_nvec) {
   }
   XTD_REQUIRE(fixed * 8 + (32u << 20) < h->arena.cap, XTD_ERR_NOMEM, "xtd_finalize: workspace of %zu bytes too small for %d vectors (%zu fixed)",
               h->arena.cap, max_nvec, fixed * 8);
+  // small problems: the local GEMM and diagonal terms become one launch
+  long max_elems = 0;
+  for (auto* c : h->ch) max_elems = std::max<long>(max_elems, (long)c->no * c->nv);
+  h->small_local = max_elems <= 16384 && !(getenv("XTD_LOCAL_BATCH") && atoi(getenv("XTD_LOCAL_BATCH")) == 0);
+  if (h->small_local && (!h->lgemms.empty() || !h->diags.empty())) {
+    std::vector<LocalTermDev> lt, ld;
+    for (auto* l : h->lgemms) {
+      LocalTermDev t;
+      t.side = l->side == XTD_SIDE_RIGHT ? 0 : 1; t.dch = l->dch; t.r0 = l->r0; t.nr = l->nr; t.c0 = l->c0; t.nc = l->nc;
+      t.sch = l->sch; t.sr0 = l->sr0; t.sc0 = l->sc0; t.k = l->side == XTD_SIDE_RIGHT ? l->mrows : l->mcols;
+      t.ldm = l->ldm; t.alpha = l->alpha; t.M = l->M.p;
+      lt.push_back(t);
+    }
+    for (auto* d : h->diags) {
+      LocalTermDev t = {};
+      t.dch = d->ch; t.M = d->D.p;
+      ld.push_back(t);
+    }
+    XTD_TRY(upload_array(&h->lt_dev, lt.data(), lt.size(), s));
+    XTD_TRY(upload_array(&h->ld_dev, ld.data(), ld.size(), s));
+  }
   h->finalized = true;
   return XTD_OK;
 }
@@ -1925,7 +1950,23 @@ static int run_j(xtd_engine* h, int nvec) {
 static int run_local(xtd_engine* h, int nvec) {
   cudaStream_t s = h->stream;
   PhaseTimer t(h, XTD_T_LOCAL);
+  const bool batched = h->small_local && (h->lt_dev || h->ld_dev);
+  if (batched) {
+    LocalSmallArgs a;
+    a.terms = h->lt_dev; a.nterms = (int)h->lgemms.size(); a.diags = h->ld_dev; a.ndiags = (int)h->diags.size();
+    a.sig = h->SIG;
+    long max_elems = 0;
+    for (int c = 0; c < 2; ++c) {
+      const bool on = c < (int)h->ch.size();
+      a.z[c] = on ? h->Z[c] : nullptr; a.sig_base[c] = on ? h->sig_base[c] : 0; a.ldz[c] = on ? h->ch[c]->ldz : 0;
+      a.vec_stride[c] = on ? (long)h->ch[c]->no * h->ch[c]->ldz : 0; a.no[c] = on ? h->ch[c]->no : 0; a.nv[c] = on ? h->ch[c]->nv : 0;
+      if (on) max_elems = std::max<long>(max_elems, (long)h->ch[c]->no * h->ch[c]->nv);
+    }
+    local_small_kernel<<<dim3((unsigned)cdiv(max_elems, 128), nvec, (unsigned)h->ch.size()), 128, 0, s>>>(a);
+    LAUNCH_CHECK();
+  }
   for (auto* l : h->lgemms) {
+    if (batched) break;
     Channel *dc = h->ch[l->dch], *sc = h->ch[l->sch];
     double* dst = h->SIG + h->sig_base[l->dch] + (long)l->r0 * dc->ldz + l->c0;
     GemmDesc d;
@@ -1960,6 +2001,7 @@ static int run_local(xtd_engine* h, int nvec) {
     LAUNCH_CHECK();
   }
   for (auto* dg : h->diags) {
+    if (batched) break;
     Channel* c = h->ch[dg->ch];
     block_diag_kernel<<<dim3((unsigned)cdiv((long)c->no * c->nv, 256), nvec), 256, 0, s>>>(h->SIG + h->sig_base[dg->ch], dg->D.p, h->Z[dg->ch],
                                                                                          c->ldz, (long)c->no * c->ldz, c->no, c->nv);
@@ -1989,10 +2031,20 @@ int xtd_sigma_partial(xtd_handle h, int nvec, const double* z_dev) {
     for (size_t c = 0; c < h->ch.size(); ++c) {
       Channel* ch = h->ch[c];
       const long nrows = (long)ch->no * ch->nv;
+      const bool need_zt = !h->kterms.empty() || ch->xc_oz_split;
+      if (need_zt && h->small_local) {
+        // small problems: gather and transposed copy in one launch
+        XTD_CUDA(cudaMemsetAsync(h->ZT[c], 0, (size_t)nvec * ch->nv * ch->ldzt * 8, s));
+        pack_t_kernel<<<dim3((unsigned)cdiv(nrows, 256), nvec), 256, 0, s>>>(h->Z[c], ch->ldz, (long)ch->no * ch->ldz, h->ZT[c], ch->ldzt,
+                                                                           (long)ch->nv * ch->ldzt, ch->nv, nrows, ch->g_indptr, ch->g_cols,
+                                                                           ch->g_vals, z_dev, h->ext_dim, nvec);
+        LAUNCH_CHECK();
+        continue;
+      }
       pack_kernel<<<dim3((unsigned)cdiv(nrows, 256), nvec), 256, 0, s>>>(h->Z[c], ch->ldz, (long)ch->no * ch->ldz, ch->nv, nrows, ch->g_indptr,
                                                                          ch->g_cols, ch->g_vals, z_dev, h->ext_dim, nvec);
       LAUNCH_CHECK();
-      if (!h->kterms.empty() || ch->xc_oz_split) {
+      if (need_zt) {
         XTD_CUDA(cudaMemsetAsync(h->ZT[c], 0, (size_t)nvec * ch->nv * ch->ldzt * 8, s));
         transpose_kernel<<<dim3((unsigned)cdiv(ch->nv, 32), (unsigned)cdiv(ch->no, 32), nvec), dim3(32, 8), 0, s>>>(
             h->ZT[c], ch->ldzt, (long)ch->nv * ch->ldzt, h->Z[c], ch->ldz, (long)ch->no * ch->ldz, ch->no, ch->nv);
