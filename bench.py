@@ -486,9 +486,14 @@ def main():
     ref_flops = sum(4.0 * (dp.naux // world + (1 if rank < dp.naux % world else 0)) * p.nao ** 2 * eng.plan.channels[kt.ch].no * nvec
                     for kt in eng.plan.k_terms)
     k_ms = (phase.get("k1", 0.0) + phase.get("k2", 0.0) + phase.get("k2_slice", 0.0)) / args.steps
+    try:
+        roof["launches_per_step"] = int(eng.last_chunks()[0]) * max(1, len(eng.plan.k_terms))   # one launch per aux chunk and exchange term
+    except Exception:
+        pass
     if roof["traffic"] is not None:
+        roof["traffic_scope"] = "per launch (ONE aux chunk), as ncu reports it; flops_per_launch_group and ms_per_step_in_kernel are per STEP"
         # `traffic` is per LAUNCH (one aux chunk) as ncu reports it; the launch it was captured on, for comparison
-        roof["traffic_captured_launch"] = _ncu_traffic(dp.name, "k2", "captured_launch")
+        roof["traffic_captured_launch"] = _ncu_traffic(dp.name, "k2_int8" if xs_on else "k2", "captured_launch")
     roof["reference_algorithm_flops_per_step"] = ref_flops
     roof["reference_algorithm_tflops_equivalent"] = (ref_flops / (k_ms * 1e-3) / 1e12) if k_ms > 0 else None
     # ---- streaming kernel of the grid path (xc_weight_kernel) against HBM bandwidth --------------------------

@@ -143,6 +143,25 @@ def main():
 
     np.savez(os.path.join(OUT, "properties.npz"), **out)
 
+    # ---- state-interaction wire format: the reference's own statements, x2c_hamiltonian/test_SOCSI.py:47-58,
+    #      read from the reference tree and executed verbatim on a stand-in `xsf_tda` object --------------------------------
+    src = open(os.path.join(mg.REF, "x2c_hamiltonian", "test_SOCSI.py")).read().splitlines()
+    i0 = next(i for i, l in enumerate(src) if "trans the formulation of X vector" in l)
+    i1 = next(i for i, l in enumerate(src) if l.strip().startswith("xm[dim+xsf_tda.no**2:,:]"))
+    block = "\n".join(l[4:] for l in src[i0:i1 + 1])                      # de-indent the body of soc_mf()
+    sd = {}
+    for (nc, no, nv, seed) in [(3, 2, 4, 81), (2, 3, 3, 82)]:
+        ns = 5
+        vects = R["XSF_TDA"].XSF_TDA.get_vect(types.SimpleNamespace(no=no))
+        dim_re = (nc + no) * (no + nv) - 1
+        xm_ = np.random.default_rng(seed).standard_normal((dim_re, ns))
+        ns_ = dict(numpy=np, xm_=xm_, xsf_tda=types.SimpleNamespace(nc=nc, no=no, nv=nv, nstates=ns, vects=vects))
+        exec(block, ns_)
+        sd[f"in_{nc}_{no}_{nv}"] = xm_
+        sd[f"out_{nc}_{no}_{nv}"] = ns_["xm"]
+    np.savez(os.path.join(OUT, "state_dict.npz"), **sd)
+    print("state_dict", {k: v.shape for k, v in sd.items()})
+
 
 if __name__ == "__main__":
     main()

@@ -51,3 +51,13 @@ def test_build_state_dict():
     st = sd.build_state_dict(xsf, xt, up)
     assert [len(st[k]) for k in ("|S->", "|So>", "|S+>")] == [3, 2, 2]
     assert st["|S->"][1][0] == 0.2 and st["|S->"][1][1].shape == (nc * nv + nc * no + no * nv + no * no + no,)
+
+
+@pytest.mark.parametrize("nc,no,nv", [(3, 2, 4), (2, 3, 3)])
+def test_si_vector_layout_against_the_reference(golden_dir, nc, no, nv):
+    """Fixture produced by executing the reference's OWN statements (x2c_hamiltonian/test_SOCSI.py:47-58, read from the reference
+    tree by tests/golden/make_golden_properties.py) on a stand-in solved XSF_TDA object with the removed OO vector."""
+    import os
+    d = np.load(os.path.join(golden_dir, "state_dict.npz"), allow_pickle=False)
+    got = sd.xsf_si_vectors(d[f"in_{nc}_{no}_{nv}"], nc, no, nv, layouts.get_vect(no))
+    assert np.abs(got - d[f"out_{nc}_{no}_{nv}"]).max() < 1e-15

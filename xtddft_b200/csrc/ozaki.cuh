@@ -47,7 +47,7 @@ __device__ __forceinline__ double oz_scale_of(double m) {
   return ldexp(1.0, e - 6);
 }
 
-// transposed source: block (32 rows, 8 k-lanes); grid (rows_pad / 32, ngroups)
+// transposed source: block (32 rows, 32 k-lanes); grid (rows_pad / 32, ngroups)
 __global__ void oz_rowmax_t_kernel(double* __restrict__ scale, int rows_pad, const double* __restrict__ X, long ld, long sq, int rows, int K,
                                    int nq, int group, long k_valid) {
   const int row = blockIdx.x * 32 + threadIdx.x, g = blockIdx.y;
@@ -57,14 +57,14 @@ __global__ void oz_rowmax_t_kernel(double* __restrict__ scale, int rows_pad, con
     for (int q = g * group; q < q1; ++q) {
       const long kmax = min((long)K, k_valid - (long)q * K);
       const double* x = X + (long)q * sq + row;
-      for (long k = threadIdx.y; k < kmax; k += 8) m = fmax(m, fabs(x[k * ld]));
+      for (long k = threadIdx.y; k < kmax; k += 32) m = fmax(m, fabs(x[k * ld]));
     }
   }
-  __shared__ double red[8][33];
+  __shared__ double red[32][33];
   red[threadIdx.y][threadIdx.x] = m;
   __syncthreads();
   if (threadIdx.y == 0) {
-    for (int w = 1; w < 8; ++w) m = fmax(m, red[w][threadIdx.x]);
+    for (int w = 1; w < 32; ++w) m = fmax(m, red[w][threadIdx.x]);
     if (row < rows_pad) scale[(long)g * rows_pad + row] = oz_scale_of(m);
   }
 }
@@ -711,7 +711,7 @@ inline int oz_slice_launch(int8_t* out, double* scale, const OzShape& sh, const 
   const int stacked = sh.RT == OZ_BN ? 1 : 0;
   const dim3 sgrid(2 * sh.nkb, sh.rows_pad / 128, nq);
   if (trans) {
-    oz_rowmax_t_kernel<<<dim3(sh.rows_pad / 32, ng), dim3(32, 8), 0, st>>>(scale, sh.rows_pad, X, ld, sq, sh.rows, sh.K, nq, group, k_valid);
+    oz_rowmax_t_kernel<<<dim3(sh.rows_pad / 32, ng), dim3(32, 32), 0, st>>>(scale, sh.rows_pad, X, ld, sq, sh.rows, sh.K, nq, group, k_valid);
     XTD_COUNT_LAUNCH();
     XTD_CUDA(cudaGetLastError());
     oz_slice_kernel<S, true><<<sgrid, 128, 0, st>>>(out, scale, sh.rows_pad, X, ld, sq, sh.rows, sh.K, sh.RT, sh.nkb, group, stacked, k_valid);
