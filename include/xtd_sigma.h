@@ -140,6 +140,20 @@ int xtd_vec_precond(void* stream, double* x_dev, long ld, const double* hdiag_de
                     long n);
 int xtd_vec_scale(void* stream, double* x_dev, long ld, const double* s_dev, int k, long n);
 
+/* The solver around the operator (replaces `lib.davidson1` / utils/Davidson.py:21-298 as called at XTDA.py:775-777, SF_TDA.py:392-395,
+ * XSF_TDA.py:1467-1470): block Davidson with the subspace resident in HBM and the host control flow in C++.  x0_dev [n0, dim] initial
+ * vectors, hdiag_dev [dim] the diagonal preconditioner; on return e_host[nroots], conv_host[nroots], x_dev [nroots, dim] (Ritz vectors).
+ * Returns the number of roots found (<= nroots) or a negative error code.  Multi-GPU: `allreduce` sums the partial sigma block over the
+ * ranks (device buffer of n doubles, on the engine stream; return 0 on success); NULL on a single rank. */
+typedef struct {
+  double tol, tol_residual /* <= 0: sqrt(tol) */, lindep, level_shift;
+  int max_cycle, max_space /* 12: the solver adds 4 (nroots - 1) */, pick_positive /* keep eigenvalues > 1e-3 (X-TDA) */;
+  int (*allreduce)(void* ctx, double* dev_buf, long n);
+  void* allreduce_ctx;
+} xtd_solver_opts;
+int xtd_davidson(xtd_handle h, int nroots, const xtd_solver_opts* opts, const double* hdiag_dev, const double* x0_dev, int n0,
+                 double* e_host, double* x_dev, int* conv_host, int* ncycle, int* nsigma);
+
 /* plain GEMM entry (tests / benchmarks of the DMMA kernel): C[M,N] = alpha * A[M,K] * B[N,K]^T */
 int xtd_dgemm_tn(void* stream, int m, int n, int k, double alpha, const double* a_dev, long lda, const double* b_dev, long ldb,
                  double* c_dev, long ldc, int accumulate);

@@ -16,6 +16,15 @@ class XtdError(RuntimeError):
     pass
 
 
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_long)
+
+
+class XtdSolverOpts(C.Structure):
+    _fields_ = [("tol", C.c_double), ("tol_residual", C.c_double), ("lindep", C.c_double), ("level_shift", C.c_double),
+                ("max_cycle", C.c_int), ("max_space", C.c_int), ("pick_positive", C.c_int), ("allreduce", ALLREDUCE_FN),
+                ("allreduce_ctx", C.c_void_p)]
+
+
 class XtdStats(C.Structure):
     _fields_ = [("flops_gemm", C.c_double), ("launches", C.c_ulonglong), ("ms", C.c_double * 12), ("flops", C.c_double * 12)]
 
@@ -65,6 +74,7 @@ SIGNATURES = {
     "xtd_vec_residual": (_I, [_P, _P, _P, _P, _L, _P, _P, _I, _L]),
     "xtd_vec_precond": (_I, [_P, _P, _L, _P, _P, _P, _I, _L]),
     "xtd_vec_scale": (_I, [_P, _P, _L, _P, _I, _L]),
+    "xtd_davidson": (_I, [_P, _I, C.POINTER(XtdSolverOpts), _P, _P, _I, _P, _P, _P, C.POINTER(_I), C.POINTER(_I)]),
     "xtd_dgemm_tn": (_I, [_P, _I, _I, _I, _D, _P, _L, _P, _L, _P, _L, _I]),
     "xtd_dgemm": (_I, [_P, _I, _I, _I, _D, _P, _L, _I, _P, _L, _I, _P, _L, _I]),
     "xtd_ozaki_gemm": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _L, _L, _P, _L, _L, _P, _L, _D, _I, _P]),

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libxtdsigma.so")
 SOURCES = ["xtd_api.cu"]
-HEADERS = ["common.cuh", "gemm.cuh", "kernels.cuh", "ozaki.cuh", os.path.join("..", "..", "include", "xtd_sigma.h")]
+HEADERS = ["common.cuh", "gemm.cuh", "kernels.cuh", "ozaki.cuh", "davidson.cuh", os.path.join("..", "..", "include", "xtd_sigma.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]
 
 

@@ -12,6 +12,7 @@
 #include "gemm.cuh"
 #include "kernels.cuh"
 #include "ozaki.cuh"
+#include "davidson.cuh"
 
 #include <cuda_profiler_api.h>
 
@@ -2344,3 +2345,263 @@ int xtd_dgemm_tn(void* stream, int m, int n, int k, double alpha, const double* 
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// Davidson solver (host control flow in C++; algorithm of xtddft_b200/davidson.py / the reference's utils/Davidson.py:21-298)
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+struct DavBuf {
+  double* d = nullptr;
+  int alloc(size_t n) { XTD_CUDA(cudaMalloc((void**)&d, std::max<size_t>(n, 2) * 8)); return XTD_OK; }
+  ~DavBuf() { if (d) cudaFree(d); }
+};
+struct DavPinned {
+  double* p = nullptr;
+  int alloc(size_t n) { XTD_CUDA(cudaMallocHost((void**)&p, std::max<size_t>(n, 2) * 8)); return XTD_OK; }
+  ~DavPinned() { if (p) cudaFreeHost(p); }
+};
+}  // namespace
+
+extern "C" int xtd_davidson(xtd_handle h, int nroots, const xtd_solver_opts* o, const double* hdiag_dev, const double* x0_dev, int n0,
+                            double* e_host, double* x_dev, int* conv_host, int* ncycle, int* nsigma_out) {
+  XTD_REQUIRE(h && h->finalized && o && hdiag_dev && x0_dev && e_host && x_dev && conv_host, XTD_ERR_ARG, "xtd_davidson: bad arguments");
+  const long dim = h->ext_dim;
+  XTD_REQUIRE(nroots >= 1 && nroots <= dim && n0 >= 1, XTD_ERR_ARG, "xtd_davidson: nroots %d / initial vectors %d", nroots, n0);
+  cudaStream_t s = h->stream;
+  const double tol = o->tol, toloose = o->tol_residual > 0.0 ? o->tol_residual : std::sqrt(o->tol), lindep = o->lindep;
+  const int max_space = o->max_space + (nroots - 1) * 4;
+  const int cap = max_space + nroots + 40;
+  const int nxt = std::max(std::max(n0, nroots), 40);
+  DavBuf xs, ax, xt, axt, ritz, aritz, tmp, gdev, cdev, ndev, sdev;
+  XTD_TRY(xs.alloc((size_t)cap * dim)); XTD_TRY(ax.alloc((size_t)cap * dim)); XTD_TRY(xt.alloc((size_t)nxt * dim));
+  XTD_TRY(ritz.alloc((size_t)nroots * dim)); XTD_TRY(aritz.alloc((size_t)nroots * dim)); XTD_TRY(tmp.alloc((size_t)nxt * dim));
+  XTD_TRY(axt.alloc((size_t)nxt * dim));       // sigma lands in a FIXED buffer: (nvec, z, hz) then repeat and the call replays as a CUDA graph
+  XTD_TRY(gdev.alloc((size_t)cap * cap)); XTD_TRY(cdev.alloc((size_t)cap * cap)); XTD_TRY(ndev.alloc(cap)); XTD_TRY(sdev.alloc(cap));
+  DavPinned gh;
+  XTD_TRY(gh.alloc((size_t)cap * cap));
+  XTD_CUDA(cudaMemcpyAsync(xt.d, x0_dev, (size_t)n0 * dim * 8, cudaMemcpyDeviceToDevice, s));
+  int nt = n0;
+
+  auto rows = [&](DavBuf& b, long r) { return b.d + r * dim; };
+  auto fetch = [&](const double* dev, size_t n) -> int {          // device -> pinned host, synchronous
+    XTD_CUDA(cudaMemcpyAsync(gh.p, dev, n * 8, cudaMemcpyDeviceToHost, s));
+    XTD_CUDA(cudaStreamSynchronize(s));
+    return XTD_OK;
+  };
+  auto dots = [&](const double* a, int m, const double* b, int k) -> int {      // gh.p[m][k] = <a_i, b_j>
+    XTD_TRY(xtd_vec_dots(s, gdev.d, k, a, dim, m, b, dim, k, dim));
+    return fetch(gdev.d, (size_t)m * k);
+  };
+  auto lincomb = [&](double* y, const double* x, const double* c_host, int m, int k, double beta) -> int {
+    XTD_CUDA(cudaMemcpyAsync(cdev.d, c_host, (size_t)m * std::max(k, 1) * 8, cudaMemcpyHostToDevice, s));
+    // (c_host is overwritten only after a later synchronising fetch, or is a live vector: the pageable copy is staged at once)
+    return xtd_vec_lincomb(s, y, dim, x, dim, cdev.d, std::max(k, 1), m, k, dim, beta);
+  };
+  auto transform = [&](double* work, int n_in, const std::vector<double>& t, int n_out) -> int {      // work[:n_out] = t work[:n_in]
+    if (n_out == 0) return XTD_OK;
+    XTD_TRY(lincomb(tmp.d, work, t.data(), n_out, n_in, 0.0));
+    XTD_CUDA(cudaMemcpyAsync(work, tmp.d, (size_t)n_out * dim * 8, cudaMemcpyDeviceToDevice, s));
+    return XTD_OK;
+  };
+  std::vector<double> tco;
+  auto orthonormalise = [&](double* work, int n_in, int* n_out) -> int {
+    int nv = n_in;
+    for (int it = 0; it < 2 && nv > 0; ++it) {
+      XTD_TRY(dots(work, nv, work, nv));
+      const int nk = gs_coefficients(gh.p, nv, lindep, tco);
+      XTD_TRY(transform(work, nv, tco, nk));
+      nv = nk;
+    }
+    *n_out = nv;
+    return XTD_OK;
+  };
+  auto sigma = [&](const double* z, double* hz, int n) -> int {
+    for (int x0 = 0; x0 < n; x0 += h->max_nvec) {
+      const int nx = std::min(h->max_nvec, n - x0);
+      if (!o->allreduce) {
+        XTD_TRY(xtd_sigma(h, nx, z + (long)x0 * dim, hz + (long)x0 * dim));
+      } else {
+        XTD_TRY(xtd_sigma_partial(h, nx, z + (long)x0 * dim));
+        double* part = nullptr;
+        long np_ = 0;
+        XTD_TRY(xtd_partial_buffer(h, nx, &part, &np_));
+        XTD_REQUIRE(o->allreduce(o->allreduce_ctx, part, np_) == 0, XTD_ERR_CUDA, "xtd_davidson: the all-reduce callback failed");
+        XTD_TRY(xtd_sigma_finish(h, nx, hz + (long)x0 * dim));
+      }
+    }
+    return XTD_OK;
+  };
+
+  std::vector<double> heff((size_t)cap * cap, 0.0), hsub, w, e, elast, v, vlast, de, dxn, sel;
+  std::vector<char> conv, conv_last;
+  bool fresh = true, xt_orth = false;
+  int space = 0, nsigma = 0, nritz = 0, icyc = 0, vrows = 0, vlast_rows = 0;
+  for (icyc = 0; icyc < o->max_cycle; ++icyc) {
+    if (fresh) {
+      space = 0;
+      XTD_TRY(orthonormalise(xt.d, nt, &nt));
+      XTD_REQUIRE(nt > 0, XTD_ERR_ARG, "xtd_davidson: %s", icyc == 0 ? "initial guess is empty or zero" : "no more linearly independent basis vectors");
+    } else if (nt > 1 && !xt_orth) {
+      XTD_TRY(orthonormalise(xt.d, nt, &nt));
+      nt = std::min(nt, 40);
+    }
+    xt_orth = false;
+    XTD_REQUIRE(nt > 0, XTD_ERR_ARG, "xtd_davidson: no linearly independent basis found");
+    XTD_REQUIRE(space + nt <= cap, XTD_ERR_STATE, "xtd_davidson: subspace overflow");
+    XTD_TRY(sigma(xt.d, axt.d, nt));
+    XTD_CUDA(cudaMemcpyAsync(rows(ax, space), axt.d, (size_t)nt * dim * 8, cudaMemcpyDeviceToDevice, s));
+    XTD_CUDA(cudaMemcpyAsync(rows(xs, space), xt.d, (size_t)nt * dim * 8, cudaMemcpyDeviceToDevice, s));
+    nsigma += nt;
+    const int head = space;
+    space += nt;
+    elast = e; vlast = v; vlast_rows = vrows; conv_last = conv;
+    // projected matrix: new rows / columns from one Gram product
+    XTD_TRY(dots(rows(xs, head), nt, ax.d, space));
+    for (int ip = 0; ip < nt; ++ip) {
+      for (int jp = 0; jp < ip; ++jp) heff[(size_t)(head + ip) * cap + head + jp] = heff[(size_t)(head + jp) * cap + head + ip] = gh.p[(size_t)ip * space + head + jp];
+      heff[(size_t)(head + ip) * cap + head + ip] = gh.p[(size_t)ip * space + head + ip];
+      for (int j = 0; j < head; ++j) heff[(size_t)(head + ip) * cap + j] = heff[(size_t)j * cap + head + ip] = gh.p[(size_t)ip * space + j];
+    }
+    hsub.assign((size_t)space * space, 0.0);
+    for (int i = 0; i < space; ++i)
+      for (int j = 0; j < space; ++j) hsub[(size_t)i * space + j] = heff[(size_t)i * cap + j];
+    XTD_REQUIRE(sym_eig(hsub, space, w) == 0, XTD_ERR_STATE, "xtd_davidson: the projected eigenproblem did not converge");
+    // pick: positive eigenvalues only (XTDA.py:769-772), then the lowest nroots
+    std::vector<int> idx;
+    for (int k = 0; k < space; ++k)
+      if (!o->pick_positive || w[k] > 1e-3) idx.push_back(k);
+    XTD_REQUIRE(!idx.empty(), XTD_ERR_STATE, "xtd_davidson: not enough eigenvalues");
+    nritz = std::min<int>(nroots, (int)idx.size());
+    e.assign(nritz, 0.0);
+    v.assign((size_t)space * nritz, 0.0);
+    vrows = space;
+    for (int k = 0; k < nritz; ++k) {
+      e[k] = w[idx[k]];
+      for (int r = 0; r < space; ++r) v[(size_t)r * nritz + k] = hsub[(size_t)r * space + idx[k]];
+    }
+    conv.assign(nritz, 0);
+    if (!fresh && !elast.empty()) {
+      // `_sort_elast`: match the previous roots to the new ones by the overlap of their subspace coefficients
+      const int nprev = (int)elast.size();
+      std::vector<double> e2(nritz, 0.0);
+      std::vector<char> c2(nritz, 0);
+      for (int k = 0; k < nritz; ++k) {
+        int best = 0;
+        double bo = -1.0;
+        bool found = false;
+        for (int q = 0; q < nprev; ++q) {
+          double ov = 0.0;
+          for (int r = 0; r < vlast_rows; ++r) ov += v[(size_t)r * nritz + k] * vlast[(size_t)r * nprev + q];
+          ov = std::fabs(ov);
+          if (ov > bo) { bo = ov; best = q; }
+          if (ov > 0.5) found = true;
+        }
+        e2[k] = found ? elast[best] : 0.0;
+        c2[k] = found ? conv_last[best] : 0;
+      }
+      elast = e2; conv_last = c2;
+    }
+    de.assign(nritz, 0.0);
+    for (int k = 0; k < nritz; ++k) de[k] = ((int)elast.size() == nritz) ? e[k] - elast[k] : e[k];
+    // Ritz vectors, their images, residuals
+    {
+      std::vector<double> vt((size_t)nritz * space);
+      for (int k = 0; k < nritz; ++k)
+        for (int r = 0; r < space; ++r) vt[(size_t)k * space + r] = v[(size_t)r * nritz + k];
+      XTD_TRY(lincomb(ritz.d, xs.d, vt.data(), nritz, space, 0.0));
+      XTD_CUDA(cudaStreamSynchronize(s));                 // vt is reused by the second upload
+      XTD_TRY(lincomb(aritz.d, ax.d, vt.data(), nritz, space, 0.0));
+      XTD_CUDA(cudaMemcpyAsync(sdev.d, e.data(), (size_t)nritz * 8, cudaMemcpyHostToDevice, s));
+      XTD_TRY(xtd_vec_residual(s, xt.d, aritz.d, ritz.d, dim, sdev.d, ndev.d, nritz, dim));
+      XTD_TRY(fetch(ndev.d, nritz));
+    }
+    dxn.assign(nritz, 0.0);
+    bool all_conv = true;
+    for (int k = 0; k < nritz; ++k) {
+      dxn[k] = std::sqrt(gh.p[k]);
+      conv[k] = (std::fabs(de[k]) < tol && dxn[k] < toloose) ? 1 : 0;
+      all_conv = all_conv && conv[k];
+    }
+    if (all_conv) { ++icyc; break; }
+    // precondition the unconverged residuals, normalise, project against the subspace, drop dependent ones
+    std::vector<int> keep;
+    for (int k = 0; k < nritz; ++k)
+      if (!conv[k] && dxn[k] * dxn[k] > lindep) keep.push_back(k);
+    for (size_t dst = 0; dst < keep.size(); ++dst)
+      if ((int)dst != keep[dst]) XTD_CUDA(cudaMemcpyAsync(rows(xt, (long)dst), rows(xt, keep[dst]), (size_t)dim * 8, cudaMemcpyDeviceToDevice, s));
+    nt = (int)keep.size();
+    if (nt) {
+      std::vector<double> shift(nt, e[0] - o->level_shift);
+      XTD_CUDA(cudaMemcpyAsync(sdev.d, shift.data(), (size_t)nt * 8, cudaMemcpyHostToDevice, s));
+      XTD_CUDA(cudaStreamSynchronize(s));
+      XTD_TRY(xtd_vec_precond(s, xt.d, dim, hdiag_dev, sdev.d, ndev.d, nt, dim));
+      dav_rsqrt_kernel<<<1, 64, 0, s>>>(ndev.d, ndev.d, nt);
+      LAUNCH_CHECK();
+      XTD_TRY(xtd_vec_scale(s, xt.d, dim, ndev.d, nt, dim));
+      XTD_TRY(xtd_vec_dots(s, gdev.d, space, xt.d, dim, nt, xs.d, dim, space, dim));
+      dav_negate_kernel<<<(unsigned)cdiv((long)nt * space, 256), 256, 0, s>>>(gdev.d, (long)nt * space);
+      LAUNCH_CHECK();
+      XTD_TRY(xtd_vec_lincomb(s, xt.d, dim, xs.d, dim, gdev.d, space, nt, space, dim, 1.0));
+      // one Gram matrix: `_normalize_xt_` filter (diagonal), normalisation, first Gram-Schmidt pass of the next cycle's `_qr`
+      XTD_TRY(dots(xt.d, nt, xt.d, nt));
+      std::vector<int> good;
+      for (int k = 0; k < nt; ++k)
+        if (gh.p[(size_t)k * nt + k] > lindep) good.push_back(k);
+      const int ng = (int)good.size();
+      if (ng) {
+        std::vector<double> inv(ng);
+        for (int a = 0; a < ng; ++a) inv[a] = 1.0 / std::sqrt(gh.p[(size_t)good[a] * nt + good[a]]);
+        const bool will_restart = space + nroots > max_space;
+        if (ng > 1 && !will_restart) {
+          std::vector<double> gs((size_t)ng * ng);
+          for (int a = 0; a < ng; ++a)
+            for (int b = 0; b < ng; ++b) gs[(size_t)a * ng + b] = gh.p[(size_t)good[a] * nt + good[b]] * inv[a] * inv[b];
+          std::vector<double> t1;
+          const int n1 = gs_coefficients(gs.data(), ng, lindep, t1);
+          sel.assign((size_t)n1 * nt, 0.0);                 // t1 composed with the selection / normalisation
+          for (int r = 0; r < n1; ++r)
+            for (int a = 0; a < ng; ++a) sel[(size_t)r * nt + good[a]] = t1[(size_t)r * ng + a] * inv[a];
+          XTD_TRY(transform(xt.d, nt, sel, n1));
+          XTD_CUDA(cudaStreamSynchronize(s));
+          nt = n1;
+          if (nt > 1) {
+            XTD_TRY(dots(xt.d, nt, xt.d, nt));
+            const int n2 = gs_coefficients(gh.p, nt, lindep, tco);
+            XTD_TRY(transform(xt.d, nt, tco, n2));
+            XTD_CUDA(cudaStreamSynchronize(s));
+            nt = n2;
+          }
+          nt = std::min(nt, 40);
+          xt_orth = true;
+        } else {
+          sel.assign((size_t)ng * nt, 0.0);
+          for (int a = 0; a < ng; ++a) sel[(size_t)a * nt + good[a]] = inv[a];
+          XTD_TRY(transform(xt.d, nt, sel, ng));
+          XTD_CUDA(cudaStreamSynchronize(s));
+          nt = ng;
+        }
+      } else {
+        nt = 0;
+      }
+    }
+    if (nt == 0) {
+      for (int k = 0; k < nritz; ++k) conv[k] = dxn[k] < toloose ? 1 : 0;
+      ++icyc;
+      break;
+    }
+    fresh = space + nroots > max_space;
+    if (fresh) {
+      XTD_CUDA(cudaMemcpyAsync(xt.d, ritz.d, (size_t)nritz * dim * 8, cudaMemcpyDeviceToDevice, s));
+      nt = nritz;
+    }
+  }
+  for (int k = 0; k < nroots; ++k) {
+    e_host[k] = k < nritz ? e[k] : 0.0;
+    conv_host[k] = k < nritz ? (int)conv[k] : 0;
+  }
+  XTD_CUDA(cudaMemcpyAsync(x_dev, ritz.d, (size_t)nritz * dim * 8, cudaMemcpyDeviceToDevice, s));
+  XTD_CUDA(cudaStreamSynchronize(s));
+  if (ncycle) *ncycle = std::min(icyc, o->max_cycle);
+  if (nsigma_out) *nsigma_out = nsigma;
+  return nritz;
+}

@@ -56,11 +56,20 @@ def timed_engine(tc: Optional[TimeCounter], plan, p, **kw) -> SigmaEngine:
 
 def solve(eng: SigmaEngine, nstates: int, settings: str, x0=None, tc: Optional[TimeCounter] = None, verbose: int = 0, **over):
     cfg = dict(dav.SOLVER[settings])
-    cfg.update(over)
+    cfg.update({k: v for k, v in over.items() if k != "python_solver"})
     hdiag = eng.hdiag()
     nroots = min(nstates, hdiag.size)
     if x0 is None:
         x0 = dav.init_guess(hdiag, nroots, cfg["window"])
+    if eng.ext_dim < dav.NATIVE_MAX_DIM and not verbose and not over.get("python_solver"):
+        # launch-bound molecules: the solver loop runs inside libxtdsigma (xtd_davidson)
+        t0 = time.perf_counter()
+        conv, e, x, cyc = dav.davidson_native(eng, np.asarray(x0), hdiag, nroots, tol=cfg["tol"], tol_residual=cfg["tol_residual"],
+                                              lindep=cfg["lindep"], max_cycle=cfg["max_cycle"], level_shift=cfg["level_shift"],
+                                              pick_positive=cfg["pick_positive"])
+        if tc is not None:
+            tc.dv = time.perf_counter() - t0
+        return conv, e, np.array(x).T, cyc, hdiag
     aop = eng.sigma
     detailed = tc is not None and eng.ext_dim >= 50000
     if detailed:
