@@ -239,10 +239,13 @@ def test_engine_emulated_block_weighted_exchange(torch_cuda, monkeypatch, nc, no
 
 @pytest.mark.parametrize("method", ["xtda", "sf_mcol"])
 @pytest.mark.parametrize("restricted", [True, False])
-def test_engine_emulated_split_gradient_grid_path(torch_cuda, monkeypatch, method, restricted):
+@pytest.mark.parametrize("short_k", ["0", "512"])
+def test_engine_emulated_split_gradient_grid_path(torch_cuda, monkeypatch, method, restricted, short_k):
     """Value + gradient kernels (UKS GGA of X-TDA on two channels, multicollinear GGA spin flip) in the split-gradient form with
     its four value GEMMs on the INT8 tensor cores (two of them batched over the trial vectors), two grid chunks with a ragged
-    last block; the streaming kernel between them is the fp64 one."""
+    last block; the streaming kernel between them is the fp64 one.  short_k = 512 (the default): the occupied-side forward GEMM,
+    whose contraction length is the occupied count, stays on the DMMA GEMM; short_k = 0 forces all four onto the INT8 kernel."""
+    monkeypatch.setenv("XTD_OZ_SHORT_K", short_k)
     from oracle import sigma as osig
     from xtddft_b200 import plan as planmod
     from xtddft_b200.engine import SigmaEngine

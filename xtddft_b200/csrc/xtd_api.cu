@@ -99,6 +99,12 @@ struct Channel {
 };
 
 constexpr long XC_SPLIT_SMEM_MAX = 200 * 1024;   // shared memory of the split-gradient streaming kernel (MO values of one point)
+// contraction lengths below this stay on the FP64 DMMA GEMM where a kernel offers the choice (XTD_OZ_SHORT_K overrides; tests use 0)
+static int oz_short_k() {
+  const char* e = getenv("XTD_OZ_SHORT_K");
+  return e ? atoi(e) : 512;
+}
+#define OZ_SHORT_K (oz_short_k())
 constexpr int OZ_XC_KQ = 8192;   // grid points per int32 accumulation group of the backward grid GEMM (8192 * S * 2^14 < 2^31)
 constexpr int NARROW_MAX = 16;   // widest first virtual block that takes the narrow-output exchange pass
 
@@ -401,11 +407,13 @@ int grid_commit(xtd_engine* h) {
           // ... and of the value component of phi (occupied side of the split-gradient form)
           c->ozOF.set((int)h->ng, OZ_BM, c->no);
           c->ozOB.set(c->no, OZ_BM, OZ_XC_KQ);
-          XTD_CUDA(cudaMalloc((void**)&c->phiF, c->ozOF.slice_bytes(1, S)));
-          XTD_CUDA(cudaMalloc((void**)&c->phiFs, c->ozOF.scale_doubles(1, 1) * 8));
+          if (c->no >= OZ_SHORT_K) {
+            XTD_CUDA(cudaMalloc((void**)&c->phiF, c->ozOF.slice_bytes(1, S)));
+            XTD_CUDA(cudaMalloc((void**)&c->phiFs, c->ozOF.scale_doubles(1, 1) * 8));
+          }
           XTD_CUDA(cudaMalloc((void**)&c->phiB, c->ozOB.slice_bytes(nqg, S)));
           XTD_CUDA(cudaMalloc((void**)&c->phiBs, c->ozOB.scale_doubles(nqg, 1) * 8));
-          XTD_TRY(oz_slice(S, c->phiF, c->phiFs, c->ozOF, c->phi.p, c->ldphi, 0, 1, 1, s));
+          if (c->no >= OZ_SHORT_K) XTD_TRY(oz_slice(S, c->phiF, c->phiFs, c->ozOF, c->phi.p, c->ldphi, 0, 1, 1, s));
           XTD_TRY(oz_slice(S, c->phiB, c->phiBs, c->ozOB, c->phi.p, c->ldphi, (long)OZ_XC_KQ * c->ldphi, (int)nqg, 1, s, true, h->ng));
         }
         XTD_CUDA(cudaStreamSynchronize(s));
@@ -1318,7 +1326,7 @@ static int run_xc_split_emulated(xtd_engine* h, int nvec) {
     for (int c = 0; c < nch; ++c) {
       Channel* ch = h->ch[c];
       XTD_TRY(oz_slice(S, zS[c], zsc[c], shZ[c], h->Z[c], ch->ldz, 0, 1, 1, s));
-      XTD_TRY(oz_slice(S, ztS[c], ztsc[c], shZt[c], h->ZT[c], ch->ldzt, (long)ch->nv * ch->ldzt, nvec, 1, s));
+      if (ch->no >= OZ_SHORT_K) XTD_TRY(oz_slice(S, ztS[c], ztsc[c], shZt[c], h->ZT[c], ch->ldzt, (long)ch->nv * ch->ldzt, nvec, 1, s));
     }
   }
   for (long g0 = 0; g0 < h->ng; g0 += GB) {
@@ -1336,6 +1344,20 @@ static int run_xc_split_emulated(xtd_engine* h, int nvec) {
         p.nmt = nmt_g; p.nnt = shZ[c].nrt; p.nkb = ch->ozPF.nkb; p.nq = 1; p.group = 1; p.b_q0 = 0;
         p.Mpad = (int)mpad_g; p.Npad = shZ[c].rows_pad; p.splits = 1; p.W = Y[c]; p.alpha = 1.0;
         XTD_TRY(oz_gemm(S, p, s));
+        h->gemm.flops += 2.0 * gb * (double)(nvec * ch->no) * ch->nv;
+        if (ch->no < OZ_SHORT_K) {
+          // F2 has the occupied count as its contraction length: a few k-steps per tile, where the INT8 kernel is all epilogue
+          // (measured at no = 137: 7.4 ms per 40 960-point chunk against 5.4 ms on the DMMA GEMM) -- keep it on FP64 DMMA
+          GemmDesc e;
+          e.b_kc = false;
+          e.A = view2d(ch->phi.p, ch->ldphi, gb, ch->no, (int)g0, 0);
+          e.B = view3d(h->Z[c], ch->ldz, (long)ch->no * ch->ldz, nvec, ch->no, ch->nv);
+          e.M = gb; e.N = ch->nv; e.K = ch->no; e.batches = nvec; e.z_div = 1; e.a_hi = 0; e.b_hi = 1;
+          e.C = T[c]; e.ldc = shZt[c].rows_pad; e.c_batch_stride = mpad_g * shZt[c].rows_pad;
+          XTD_TRY(gemm(h->gemm, e, s));
+          h->gemm.flops += 2.0 * gb * (double)(nvec * ch->no) * ch->nv;
+          continue;
+        }
         OzGemmParams q;                       // F2, one batch per trial vector
         q.A = ch->phiF + (size_t)(g0 / OZ_BM) * ch->ozOF.nkb * S * (OZ_BM * OZ_KB);
         q.B = ztS[c]; q.sa = ch->phiFs + g0; q.sb = ztsc[c];
@@ -1344,7 +1366,7 @@ static int run_xc_split_emulated(xtd_engine* h, int nvec) {
         q.batches = nvec; q.b_bstride = (long)shZt[c].slice_bytes(1, S); q.sb_bstride = shZt[c].rows_pad;
         q.w_bstride = mpad_g * shZt[c].rows_pad;
         XTD_TRY(oz_gemm(S, q, s));
-        h->gemm.flops += 4.0 * gb * (double)(nvec * ch->no) * ch->nv;
+        h->gemm.flops += 2.0 * gb * (double)(nvec * ch->no) * ch->nv;
       }
     }
     {
