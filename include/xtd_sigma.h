@@ -154,6 +154,11 @@ typedef struct {
 int xtd_davidson(xtd_handle h, int nroots, const xtd_solver_opts* opts, const double* hdiag_dev, const double* x0_dev, int n0,
                  double* e_host, double* x_dev, int* conv_host, int* ncycle, int* nsigma);
 
+/* host-only pieces of xtd_davidson, exported for the CPU test suite: eigen-decomposition of a symmetric n x n matrix (row-major in,
+ * eigenvectors in the columns out, eigenvalues ascending) and Gram-Schmidt coefficients from a Gram matrix (returns the rows kept) */
+int xtd_host_sym_eig(double* a, int n, double* w);
+int xtd_host_gs_coefficients(const double* g, int n, double lindep, double* t_out);
+
 /* plain GEMM entry (tests / benchmarks of the DMMA kernel): C[M,N] = alpha * A[M,K] * B[N,K]^T */
 int xtd_dgemm_tn(void* stream, int m, int n, int k, double alpha, const double* a_dev, long lda, const double* b_dev, long ldb,
                  double* c_dev, long ldc, int accumulate);

@@ -75,6 +75,8 @@ SIGNATURES = {
     "xtd_vec_precond": (_I, [_P, _P, _L, _P, _P, _P, _I, _L]),
     "xtd_vec_scale": (_I, [_P, _P, _L, _P, _I, _L]),
     "xtd_davidson": (_I, [_P, _I, C.POINTER(XtdSolverOpts), _P, _P, _I, _P, _P, _P, C.POINTER(_I), C.POINTER(_I)]),
+    "xtd_host_sym_eig": (_I, [_P, _I, _P]),
+    "xtd_host_gs_coefficients": (_I, [_P, _I, _D, _P]),
     "xtd_dgemm_tn": (_I, [_P, _I, _I, _I, _D, _P, _L, _P, _L, _P, _L, _I]),
     "xtd_dgemm": (_I, [_P, _I, _I, _I, _D, _P, _L, _I, _P, _L, _I, _P, _L, _I]),
     "xtd_ozaki_gemm": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _L, _L, _P, _L, _L, _P, _L, _D, _I, _P]),

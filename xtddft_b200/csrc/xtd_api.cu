@@ -2627,3 +2627,21 @@ extern "C" int xtd_davidson(xtd_handle h, int nroots, const xtd_solver_opts* o, 
   if (nsigma_out) *nsigma_out = nsigma;
   return nritz;
 }
+
+// Host-only pieces of the native solver, exported so the CPU test suite can hold them to NumPy (no device needed):
+// symmetric eigenproblem (a[n][n] row-major in, eigenvectors in columns out, w ascending) and the Gram-Schmidt coefficients.
+extern "C" int xtd_host_sym_eig(double* a, int n, double* w) {
+  XTD_REQUIRE(a && w && n >= 1, XTD_ERR_ARG, "xtd_host_sym_eig: bad arguments");
+  std::vector<double> m(a, a + (size_t)n * n), ev;
+  XTD_REQUIRE(sym_eig(m, n, ev) == 0, XTD_ERR_STATE, "xtd_host_sym_eig: no convergence");
+  std::copy(m.begin(), m.end(), a);
+  std::copy(ev.begin(), ev.end(), w);
+  return XTD_OK;
+}
+extern "C" int xtd_host_gs_coefficients(const double* g, int n, double lindep, double* t_out) {
+  XTD_REQUIRE(g && t_out && n >= 1, XTD_ERR_ARG, "xtd_host_gs_coefficients: bad arguments");
+  std::vector<double> t;
+  const int nk = gs_coefficients(g, n, lindep, t);
+  std::copy(t.begin(), t.end(), t_out);
+  return nk;
+}
