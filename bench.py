@@ -169,6 +169,9 @@ def cpu_reference_rate(dp, nvec_sample: int = 1, target_s: float = 20.0):
     naux_s = int(max(1, min(dp.naux, (target_s * 0.6) / max(per_aux * ndens, 1e-9))))
     per_g = 4.0 * n ** 2 * (2 if dp.nvar == 4 else 1) / 1e9 / max(gf, 1.0)
     ng_s = int(max(64, min(dp.ng, (target_s * 0.3) / max(per_g * (2 if dp.method == "xtda" else 1), 1e-9))))
+    # the sample itself must stay cheap to generate and to hold on the host (seeded NumPy arrays): <= 8 GiB of tensor, <= 4 GiB of AO values
+    naux_s = int(min(naux_s, max(1, (8 << 30) // (8 * n * n))))
+    ng_s = int(min(ng_s, max(64, (4 << 30) // (8 * n * max(dp.nvar, 1)))))
     full = naux_s == dp.naux and ng_s == dp.ng
     ps = host_sample(dp, naux_s, ng_s)
     vind, hd = oracle_vind_for(ps, dp.method)
@@ -226,8 +229,9 @@ def run_reference(args):
     """`--impl reference`: the reference's CPU implementation of the path.  PySCF is not installable here (no wheel,
     no network) and the reference tree does not import without it (`baseline/_ref` and `import pyscf` are probed and
     reported), so this arm times the oracle port (kind "port") on ALL host cores -- the BLAS thread count is set explicitly,
-    whatever OMP_NUM_THREADS the launcher exported.  One measurement with a ~60 s budget: a full-size sigma vector when it
-    fits (configs 1, 2), else a sample of the aux functions / grid points extrapolated linearly (`extrapolated: true`);
+    whatever OMP_NUM_THREADS the launcher exported.  One measurement with a ~30 s budget of CPU work (and a sample that
+    stays below 12 GiB of host memory): a full-size sigma vector when it fits (configs 1, 2), else a sample of the aux
+    functions / grid points extrapolated linearly (`extrapolated: true`);
     `--steps` / `--warmup` do not repeat a minute-long CPU run."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -236,7 +240,7 @@ def run_reference(args):
     from xtddft_b200.workloads import plan_for
     dp = make_device_problem(args.config, args.scale)
     nvec = args.nvec or dp.nroots
-    cb = cpu_reference_rate(dp, 1, target_s=float(os.environ.get("XTD_REF_BUDGET_S", "60")))
+    cb = cpu_reference_rate(dp, 1, target_s=float(os.environ.get("XTD_REF_BUDGET_S", "30")))
     v = float(cb["value"])
     have_pyscf = False
     try:

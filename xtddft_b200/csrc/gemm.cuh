@@ -476,7 +476,7 @@ inline int gemm(GemmContext& ctx, const GemmDesc& d, cudaStream_t stream) {
     // i.e. trade wave quantisation on 148 SMs against pipeline fill / epilogue / partial-sum traffic.
     const long tiles = (long)tm * tn * d.batches;
     const double ovh = 4.0;
-    long max_s = total_it / 32;
+    long max_s = total_it / 64;      // (a split costs a second launch for the reduction: not worth it below ~64 iterations per unit)
     if (max_s > 64) max_s = 64;
     if (max_s > 65535 / d.batches) max_s = 65535 / d.batches;
     if (max_s < 1) max_s = 1;
