@@ -111,3 +111,34 @@ def test_shards_sum_to_whole(torch_cuda):
         e.close()
     assert (acc - whole).abs().max().item() <= 1e-11 * max(1.0, whole.abs().max().item())
     assert torch.isfinite(full).all()
+
+
+@pytest.mark.parametrize("cfg", [5, 3, 4])
+def test_emulated_path_against_fp64_path_at_full_size(torch_cuda, cfg):
+    """The engine's default at BASELINE sizes (contractions emulated on the INT8 tensor cores, 6 digit planes) against the FP64 DMMA
+    path on the SAME full-size inputs: sigma vectors must agree far inside the 1e-9 tolerance.  The two engines are built one after
+    the other (config 5 holds 123 GB of fp64 tensor blocks on the FP64 path)."""
+    torch = torch_cuda
+    free, _ = torch.cuda.mem_get_info()
+    if cfg == 5 and free < 160 << 30:
+        pytest.skip("needs ~160 GB free HBM")
+    from xtddft_b200.synth_device import make_device_problem
+    from xtddft_b200.workloads import default_workspace_bytes, engine_for_device_problem
+    out = {}
+    z = None
+    for slices in (0, 6):
+        torch.cuda.empty_cache()
+        dp = make_device_problem(cfg, 1.0)
+        eng = engine_for_device_problem(dp, max_nvec=4, workspace_bytes=min(default_workspace_bytes(dp, 1), 16 << 30), exchange_slices=slices)
+        try:
+            if z is None:
+                z = _rand(torch, 3, eng.ext_dim, 21)
+            out[slices] = eng.sigma(z).cpu()
+            assert eng.exchange_slices == slices
+        finally:
+            eng.close()
+            del eng
+            torch.cuda.empty_cache()
+    ref, got = out[0], out[6]
+    err = (got - ref).abs().max().item() / max(1.0, ref.abs().max().item())
+    assert err < 1e-10, err
