@@ -530,7 +530,10 @@ def main():
         "metric": "davidson_sigma_vectors_per_s", "value": value, "unit": "sigma-vectors/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": config_dict(dp, nvec, dim, world),
+        "config": dict(config_dict(dp, nvec, dim, world),
+                       contraction_arithmetic=(f"fp64 in / fp64 out; dense contractions emulated on the INT8 tensor cores: {xs_on} balanced radix-256 digit "
+                                               "planes per operand, exact int32 accumulation, fp64 recombination (sigma equal to the FP64 DMMA path to "
+                                               "~4e-16 relative at this size)") if xs_on else "fp64 (DMMA tensor-core GEMM)"),
         "clocks": clocks,
         "e2e": {"value": nvec / e2e_s, "unit": "sigma-vectors/s", "h2d_bytes_per_step": nvec * dim * 8, "d2h_bytes_per_step": nvec * dim * 8},
         "gpu_launches": int(launches),
