@@ -26,7 +26,7 @@ extern "C" {
 typedef struct xtd_engine* xtd_handle;
 
 enum { XTD_FXC_NONE = 0, XTD_FXC_UKS = 1, XTD_FXC_ALDA0 = 2, XTD_FXC_MCOL = 3, XTD_FXC_UKS_TAU = 4, XTD_FXC_MCOL_TAU = 5 };
-enum { XTD_SIDE_RIGHT = 0, XTD_SIDE_LEFT = 1 };
+enum { XTD_SIDE_RIGHT = 0, XTD_SIDE_LEFT = 1, XTD_SIDE_LEFT_T = 2, XTD_SIDE_RIGHT_T = 3 };
 
 typedef struct {
   double flops_gemm;          /* useful FP64 flops issued through the DMMA GEMM since the last reset */
@@ -61,6 +61,12 @@ int xtd_channel_layout(xtd_handle h, int ch, int nvec, long* base, long* vec_str
  * in aux chunks: L[np, nao, nao] (ld_row, stride_p) or lower-triangular packed rows (packed=1, stride_p).
  * The chunk is transformed to the MO blocks each term needs and is not kept. */
 int xtd_add_kterm(xtd_handle h, int tensor, int ch, const double* weights_host, int nob, int nvb);
+/* Exchange of the TRANSPOSED trial density -- the B-matrix-type term that the hermi = 1 response of the Z-vector / coupled-perturbed
+ * operator adds to the direct term above (`vresp(dm + dm.T)`, grad_hb/tdroks_sfu.py:284-298, grad_hb/tduks_sfu.py:249-258):
+ *   sigma[i,a] += weight * sum_P sum_jb L^P_ib z_jb L^P_ja
+ * on the MO-resident occupied-virtual block of channel `ch` (kept as Lov[P][i][a]); 4 naux no^2 nv flops per vector.  Declare
+ * before xtd_df_begin. */
+int xtd_add_kterm_t(xtd_handle h, int tensor, int ch, double weight);
 int xtd_add_jblock(xtd_handle h, int ch, int r0, int nr, int c0, int nc);
 int xtd_set_jmix(xtd_handle h, const double* mix_host, int n);
 /* Exchange contraction sigma += U . Lvv of uniform-weight terms: slices = 0 (default) runs it as FP64 DMMA GEMMs; slices = 3..8
@@ -96,7 +102,11 @@ int xtd_grid_commit(xtd_handle h);
 
 /* local terms (Fock blocks, Delta-A couplings; XTDA.py:628-687, XSF_TDA.py:1146-1274):
  *   RIGHT: dst[r,c] += alpha * sum_b src[r,b] M[b,c]   M[mrows=k, mcols=nc]
- *   LEFT : dst[r,c] += alpha * sum_j M[r,j] src[j,c]   M[mrows=nr, mcols=k] */
+ *   LEFT : dst[r,c] += alpha * sum_j M[r,j] src[j,c]   M[mrows=nr, mcols=k]
+ * and with the source block entering TRANSPOSED (ROHF orbital-Hessian couplings between the open-virtual block of one spin and the
+ * closed-open block of the other, grad_hb/tdroks_sfu.py:310,319):
+ *   LEFT_T : dst[r,c] += alpha * sum_k M[r,k] src[c,k]   M[mrows=nr, mcols=k]
+ *   RIGHT_T: dst[r,c] += alpha * sum_j src[j,r] M[j,c]   M[mrows=k, mcols=nc] */
 int xtd_add_local_gemm(xtd_handle h, int side, int dst_ch, int r0, int nr, int c0, int nc, int src_ch, int sr0, int sc0,
                        const double* mat_host, int mrows, int mcols, double alpha);
 int xtd_add_rank1(xtd_handle h, int dst_ch, const double* u_host, int src_ch, const double* v_host); /* dense [no,nv] */

@@ -32,6 +32,11 @@ class PlanInterpreter:
                 L = self.tensors[kt.tensor]
                 self.loo[key] = es("Pmn,mi,nj->Pij", L, self.co[kt.ch], self.co[kt.ch])
                 self.lvv[key] = es("Pmn,ma,nb->Pab", L, self.cv[kt.ch], self.cv[kt.ch])
+        self.lov = {}
+        for kt in plan.kt_terms:
+            key = (kt.tensor, kt.ch)
+            if key not in self.lov:
+                self.lov[key] = es("Pmn,mi,na->Pia", self.tensors[kt.tensor], self.co[kt.ch], self.cv[kt.ch])
         self.ljb = []
         for jb in plan.j_blocks:
             co = self.co[jb.ch][:, jb.r0:jb.r0 + jb.nr]
@@ -90,6 +95,11 @@ class PlanInterpreter:
                             zt[:, j0:j0 + nj, b0:b0 + nbb] = kt.weights[ib, ab, jb, bb] * z[:, j0:j0 + nj, b0:b0 + nbb]
                     u = es("Pij,xjb->Pxib", loo[:, i0:i0 + ni, :], zt)
                     sig[kt.ch][:, i0:i0 + ni, a0:a0 + na] += es("Pxib,Pba->xia", u, lvv[:, :, a0:a0 + na])
+        # exchange of the transposed trial density (Z-vector plans)
+        for kt in plan.kt_terms:
+            lov = self.lov[(kt.tensor, kt.ch)]
+            w = es("Pib,xjb->Pxij", lov, zs[kt.ch])
+            sig[kt.ch] += kt.weight * es("Pxij,Pja->xia", w, lov)
         # Coulomb blocks
         if plan.j_blocks:
             rho = [es("Pia,xia->xP", self.ljb[k], zs[jb.ch][:, jb.r0:jb.r0 + jb.nr, jb.c0:jb.c0 + jb.nc])
@@ -134,7 +144,7 @@ class PlanInterpreter:
                     if tau:
                         a[k] += 0.5 * es("gx,go->gxo", wv[4], ph[k])
                 rt = es("cgxo,cgm->xom", a, p.ao)
-                sig[c] += es("xom,mv->xov", rt, self.cv[c])
+                sig[c] += plan.xc_scale * es("xom,mv->xov", rt, self.cv[c])
         return sig
 
     def add_local_blocks(self, zs, sig):
@@ -146,9 +156,16 @@ class PlanInterpreter:
             if lg.side == "R":
                 k = lg.mat.shape[0]
                 sig[dc][:, r0:r0 + nr, c0:c0 + ncol] += lg.alpha * es("xrb,bc->xrc", zs[sc][:, sr0:sr0 + nr, sc0:sc0 + k], lg.mat)
-            else:
+            elif lg.side == "L":
                 k = lg.mat.shape[1]
                 sig[dc][:, r0:r0 + nr, c0:c0 + ncol] += lg.alpha * es("rj,xjc->xrc", lg.mat, zs[sc][:, sr0:sr0 + k, sc0:sc0 + ncol])
+            elif lg.side == "LT":
+                k = lg.mat.shape[1]
+                sig[dc][:, r0:r0 + nr, c0:c0 + ncol] += lg.alpha * es("rk,xck->xrc", lg.mat, zs[sc][:, sr0:sr0 + ncol, sc0:sc0 + k])
+            else:
+                assert lg.side == "RT"
+                k = lg.mat.shape[0]
+                sig[dc][:, r0:r0 + nr, c0:c0 + ncol] += lg.alpha * es("xjr,jc->xrc", zs[sc][:, sr0:sr0 + k, sc0:sc0 + nr], lg.mat)
         for r1 in plan.rank1s:
             sig[r1.dst_ch] += es("x,ia->xia", es("ia,xia->x", r1.v, zs[r1.src_ch]), r1.u)
         for d in plan.diags:

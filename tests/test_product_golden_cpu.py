@@ -75,9 +75,10 @@ def test_xsf_init_guess(golden_dir, tag):
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/xtddft"), reason="the reference tree exists only in the build container")
 def test_goldens_regenerate_bit_for_bit(golden_dir, tmp_path):
-    """Re-run the reference's own code (make_golden.py, make_golden_properties.py) and diff against the committed files."""
+    """Re-run the reference's own code (make_golden.py, make_golden_properties.py, make_golden_zvector.py) and diff against the
+    committed files."""
     env = dict(os.environ, XTD_GOLDEN_OUT=str(tmp_path), OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1")
-    for script in ("make_golden.py", "make_golden_properties.py"):
+    for script in ("make_golden.py", "make_golden_properties.py", "make_golden_zvector.py"):
         res = subprocess.run([sys.executable, os.path.join(golden_dir, script)], env=env, capture_output=True, text=True, timeout=900)
         assert res.returncode == 0, res.stderr[-2000:]
     made = sorted(f for f in os.listdir(tmp_path) if f.endswith(".npz"))

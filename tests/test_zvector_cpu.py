@@ -1,0 +1,93 @@
+"""SURVEY 8f row f3 on the CPU: the oracle restatement of the Z-vector operator and right-hand side against the fixtures produced by the
+reference's own `grad_elec` functions (tests/golden/make_golden_zvector.py), the engine plan of the operator executed by the NumPy plan
+interpreter against the oracle, and the device solver's control flow (NumPy vector backend) against dense solves."""
+import copy
+import os
+
+import numpy as np
+import pytest
+
+from numpy_vectors import NumpyVectors
+from oracle import zvector as ozv
+from plan_interp import PlanInterpreter
+from xtddft_b200 import plan as planmod
+from xtddft_b200.synth import make_problem
+from xtddft_b200.zvector import solve_linear
+
+TAGS = ["roks_gga_no2", "roks_lda_no3", "roks_hf_no2", "uks_gga_no2", "uks_lda_pure_no2"]
+
+
+def load_case(golden_dir, tag):
+    d = np.load(os.path.join(golden_dir, f"zvector_{tag}.npz"), allow_pickle=False)
+    nc, no, nv, naux, ng, seed, restricted = [int(v) for v in d["params"]]
+    p = make_problem(nc + no + nv, nc, no, nv, naux, ng, xctype=str(d["xctype"]), hyb=float(d["hyb"]), restricted=bool(restricted), seed=seed)
+    return d, p
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / max(1.0, np.abs(b).max()))
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_oracle_against_the_reference_closures(golden_dir, tag):
+    d, p = load_case(golden_dir, tag)
+    v = d["amp"].reshape(p.nc, p.nv)
+    if p.restricted:
+        op, rhs = ozv.roks_matvec(p), ozv.roks_rhs(p, v)
+    else:
+        op = ozv.uks_fvind(p)
+        rhs = np.hstack([w.ravel() for w in ozv.uks_rhs(p, v)])
+    assert _rel(np.stack([op(x) for x in d["x"]]), d["ax"]) < 1e-12
+    assert _rel(rhs, d["rhs"]) < 1e-12
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_plan_against_the_reference_closures(golden_dir, tag):
+    d, p = load_case(golden_dir, tag)
+    it = PlanInterpreter(planmod.build_zvector_plan(p, with_diag=False), p)
+    assert _rel(it.sigma(d["x"]), d["ax"]) < 1e-12
+
+
+@pytest.mark.parametrize("xct,hyb,kw", [("GGA", 0.2, {}), ("LDA", 0.0, {}), ("HF", 1.0, {}), ("MGGA", 0.2, {}),
+                                        ("GGA", 0.25, dict(omega=0.33, alpha=0.65))])
+@pytest.mark.parametrize("no", [1, 2, 3])
+@pytest.mark.parametrize("restricted", [True, False])
+def test_plan_against_oracle(xct, hyb, kw, no, restricted):
+    p = make_problem(8 + no, 3, no, 5, 9, 30, xctype=xct, hyb=hyb, restricted=restricted, seed=70 + no, **kw)
+    pl = planmod.build_zvector_plan(p, with_diag=False)
+    it = PlanInterpreter(pl, p)
+    op = ozv.roks_matvec(p) if restricted else ozv.uks_fvind(p)
+    z = np.random.default_rng(1).standard_normal((3, pl.ext_dim))
+    assert _rel(it.sigma(z), np.stack([op(x) for x in z])) < 1e-12
+
+
+@pytest.mark.parametrize("restricted", [True, False])
+def test_plan_preconditioner_diagonal(restricted):
+    """plan.hdiag = the diagonal of the operator without its response part (Fock couplings / orbital-energy gaps)."""
+    p = make_problem(10, 3, 2, 5, 9, 0, xctype="HF", hyb=1.0, restricted=restricted, seed=81)
+    pl = planmod.build_zvector_plan(p)
+    if restricted:
+        q = copy.copy(p)
+        q.cderi = np.zeros_like(p.cderi)
+        ref = np.diagonal(ozv.dense_operator(ozv.roks_matvec(q), pl.ext_dim))
+    else:
+        ref = ozv.uks_gaps(p)
+    assert np.abs(pl.hdiag - ref).max() < 1e-14
+
+
+@pytest.mark.parametrize("restricted", [True, False])
+def test_solver_control_flow_against_dense_solve(restricted):
+    p = make_problem(12, 3, 2, 7, 11, 40, xctype="GGA", hyb=0.25, restricted=restricted, seed=83)
+    pl = planmod.build_zvector_plan(p, with_diag=True)
+    it = PlanInterpreter(pl, p)
+    v = np.random.default_rng(5).standard_normal((p.nc, p.nv))
+    v /= np.linalg.norm(v)
+    if restricted:
+        w = ozv.roks_rhs(p, v)
+        ref, b = ozv.roks_solve(p, w), w
+    else:
+        wa, wb = ozv.uks_rhs(p, v)
+        ref, b = ozv.uks_solve(p, wa, wb), -np.hstack([wa.ravel(), wb.ravel()])
+    z, conv, cycles, res = solve_linear(it.sigma, b, pl.hdiag, tol=1e-11, max_cycle=pl.ext_dim, backend=NumpyVectors(pl.ext_dim))
+    assert conv and cycles < pl.ext_dim and res < 1e-11
+    assert np.abs(z - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())

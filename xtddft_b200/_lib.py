@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libxtdsigma.so")
 
 XTD_FXC_NONE, XTD_FXC_UKS, XTD_FXC_ALDA0, XTD_FXC_MCOL, XTD_FXC_UKS_TAU, XTD_FXC_MCOL_TAU = 0, 1, 2, 3, 4, 5
-XTD_SIDE_RIGHT, XTD_SIDE_LEFT = 0, 1
+XTD_SIDE_RIGHT, XTD_SIDE_LEFT, XTD_SIDE_LEFT_T, XTD_SIDE_RIGHT_T = 0, 1, 2, 3
 T_NAMES = ["pack", "xc_gemm", "xc_stream", "k1", "k2", "j", "local", "unpack", "total", "k2_slice", "xc_slice"]
 
 
@@ -43,6 +43,7 @@ SIGNATURES = {
     "xtd_add_channel": (_I, [_P, _I, _P, _I, _I, _P, _I, _P, _I, _P, _I]),
     "xtd_channel_layout": (_I, [_P, _I, _I, C.POINTER(_L), C.POINTER(_L), C.POINTER(_L)]),
     "xtd_add_kterm": (_I, [_P, _I, _I, _P, _I, _I]),
+    "xtd_add_kterm_t": (_I, [_P, _I, _I, _D]),
     "xtd_add_jblock": (_I, [_P, _I, _I, _I, _I, _I]),
     "xtd_set_jmix": (_I, [_P, _P, _I]),
     "xtd_set_exchange_emulation": (_I, [_P, _I]),

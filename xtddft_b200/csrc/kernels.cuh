@@ -639,10 +639,18 @@ __global__ void local_small_kernel(const LocalSmallArgs a) {
       const double* sr = src + (long)(l.sr0 + i - l.r0) * lds + l.sc0;
       const double* m = l.M + (c - l.c0);
       for (int b = 0; b < l.k; ++b) v = fma(sr[b], m[(long)b * l.ldm], v);
-    } else {                  // LEFT: dst[r][c] += alpha sum_j M[r][j] src[sr0 + j][sc0 + c]
+    } else if (l.side == 1) { // LEFT: dst[r][c] += alpha sum_j M[r][j] src[sr0 + j][sc0 + c]
       const double* m = l.M + (long)(i - l.r0) * l.ldm;
       const double* sc = src + (long)l.sr0 * lds + l.sc0 + (c - l.c0);
       for (int j = 0; j < l.k; ++j) v = fma(m[j], sc[(long)j * lds], v);
+    } else if (l.side == 2) { // LEFT_T: dst[r][c] += alpha sum_k M[r][k] src[sr0 + c][sc0 + k]
+      const double* m = l.M + (long)(i - l.r0) * l.ldm;
+      const double* sr = src + (long)(l.sr0 + c - l.c0) * lds + l.sc0;
+      for (int k = 0; k < l.k; ++k) v = fma(m[k], sr[k], v);
+    } else {                  // RIGHT_T: dst[r][c] += alpha sum_j src[sr0 + j][sc0 + r] M[j][c]
+      const double* sc = src + (long)l.sr0 * lds + l.sc0 + (i - l.r0);
+      const double* m = l.M + (c - l.c0);
+      for (int j = 0; j < l.k; ++j) v = fma(sc[(long)j * lds], m[(long)j * l.ldm], v);
     }
     acc = fma(l.alpha, v, acc);
   }

@@ -59,6 +59,8 @@ struct Channel {
   DevBuf Lvo[2];                    // [naux_loc][v2off][ldvv]: rows of Lvv in the narrow first virtual block (open shells),
   bool need_narrow[2] = {false, false};   // gathered so (aux, row) flattens: narrow-output exchange pass (run_k)
   DevBuf Lvt[2];                    // [naux_loc][tail_w][ldvv]: the last rows of Lvv past a multiple of 128 in the second block
+  DevBuf Lov[2];                    // [naux_loc][no][ldz]: occupied-virtual block, exchange of the transposed trial density
+  bool need_kt[2] = {false, false}; // (xtd_add_kterm_t: the B-matrix-type term of the Z-vector operator)
   int tail_start = 0, tail_w = 0;   // (a short column tail of the block-weighted output takes the same pass)
   long ldoo, ldvv;
   bool need_k[2] = {false, false};
@@ -113,6 +115,10 @@ struct KTermRec {
   double w[2][2][2][2];
   bool uniform;
 };
+struct KTermTRec {
+  int tensor, ch;
+  double w;
+};
 struct JBlockRec {
   int ch, r0, nr, c0, nc;
   long ld;
@@ -163,6 +169,7 @@ struct xtd_engine {
   int nmo[2] = {0, 0};
   std::vector<Channel*> ch;
   std::vector<KTermRec> kterms;
+  std::vector<KTermTRec> ktterms;
   std::vector<JBlockRec*> jblocks;
   std::vector<double> jmix;
   DevBuf jmix_dev;
@@ -622,6 +629,17 @@ int xtd_add_kterm(xtd_handle h, int tensor, int chn, const double* w, int nob, i
   return XTD_OK;
 }
 
+int xtd_add_kterm_t(xtd_handle h, int tensor, int chn, double weight) {
+  XTD_REQUIRE(h && !h->finalized && (tensor == 0 || tensor == 1), XTD_ERR_ARG, "xtd_add_kterm_t: bad arguments");
+  XTD_REQUIRE(chn >= 0 && chn < (int)h->ch.size(), XTD_ERR_ARG, "bad channel");
+  XTD_REQUIRE(h->naux_filled[tensor] == 0 && h->naux[tensor] == 0, XTD_ERR_STATE, "exchange terms must be declared before xtd_df_begin");
+  KTermTRec k;
+  k.tensor = tensor; k.ch = chn; k.w = weight;
+  h->ktterms.push_back(k);
+  h->ch[chn]->need_kt[tensor] = true;
+  return XTD_OK;
+}
+
 int xtd_add_jblock(xtd_handle h, int chn, int r0, int nr, int c0, int nc) {
   XTD_REQUIRE(h && !h->finalized && chn >= 0 && chn < (int)h->ch.size(), XTD_ERR_ARG, "xtd_add_jblock: bad arguments");
   Channel* c = h->ch[chn];
@@ -699,6 +717,8 @@ int xtd_df_begin(xtd_handle h, int tensor, long naux_local) {
   XTD_REQUIRE(h && (tensor == 0 || tensor == 1) && naux_local >= 0, XTD_ERR_ARG, "xtd_df_begin: bad arguments");
   h->naux[tensor] = naux_local;
   h->naux_filled[tensor] = 0;
+  for (auto* c : h->ch)
+    if (c->need_kt[tensor]) XTD_TRY(c->Lov[tensor].alloc((size_t)naux_local * c->no * c->ldz, h->stream));
   for (auto* c : h->ch) {
     if (!c->need_k[tensor]) continue;
     XTD_TRY(c->Loo[tensor].alloc((size_t)naux_local * c->no * c->ldoo, h->stream));
@@ -761,7 +781,7 @@ int xtd_df_add(xtd_handle h, int tensor, const double* l_dev, long np, long ld_r
   // per-aux workspace: staging copy (if needed) + the largest half-transformed block
   int max_n = 0;
   for (auto* c : h->ch) {
-    bool need_o = c->need_k[tensor];
+    bool need_o = c->need_k[tensor] || c->need_kt[tensor];
     if (tensor == 0)
       for (auto* j : h->jblocks) need_o = need_o || (h->ch[j->ch] == c);
     if (need_o) max_n = std::max(max_n, c->no);
@@ -838,7 +858,7 @@ int xtd_df_add(xtd_handle h, int tensor, const double* l_dev, long np, long ld_r
     }
     for (size_t ci = 0; ci < h->ch.size(); ++ci) {
       Channel* c = h->ch[ci];
-      bool need_o = c->need_k[tensor];
+      bool need_o = c->need_k[tensor] || c->need_kt[tensor];
       if (tensor == 0)
         for (auto* j : h->jblocks) need_o = need_o || (j->ch == (int)ci);
       if (need_o) {
@@ -876,6 +896,14 @@ int xtd_df_add(xtd_handle h, int tensor, const double* l_dev, long np, long ld_r
               XTD_TRY(gemm(h->gemm, f, s));
             }
           }
+        }
+        if (c->need_kt[tensor]) {
+          // Lov[P][i][a] = sum_mu HoT[P][i][mu] CvT[a][mu]
+          GemmDesc e;
+          e.A = Hv; e.B = view2d(c->CvT.p, ldN, c->nv, N);
+          e.M = c->no; e.N = c->nv; e.K = N; e.batches = pn; e.a_hi = 1; e.b_hi = 0;
+          e.C = c->Lov[tensor].p + P0 * c->no * c->ldz; e.ldc = c->ldz; e.c_batch_stride = (long)c->no * c->ldz;
+          XTD_TRY(gemm(h->gemm, e, s));
         }
         if (tensor == 0)
           for (auto* j : h->jblocks) {
@@ -968,8 +996,13 @@ int xtd_add_local_gemm(xtd_handle h, int side, int dch, int r0, int nr, int c0, 
   XTD_REQUIRE(c0 % 2 == 0 && sc0 % 2 == 0, XTD_ERR_ALIGN, "local gemm: column offsets must be even");
   if (side == XTD_SIDE_RIGHT) {
     XTD_REQUIRE(mcols == nc && sr0 + nr <= sc->no && sc0 + mrows <= sc->nv, XTD_ERR_ARG, "right gemm: shapes inconsistent");
-  } else {
-    XTD_REQUIRE(side == XTD_SIDE_LEFT && mrows == nr && sr0 + mcols <= sc->no && sc0 + nc <= sc->nv, XTD_ERR_ARG, "left gemm: shapes inconsistent");
+  } else if (side == XTD_SIDE_LEFT) {
+    XTD_REQUIRE(mrows == nr && sr0 + mcols <= sc->no && sc0 + nc <= sc->nv, XTD_ERR_ARG, "left gemm: shapes inconsistent");
+  } else if (side == XTD_SIDE_LEFT_T) {      // dst[r][c] += alpha sum_k M[r][k] src[sr0 + c][sc0 + k]
+    XTD_REQUIRE(mrows == nr && sr0 + nc <= sc->no && sc0 + mcols <= sc->nv, XTD_ERR_ARG, "transposed left gemm: shapes inconsistent");
+  } else {                                   // dst[r][c] += alpha sum_j src[sr0 + j][sc0 + r] M[j][c]
+    XTD_REQUIRE(side == XTD_SIDE_RIGHT_T && mcols == nc && sr0 + mrows <= sc->no && sc0 + nr <= sc->nv, XTD_ERR_ARG,
+                "transposed right gemm: shapes inconsistent");
   }
   LocalGemmRec* l = new LocalGemmRec();
   l->side = side; l->dch = dch; l->r0 = r0; l->nr = nr; l->c0 = c0; l->nc = nc; l->sch = sch; l->sr0 = sr0; l->sc0 = sc0;
@@ -1055,8 +1088,9 @@ int xtd_finalize(xtd_handle h, int max_nvec) {
     std::vector<LocalTermDev> lt, ld;
     for (auto* l : h->lgemms) {
       LocalTermDev t;
-      t.side = l->side == XTD_SIDE_RIGHT ? 0 : 1; t.dch = l->dch; t.r0 = l->r0; t.nr = l->nr; t.c0 = l->c0; t.nc = l->nc;
-      t.sch = l->sch; t.sr0 = l->sr0; t.sc0 = l->sc0; t.k = l->side == XTD_SIDE_RIGHT ? l->mrows : l->mcols;
+      t.side = l->side; t.dch = l->dch; t.r0 = l->r0; t.nr = l->nr; t.c0 = l->c0; t.nc = l->nc;
+      t.sch = l->sch; t.sr0 = l->sr0; t.sc0 = l->sc0;
+      t.k = (l->side == XTD_SIDE_RIGHT || l->side == XTD_SIDE_RIGHT_T) ? l->mrows : l->mcols;
       t.ldm = l->ldm; t.alpha = l->alpha; t.M = l->M.p;
       lt.push_back(t);
     }
@@ -1914,6 +1948,54 @@ static int run_k(xtd_engine* h, int nvec) {
   return XTD_OK;
 }
 
+// Exchange of the transposed trial density (hermi = 1 response of the Z-vector operator; grad_hb/tdroks_sfu.py:284-298):
+//   sigma[x][i][a] += w sum_P sum_j Lov[P][j][a] W[P][i][x][j],   W[P][i][x][j] = sum_b Lov[P][i][b] z[x][j][b]
+// 4 naux no^2 nv flops per vector -- no / nv of the direct exchange term -- as two DMMA GEMMs per aux chunk.
+static int run_kt(xtd_engine* h, int nvec) {
+  cudaStream_t s = h->stream;
+  for (const KTermTRec& k : h->ktterms) {
+    Channel* ch = h->ch[k.ch];
+    const long naux = h->naux[k.tensor];
+    if (naux == 0 || k.w == 0.0) continue;
+    const double* Lov = ch->Lov[k.tensor].p;
+    const long ldw = ch->ldzt;                                   // pad_ld(no)
+    const size_t per_p = (size_t)nvec * ch->no * ldw;
+    long pc = (long)(h->scratch_doubles / per_p);
+    XTD_REQUIRE(pc >= 1, XTD_ERR_NOMEM, "workspace too small for the transposed-exchange intermediate of one aux function");
+    pc = std::min<long>(pc, naux);
+    if (h->max_pc > 0) pc = std::min<long>(pc, h->max_pc);
+    h->last_aux_chunks = std::max<long>(h->last_aux_chunks, cdiv(naux, pc));
+    double* W = h->scratch;
+    for (long P0 = 0; P0 < naux; P0 += pc) {
+      const int pn = (int)std::min<long>(pc, naux - P0);
+      {
+        PhaseTimer t(h, XTD_T_K1);
+        // rows (P, i) flattened; W[(P,i)][x][j]
+        GemmDesc d;
+        d.A = view2d(Lov + P0 * ch->no * ch->ldz, ch->ldz, pn * ch->no, ch->nv);
+        d.B = view3d(h->Z[k.ch], ch->ldz, (long)ch->no * ch->ldz, nvec, ch->no, ch->nv);
+        d.M = pn * ch->no; d.N = ch->no; d.K = ch->nv;
+        d.batches = nvec; d.z_div = 1; d.a_hi = 0; d.b_hi = 1;
+        d.C = W; d.ldc = (long)nvec * ldw; d.c_batch_stride = ldw;
+        XTD_TRY(gemm(h->gemm, d, s));
+      }
+      {
+        PhaseTimer t(h, XTD_T_K2);
+        GemmDesc d;
+        d.b_kc = false;
+        d.A = view3d(W, ldw, (long)nvec * ch->no * ldw, pn, nvec * ch->no, ch->no);
+        d.B = view3d(Lov, ch->ldz, (long)ch->no * ch->ldz, (int)(naux - P0), ch->no, ch->nv, 0, 0, (int)P0);
+        d.M = nvec * ch->no; d.N = ch->nv; d.K = ch->no; d.nouter = pn;
+        d.C = h->SIG + h->sig_base[k.ch]; d.ldc = ch->ldz; d.accumulate = true;
+        d.c_row_div = nvec; d.c_row_hi = ch->ldz; d.c_row_lo = (long)ch->no * ch->ldz;
+        d.alpha = k.w;
+        XTD_TRY(gemm(h->gemm, d, s));
+      }
+    }
+  }
+  return XTD_OK;
+}
+
 static int run_j(xtd_engine* h, int nvec) {
   cudaStream_t s = h->stream;
   const int njb = (int)h->jblocks.size();
@@ -2006,11 +2088,24 @@ static int run_local(xtd_engine* h, int nvec) {
         d.A = view3d(h->Z[l->sch], sc->ldz, (long)sc->no * sc->ldz, nvec, l->nr, l->mrows, l->sr0, l->sc0);
         d.M = l->nr; d.batches = nvec; d.a_hi = 1; d.b_hi = 0; d.C = dst; d.c_batch_stride = (long)dc->no * dc->ldz;
       }
-    } else {
+    } else if (l->side == XTD_SIDE_LEFT) {
       d.A = view2d(l->M.p, l->ldm, l->mrows, l->mcols);
       d.b_kc = false;
       d.B = view3d(h->Z[l->sch], sc->ldz, (long)sc->no * sc->ldz, nvec, l->mcols, l->nc, l->sr0, l->sc0);
       d.M = l->nr; d.N = l->nc; d.K = l->mcols; d.batches = nvec; d.a_hi = 0; d.b_hi = 1;
+      d.C = dst; d.c_batch_stride = (long)dc->no * dc->ldz;
+    } else if (l->side == XTD_SIDE_LEFT_T) {
+      // dst[r][c] += alpha sum_k M[r][k] src[c][k]: the source block enters transposed (both operands K-contiguous)
+      d.A = view2d(l->M.p, l->ldm, l->mrows, l->mcols);
+      d.B = view3d(h->Z[l->sch], sc->ldz, (long)sc->no * sc->ldz, nvec, l->nc, l->mcols, l->sr0, l->sc0);
+      d.M = l->nr; d.N = l->nc; d.K = l->mcols; d.batches = nvec; d.a_hi = 0; d.b_hi = 1;
+      d.C = dst; d.c_batch_stride = (long)dc->no * dc->ldz;
+    } else {
+      // dst[r][c] += alpha sum_j src[j][r] M[j][c]: neither operand K-contiguous
+      d.a_kc = false; d.b_kc = false;
+      d.A = view3d(h->Z[l->sch], sc->ldz, (long)sc->no * sc->ldz, nvec, l->mrows, l->nr, l->sr0, l->sc0);
+      d.B = view2d(l->M.p, l->ldm, l->mrows, l->mcols);
+      d.M = l->nr; d.N = l->nc; d.K = l->mrows; d.batches = nvec; d.a_hi = 1; d.b_hi = 0;
       d.C = dst; d.c_batch_stride = (long)dc->no * dc->ldz;
     }
     XTD_TRY(gemm(h->gemm, d, s));
@@ -2077,6 +2172,7 @@ int xtd_sigma_partial(xtd_handle h, int nvec, const double* z_dev) {
   }
   if (h->fxc_kind != XTD_FXC_NONE && h->ng > 0) XTD_TRY(run_xc(h, nvec));
   XTD_TRY(run_k(h, nvec));
+  XTD_TRY(run_kt(h, nvec));
   XTD_TRY(run_j(h, nvec));
   return XTD_OK;
 }

@@ -91,12 +91,14 @@ class SigmaEngine:
         for kt in plan.k_terms:
             w = np.ascontiguousarray(kt.weights, dtype=np.float64)
             _lib.check(self.lib.xtd_add_kterm(self._h, kt.tensor, kt.ch, _np_ptr(w), w.shape[0], w.shape[1]), "xtd_add_kterm")
+        for kt in plan.kt_terms:
+            _lib.check(self.lib.xtd_add_kterm_t(self._h, kt.tensor, kt.ch, float(kt.weight)), "xtd_add_kterm_t")
         for jb in plan.j_blocks:
             _lib.check(self.lib.xtd_add_jblock(self._h, jb.ch, jb.r0, jb.nr, jb.c0, jb.nc), "xtd_add_jblock")
         if plan.j_blocks:
             m = np.ascontiguousarray(plan.j_mix, dtype=np.float64)
             _lib.check(self.lib.xtd_set_jmix(self._h, _np_ptr(m), m.shape[0]), "xtd_set_jmix")
-        self.tensors_used = sorted({kt.tensor for kt in plan.k_terms} | ({0} if plan.j_blocks else set()))
+        self.tensors_used = sorted({kt.tensor for kt in plan.k_terms} | {kt.tensor for kt in plan.kt_terms} | ({0} if plan.j_blocks else set()))
 
     # ---- plumbing ---------------------------------------------------------------------------------
     def _set_stream(self):
@@ -228,7 +230,7 @@ class SigmaEngine:
             m = np.ascontiguousarray(lg.mat, dtype=np.float64)
             dc, r0, nr, c0, ncol = lg.dst
             sc, sr0, sc0 = lg.src
-            side = _lib.XTD_SIDE_RIGHT if lg.side == "R" else _lib.XTD_SIDE_LEFT
+            side = {"R": _lib.XTD_SIDE_RIGHT, "L": _lib.XTD_SIDE_LEFT, "LT": _lib.XTD_SIDE_LEFT_T, "RT": _lib.XTD_SIDE_RIGHT_T}[lg.side]
             _lib.check(self.lib.xtd_add_local_gemm(self._h, side, dc, r0, nr, c0, ncol, sc, sr0, sc0, _np_ptr(m), m.shape[0], m.shape[1],
                                                    float(lg.alpha)), "xtd_add_local_gemm")
         for r1 in plan.rank1s:
@@ -288,6 +290,8 @@ class SigmaEngine:
                 f = torch.from_numpy(np.ascontiguousarray(p.fxc_alda0[g0:g1])).to(eng.device)
             else:
                 f = torch.from_numpy(np.ascontiguousarray(p.fxc_mcol[..., g0:g1])).to(eng.device)
+            if plan.xc_scale != 1.0:            # the grid term is linear in the kernel table (Z-vector plans: hermi = 1 densities)
+                f = f * float(plan.xc_scale)
             eng.set_fxc(plan.xc_kind, f)
             del ao, w, f
             eng.grid_commit()                   # AO values are dropped before the tensor streams in

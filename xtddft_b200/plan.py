@@ -61,6 +61,14 @@ class KTerm:
 
 
 @dataclass
+class KTermT:
+    """Exchange of the transposed trial density: sigma[i,a] += weight * sum_P sum_jb L^P_ib z_jb L^P_ja (Z-vector plans)."""
+    tensor: int
+    ch: int
+    weight: float
+
+
+@dataclass
 class JBlock:
     ch: int
     r0: int
@@ -72,6 +80,7 @@ class JBlock:
 @dataclass
 class LocalGemm:
     side: str                      # 'R': dst[r,c] += a * sum_b src[r,b] M[b,c] ; 'L': dst[r,c] += a * sum_j M[r,j] src[j,c]
+    #                                'LT': dst[r,c] += a * sum_k M[r,k] src[c,k] ; 'RT': dst[r,c] += a * sum_j src[j,r] M[j,c]  (source transposed)
     dst: Tuple[int, int, int, int, int]   # ch, r0, nr, c0, nc
     src: Tuple[int, int, int]             # ch, r0, c0
     mat: np.ndarray
@@ -106,6 +115,8 @@ class Plan:
     method: str
     channels: List[ChannelSpec]
     k_terms: List[KTerm] = field(default_factory=list)
+    kt_terms: List[KTermT] = field(default_factory=list)
+    xc_scale: float = 1.0          # factor on the grid term (Z-vector plans: symmetrised densities)
     j_blocks: List[JBlock] = field(default_factory=list)
     j_mix: Optional[np.ndarray] = None
     xc_kind: str = "none"          # none | uks | alda0 | mcol | uks_tau | mcol_tau (meta-GGA tables with a tau component)
@@ -509,3 +520,115 @@ def finish_xsf_hdiag(plan: Plan, co_j: Optional[np.ndarray], ov_j: Optional[np.n
         d3 = nc * nv + nc * no + no * nv
         hd = np.hstack([hd[:d3], np.einsum("x,xy,xy->y", hd[d3:], vects, vects)])
     return hd
+
+
+# --------------------------------------------------------------------------------------------------
+# Z-vector (coupled-perturbed) operator of the spin-flip-up TDA gradients  
+# --------------------------------------------------------------------------------------------------
+def zvector_sym_fock(p: ProblemData) -> dict:
+    """Symmetrised MO Fock blocks of the ROKS orbital Hessian (grad_hb/tdroks_sfu.py:224-234)."""
+    nc, no = p.nc, p.no
+    fa, fb = p.fock_ks
+    C, O, V = slice(0, nc), slice(nc, nc + no), slice(nc + no, None)
+    sym = lambda f, r, c: 0.5 * (f[r, c] + f[c, r].T)
+    return dict(acc=sym(fa, C, C), aoc=sym(fa, O, C), avc=sym(fa, V, C), avv=sym(fa, V, V), aoo=sym(fa, O, O),
+                bcc=sym(fb, C, C), bvc=sym(fb, V, C), bvv=sym(fb, V, V), bvo=sym(fb, V, O), boo=sym(fb, O, O))
+
+
+def build_zvector_plan(p: ProblemData, with_diag: bool = True) -> Plan:
+    """The linear operator of the Z-vector equation as an engine plan.
+
+    ROKS reference (`p.restricted`): `matvec` of grad_hb/tdroks_sfu.py:284-321 -- the ROHF orbital Hessian on the rotations
+    x = [vc (nv x nc) | vo (nv x no) | oc (no x nc)] (virtual-major blocks):  F-couplings - 2 G[Z^S], where G is the hermi = 1
+    response `vresp` (tdroks_sfu.py:283,295) of the symmetrised density (dm + dm^T)/2 projected on the occupied-virtual blocks.
+    UKS reference: `fvind` of grad_hb/tduks_sfu.py:249-258 on x = [alpha (nv x nocc_a) | beta (nvir_b x nocc_b)], G[dm + dm^T];
+    `with_diag` adds the orbital-energy differences, i.e. the operator `ucphf.solve` inverts (tduks_sfu.py:261-263).
+
+    In the engine's MO-resident vocabulary the response of a symmetrised trial density is the TDA response (direct exchange,
+    Coulomb, grid kernel -- the X-TDA plan's terms) plus the exchange of the TRANSPOSED density (`KTermT`):
+        K[dm + dm^T]_ai = sum_P sum_jb (L_ab L_ij + L_aj L_ib) z_jb ,   J and f_xc just double.
+    """
+    nc, no, nv = p.nc, p.no, p.nv
+    na, nb, nva, nvb = p.nocc_a, p.nocc_b, p.nvir_a, p.nvir_b
+    occ_a, ob_a = _two_block(nc, no, 0)
+    vir_a = (na + np.arange(nva)).astype(np.int32)
+    occ_b = np.arange(nb, dtype=np.int32)
+    vir_b, vb_b = _two_block(no, nv, nb)
+    cha = ChannelSpec(0, occ_a, 0, vir_a, ob_a, [(0, nva)])
+    chb = ChannelSpec(1, occ_b, 1, vir_b, [(0, nb)], vb_b)
+    plan = Plan("zvector_roks" if p.restricted else "zvector_uks", [cha, chb])
+    oa_pos, va_pos = _pos(ob_a), np.arange(nva)
+    ob_pos, vb_pos = np.arange(nb), _pos(vb_b)
+    v2off = vb_b[1][0] if len(vb_b) > 1 else 0
+    o2off = ob_a[1][0] if len(ob_a) > 1 else 0
+    # G[dm + dm^T] = g * (2 J + 2 f_xc - hyb (K + K^T-type));  ROKS: -2 G[(dm + dm^T)/2]  ->  g = -1;  UKS: g = +1
+    g = -1.0 if p.restricted else 1.0
+    if p.has_df:
+        plan.j_blocks = [JBlock(0, 0, cha.no, 0, cha.nv), JBlock(1, 0, chb.no, 0, chb.nv)]
+        plan.j_mix = 2.0 * g * np.ones((2, 2))
+        if p.hybrid:
+            for ci, chs in enumerate((cha, chb)):
+                shape = (len(chs.o_blocks), len(chs.v_blocks)) * 2
+                plan.k_terms.append(KTerm(0, ci, np.full(shape, -g * p.hyb)))
+                plan.kt_terms.append(KTermT(0, ci, -g * p.hyb))
+                if p.omega != 0.0 and p.has_df_lr:
+                    plan.k_terms.append(KTerm(1, ci, np.full(shape, -g * (p.alpha - p.hyb))))
+                    plan.kt_terms.append(KTermT(1, ci, -g * (p.alpha - p.hyb)))
+    if p.xctype != "HF":
+        plan.xc_kind = "uks_tau" if p.xctype == "MGGA" else "uks"
+        plan.xc_scale = 2.0 * g
+
+    if p.restricted:
+        f = zvector_sym_fock(p)
+        cva, ova = (0, 0, nc, 0, nv), (0, o2off, no, 0, nv)         # alpha: rows c / rows o
+        cvb, cob = (1, 0, nc, v2off, nv), (1, 0, nc, 0, no)         # beta: cols v / cols o
+        lg = plan.local_gemms
+        # Fxvc (tdroks_sfu.py:301-308), split over the two channels that carry the vc block
+        lg += [LocalGemm("R", cva, (0, 0, 0), f["avv"].T.copy(), -1.0), LocalGemm("L", cva, (0, 0, 0), f["acc"].T.copy(), 1.0),
+               LocalGemm("L", cva, (0, o2off, 0), f["aoc"].T.copy(), 1.0),
+               LocalGemm("R", cvb, (1, 0, v2off), f["bvv"].T.copy(), -1.0), LocalGemm("L", cvb, (1, 0, v2off), f["bcc"].T.copy(), 1.0),
+               LocalGemm("R", cvb, (1, 0, 0), f["bvo"].T.copy(), -1.0)]
+        if no > 0:
+            # Fxvo (:309-314): the oc block of the beta channel enters transposed
+            lg += [LocalGemm("RT", ova, (1, 0, 0), f["bvc"].T.copy(), -1.0), LocalGemm("L", ova, (0, 0, 0), f["aoc"].copy(), 1.0),
+                   LocalGemm("R", ova, (0, o2off, 0), f["avv"].copy(), -1.0), LocalGemm("L", ova, (0, o2off, 0), f["aoo"].copy(), 1.0)]
+            # Fxoc (:315-320): the vo block of the alpha channel enters transposed
+            lg += [LocalGemm("R", cob, (1, 0, 0), f["boo"].T.copy(), -1.0), LocalGemm("L", cob, (1, 0, 0), f["bcc"].copy(), 1.0),
+                   LocalGemm("R", cob, (1, 0, v2off), f["bvo"].copy(), -1.0), LocalGemm("LT", cob, (0, o2off, 0), f["avc"].T.copy(), 1.0)]
+        d = lambda m: np.diagonal(m)
+        h_vc = -(d(f["avv"]) + d(f["bvv"]))[:, None] + (d(f["acc"]) + d(f["bcc"]))[None, :]
+        h_vo = -d(f["avv"])[:, None] + d(f["aoo"])[None, :]
+        h_oc = -d(f["boo"])[:, None] + d(f["bcc"])[None, :]
+        plan.hdiag = np.hstack([h_vc.ravel(), h_vo.ravel(), h_oc.ravel()])
+        # layout: x = [vc (a,i) | vo (a,t) | oc (t,i)]; the vc block feeds both channels and collects from both
+        a_, i_ = np.meshgrid(np.arange(nv), np.arange(nc), indexing="ij")
+        e_vc = (a_ * nc + i_).ravel()
+        ent = [np.stack([e_vc, np.zeros_like(e_vc), oa_pos[i_.ravel()], va_pos[a_.ravel()]], axis=1),
+               np.stack([e_vc, np.ones_like(e_vc), ob_pos[i_.ravel()], vb_pos[no + a_.ravel()]], axis=1)]
+        if no > 0:
+            a_, t_ = np.meshgrid(np.arange(nv), np.arange(no), indexing="ij")
+            e_vo = (nv * nc + a_ * no + t_).ravel()
+            ent.append(np.stack([e_vo, np.zeros_like(e_vo), oa_pos[nc + t_.ravel()], va_pos[a_.ravel()]], axis=1))
+            t_, i_ = np.meshgrid(np.arange(no), np.arange(nc), indexing="ij")
+            e_oc = (nv * nc + nv * no + t_ * nc + i_).ravel()
+            ent.append(np.stack([e_oc, np.ones_like(e_oc), ob_pos[i_.ravel()], vb_pos[t_.ravel()]], axis=1))
+        ent = np.concatenate(ent).astype(np.int64)
+        plan.ext_dim = nv * nc + nv * no + no * nc
+    else:
+        ea, eb = p.mo_energy
+        e_a = ea[na:, None] - ea[None, :na]                       # [nv, nocc_a]  virtual-major like the vectors
+        e_b = eb[nb:, None] - eb[None, :nb]
+        plan.hdiag = np.hstack([e_a.ravel(), e_b.ravel()])
+        if with_diag:
+            plan.diags += [DiagTerm(0, _embed(e_a.T, oa_pos, va_pos, cha.no, cha.nv)),
+                           DiagTerm(1, _embed(e_b.T, ob_pos, vb_pos, chb.no, chb.nv))]
+        a_, i_ = np.meshgrid(np.arange(nva), np.arange(na), indexing="ij")
+        e1 = (a_ * na + i_).ravel()
+        a2, i2 = np.meshgrid(np.arange(nvb), np.arange(nb), indexing="ij")
+        e2 = (nva * na + a2 * nb + i2).ravel()
+        ent = np.concatenate([np.stack([e1, np.zeros_like(e1), oa_pos[i_.ravel()], va_pos[a_.ravel()]], axis=1),
+                              np.stack([e2, np.ones_like(e2), ob_pos[i2.ravel()], vb_pos[a2.ravel()]], axis=1)]).astype(np.int64)
+        plan.ext_dim = nva * na + nvb * nb
+    plan.layout_entries, plan.layout_coefs = ent, np.ones(ent.shape[0])
+    plan.meta = dict(nc=nc, no=no, nv=nv, o2off=o2off, v2off=v2off)
+    return plan

@@ -1,0 +1,131 @@
+"""Z-vector (coupled-perturbed) equation of the spin-flip-up TDA nuclear gradients on the B200 sigma engine.
+
+The reference solves, for every state whose gradient is wanted,
+
+  * ROKS reference:  matvec(z) = w            xtddft/grad_hb/tdroks_sfu.py:284-327  (`lib.solve(matvec, w, tol=1e-12, ...)`)
+  * UKS reference:   (e_a - e_i) z + fvind(z) = -(wvoa, wvob)     xtddft/grad_hb/tduks_sfu.py:249-263  (`ucphf.solve(fvind, ...)`)
+
+where `matvec` / `fvind` apply the hermi = 1 response `vresp` (grid f_xc + J - hyb K of the symmetrised rotation density) -- one AO
+J/K build and one grid pass per iteration.  Here the operator is an engine plan (`plan.build_zvector_plan`): the MO-resident exchange
+and Coulomb blocks, the MO-on-grid kernel contraction and the ROHF Fock couplings of the sigma path, plus the exchange of the
+transposed density (`xtd_add_kterm_t`); the Krylov vectors live in HBM and the subspace algebra runs in the `xtd_vec_*` kernels.
+
+The right-hand side (the Q matrix: J/K and f_xc images of occupied-occupied and virtual-virtual densities, third-derivative kernel
+for multicollinear functionals) is an INPUT here, as are the integral derivatives that follow the solve; both need pieces outside
+the sigma path (libcint derivative integrals, libxc third derivatives).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+
+from . import plan as planmod
+from .adapters import problem_from_mf
+
+
+def solve_linear(aop, b, hdiag, *, tol: float = 1e-12, max_cycle: int = 40, lindep: float = 1e-13, backend=None, verbose: int = 0):
+    """Solve A x = b for a general (not necessarily symmetric) operator by Galerkin projection on a preconditioned Krylov space --
+    the scheme of `pyscf.lib.linalg_helper.dsolve` that `lib.solve` names (tdroks_sfu.py:324): new direction = diagonally
+    preconditioned residual, projected system solved on the host (<= max_cycle unknowns).  Differences: the directions are kept
+    orthonormal (two Gram-Schmidt passes on the device), and vectors never leave the device.
+
+    aop(X[k, dim]) -> [k, dim] on the backend's vectors; b, hdiag: host arrays.  Returns (x_host, converged, cycles, residual norm).
+    """
+    b = np.asarray(b, dtype=np.float64).ravel()
+    dim = b.size
+    vb = backend
+    if vb is None:
+        from .davidson import CudaVectors
+        vb = CudaVectors(dim)
+    m = min(max_cycle, dim)
+    V, AV = vb.alloc(m), vb.alloc(m)
+    bd = vb.from_host(b[None])
+    hd = vb.from_host(np.asarray(hdiag, dtype=np.float64).ravel())
+    t, r = vb.alloc(1), vb.alloc(1)
+    zero = np.zeros(1)
+    vb.copy(t, bd)
+    H = np.zeros((m, m))
+    g = np.zeros(m)
+    c = np.zeros(0)
+    res = float(np.linalg.norm(b))
+    conv = res < tol
+    k = 0
+    while not conv and k < m:
+        n0 = float(vb.precond(t, hd, zero)[0])                      # t <- t / hdiag   (|hdiag| clamped at 1e-8)
+        if n0 <= 0.0:
+            break
+        vb.scale(t, np.array([1.0 / np.sqrt(n0)]))                  # unit length, so `lindep` is a relative threshold
+        for _ in range(2):                                          # CGS2 against the kept directions
+            if k:
+                vb.lincomb(t, V[:k], -vb.dots(t, V[:k]), 1.0)
+        nrm2 = float(vb.dots(t, t)[0, 0])
+        if nrm2 <= lindep:
+            break
+        vb.scale(t, np.array([1.0 / np.sqrt(nrm2)]))
+        vb.copy(V[k:k + 1], t)
+        vb.copy(AV[k:k + 1], aop(V[k:k + 1]))
+        k += 1
+        H[:k, k - 1] = vb.dots(V[:k], AV[k - 1:k])[:, 0]
+        H[k - 1, :k] = vb.dots(V[k - 1:k], AV[:k])[0]
+        g[k - 1] = vb.dots(V[k - 1:k], bd)[0, 0]
+        c = np.linalg.solve(H[:k, :k], g[:k])
+        vb.lincomb(r, AV[:k], c[None], 0.0)
+        vb.lincomb(r, bd, -np.ones((1, 1)), 1.0)                    # r = A x - b
+        res = float(np.sqrt(vb.dots(r, r)[0, 0]))
+        if verbose:
+            print(f"zvector solve: cycle {k}  |r| = {res:.3e}")
+        conv = res < tol
+        vb.copy(t, r)
+    x = vb.alloc(1)
+    if k:
+        vb.lincomb(x, V[:k], c[None], 0.0)
+    return vb.to_host(x)[0], bool(conv), k, res
+
+
+class ZVector:
+    """Operator and solver of the Z-vector equation for one mean-field reference.
+
+        zv = ZVector(mf_or_problem)          # ROKS or UKS reference, density-fitted
+        az = zv.matvec(z)                    # the reference's `matvec` (ROKS) / `(e_a - e_i) z + fvind(z)` (UKS)
+        z  = zv.solve(rhs)                   # ROKS: rhs = w;  UKS: rhs = hstack(wvoa.ravel(), wvob.ravel()), solves A z = -rhs
+
+    Vector layout (virtual-major blocks, as the reference's closures take them): ROKS [vc (nv,nc) | vo (nv,no) | oc (no,nc)],
+    UKS [alpha (nv, nocc_a) | beta (nvir_b, nocc_b)].  `with_diag=False` (UKS) gives the bare `fvind`.
+    """
+    cphf_max_cycle = 40          # grad_tdrhf_Gradients_cphf_max_cycle (20) + 20, tdroks_sfu.py:434
+    cphf_conv_tol = 1e-8         # tduks_sfu.py:374
+
+    def __init__(self, mf, *, with_diag: bool = True, max_nvec: int = 4, workspace_bytes: Optional[int] = None, distributed: bool = True):
+        from .drivers_common import make_engine
+        self.problem = p = problem_from_mf(mf, kernel="uks")
+        self.restricted = bool(p.restricted)
+        self.nc, self.no, self.nv = p.nc, p.no, p.nv
+        self.plan = planmod.build_zvector_plan(p, with_diag=with_diag)
+        self.engine = make_engine(self.plan, p, max_nvec=max_nvec, workspace_bytes=workspace_bytes, distributed=distributed)
+        self.hdiag = np.asarray(self.plan.hdiag)
+        self.dim = int(self.plan.ext_dim)
+
+    def matvec(self, x) -> np.ndarray:
+        x = np.asarray(x, dtype=np.float64)
+        out = self.engine.sigma_host(x.reshape(-1, self.dim))
+        return out[0] if x.ndim == 1 else out
+
+    def solve(self, rhs, tol: Optional[float] = None, max_cycle: Optional[int] = None, lindep: float = 1e-13, verbose: int = 0):
+        """Returns the stacked solution vector; `self.converged`, `self.cycles`, `self.residual` describe the run."""
+        rhs = np.asarray(rhs, dtype=np.float64).ravel()
+        if tol is None:
+            tol = 1e-12 if self.restricted else self.cphf_conv_tol        # tdroks_sfu.py:325 / tduks_sfu.py:263
+        b = rhs if self.restricted else -rhs
+        z, self.converged, self.cycles, self.residual = solve_linear(self.engine.sigma, b, self.hdiag, tol=tol,
+                                                                    max_cycle=max_cycle or self.cphf_max_cycle, lindep=lindep,
+                                                                    verbose=verbose)
+        return z
+
+    def split(self, z):
+        """The rotation blocks the reference continues with: ROKS (zvc, zvo, zoc) (tdroks_sfu.py:328-330), UKS (z1a, z1b)."""
+        nc, no, nv = self.nc, self.no, self.nv
+        z = np.asarray(z).ravel()
+        if self.restricted:
+            return z[:nv * nc].reshape(nv, nc), z[nv * nc:nv * nc + nv * no].reshape(nv, no), z[nv * nc + nv * no:].reshape(no, nc)
+        return z[:nv * (nc + no)].reshape(nv, nc + no), z[nv * (nc + no):].reshape(no + nv, nc)
