@@ -318,6 +318,49 @@ def compact_config_record(cfg: int, steps: int = 2, warmup: int = 3, cpu_budget_
     return rec
 
 
+def zvector_record(cfg: int = 4, steps: int = 3, warmup: int = 3) -> dict:
+    """SURVEY 8f row f3 measured on a BASELINE X-TDA workload's inputs: the Z-vector operator (grad_hb/tdroks_sfu.py:284-321) as one
+    engine call per Krylov vector, and a full device solve for a seeded right-hand side."""
+    import dataclasses
+    import torch
+    from xtddft_b200.synth_device import make_device_problem
+    from xtddft_b200.workloads import default_workspace_bytes, engine_for_device_problem
+    from xtddft_b200.zvector import solve_linear
+    dp = dataclasses.replace(make_device_problem(cfg, 1.0), method="zvector")
+    eng = engine_for_device_problem(dp, max_nvec=4, workspace_bytes=default_workspace_bytes(dp, 1))
+    try:
+        dev = eng.device
+        g = torch.Generator(device=dev); g.manual_seed(777)
+        z = torch.randn((1, eng.ext_dim), generator=g, device=dev, dtype=torch.float64)
+        z /= z.norm()
+        out = torch.empty_like(z)
+        for _ in range(warmup):
+            eng.sigma(z, out)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            eng.sigma(z, out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        st = eng.stats()
+        phase = {k: v for k, v in st["ms"].items() if k != "total" and v > 0}
+        rhs = torch.randn(eng.ext_dim, generator=g, device=dev, dtype=torch.float64)
+        rhs = (rhs / rhs.norm()).cpu().numpy()
+        t0 = time.perf_counter()
+        x, conv, cycles, res = solve_linear(eng.sigma, rhs, eng.plan.hdiag, tol=1e-8, max_cycle=40)
+        torch.cuda.synchronize()
+        return {"config": cfg, "workload": dp.name + " inputs, Z-vector equation (row f3)", "method": eng.plan.method, "dim": int(eng.ext_dim),
+                "ms_per_operator_call": ms, "phase_ms": phase, "exchange_slices": int(eng.exchange_slices),
+                "solve": {"seconds": time.perf_counter() - t0, "cycles": int(cycles), "converged": bool(conv), "residual": float(res),
+                          "tol": 1e-8, "rhs": "seeded unit vector"}}
+    finally:
+        eng.close()
+        del eng
+        torch.cuda.empty_cache()
+
+
 # ---------------------------------------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------------------------------------
@@ -562,6 +605,10 @@ def main():
                 table.append(compact_config_record(c))
             except Exception as ex:      # a failed side measurement must not lose the headline record
                 table.append({"config": c, "error": f"{type(ex).__name__}: {ex}"})
+        try:
+            table.append(zvector_record(4))
+        except Exception as ex:
+            table.append({"config": 4, "method": "zvector_roks", "error": f"{type(ex).__name__}: {ex}"})
         out_json["configs"] = table
     emit(out_json)
     if world > 1:

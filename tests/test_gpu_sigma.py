@@ -188,6 +188,26 @@ def test_gga_split_gradient_form(torch_cuda, monkeypatch, split, nc, no, nv):
     eng.close()
 
 
+@pytest.mark.parametrize("nc,no,nv", [(6, 2, 17), (70, 3, 150), (33, 1, 140)])
+def test_gga_split_streaming_kernels_by_batch_size(torch_cuda, monkeypatch, nc, no, nv):
+    """The split-gradient streaming step has two kernels: warps over trial vectors (more than 8 vectors) and, for small batches, the
+    warps of a CTA sharing the grid point by orbital range (`xc_weight_split_op_kernel`, 1 / 2 / 4 vectors per pass with a ragged last
+    pass).  Every batch size class against the oracle, UKS kernel on two channels and the multicollinear kernel on one, odd / even
+    occupied counts (8- and 16-byte accesses)."""
+    monkeypatch.setenv("XTD_XC_SPLIT", "1")
+    p = make_problem(nc + no + nv, nc, no, nv, 7, 300, xctype="GGA", hyb=0.2, seed=230 + no)
+    vind, hd = osig.xtda_gen_vind(p)
+    eng = _engine(planmod.build_xtda_plan(p), p, max_nvec=12)
+    for nvec in (1, 2, 5, 8, 11):
+        _check(torch_cuda, eng, vind, hd.size, nvec=nvec, seed=nvec)
+    eng.close()
+    vind, hd = osig.sf_gen_vind(p, -1, 1)
+    eng = _engine(planmod.build_sf_plan(p, isf=-1, method=1), p, max_nvec=12)
+    for nvec in (1, 2, 6, 9):
+        _check(torch_cuda, eng, vind, hd.size, nvec=nvec, seed=nvec)
+    eng.close()
+
+
 @pytest.mark.parametrize("narrow", ["on", "off"])
 @pytest.mark.parametrize("nc,no,nv", [(131, 3, 150), (40, 4, 33), (7, 2, 260), (20, 3, 141)])
 def test_xsf_narrow_open_block(torch_cuda, monkeypatch, narrow, nc, no, nv):

@@ -99,3 +99,21 @@ def test_solve(torch_cuda, restricted):
     blocks = zv.split(z)
     assert sum(b.size for b in blocks) == zv.dim
     zv.engine.close()
+
+
+def test_workload_route_solves(torch_cuda):
+    """The bench's route (device-generated BASELINE config-4 inputs at 1/8 scale, tensor streamed block by block): the device solve
+    converges and the solution satisfies the equation under an independent application of the operator."""
+    import dataclasses
+    from xtddft_b200.synth_device import make_device_problem
+    from xtddft_b200.workloads import engine_for_device_problem
+    from xtddft_b200.zvector import solve_linear
+    dp = dataclasses.replace(make_device_problem(4, 0.125), method="zvector")
+    eng = engine_for_device_problem(dp, max_nvec=4, workspace_bytes=1 << 30)
+    rhs = np.random.default_rng(9).standard_normal(eng.ext_dim)
+    rhs /= np.linalg.norm(rhs)
+    x, conv, cycles, res = solve_linear(eng.sigma, rhs, eng.plan.hdiag, tol=1e-9, max_cycle=60)
+    assert conv and res < 1e-9
+    ax = eng.sigma_host(x[None])[0]
+    assert np.abs(ax - rhs).max() < 1e-8
+    eng.close()

@@ -468,6 +468,165 @@ __global__ void __launch_bounds__(512, 2) xc_weight_split_kernel(const XcArgs2 a
   }
 }
 
+// The same step for SMALL batches of trial vectors (a Z-vector solve applies the operator to one vector at a time, the last Davidson
+// cycles to a few): with one warp per trial vector a CTA would be one or two warps, each staging ~50 KB of MO values by itself and
+// four of them resident per SM -- latency-bound (config 4, one vector: 84 ms against 8 ms of HBM time).  Here the eight warps of a
+// CTA share the grid point by ORBITAL range: all 256 threads stage the point, every warp accumulates the partial densities of its
+// slice for XB vectors at a time, one shared-memory reduction (double-buffered: one barrier per batch) combines them, every warp
+// forms the potentials and writes its slice back.  Each byte of Y0 / T and of the MO values is still read from HBM exactly once.
+template <int KIND, int W, int XB>
+__global__ void __launch_bounds__(256, (XB >= 4 ? 2 : 3)) xc_weight_split_op_kernel(const XcArgs2 a) {
+  constexpr int NVAR = 4;
+  constexpr int NCH = (KIND == XC_KIND_UKS) ? 2 : 1;
+  constexpr int NR = NCH * NVAR;
+  constexpr int NWARPS = 8;
+  extern __shared__ __align__(16) double xc_sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long g = blockIdx.x;
+  double* sphi[NCH];
+  double* sphiv[NCH];
+  int nop[NCH], nvp[NCH];
+  double* cur = xc_sm;
+#pragma unroll
+  for (int s = 0; s < NCH; ++s) {
+    nop[s] = (a.no[s] + 1) & ~1;
+    nvp[s] = (a.nv[s] + 1) & ~1;
+    sphi[s] = cur; cur += 4 * nop[s];
+    sphiv[s] = cur; cur += 3 * nvp[s];
+    const double* p = a.phi[s] + (a.g0 + g) * a.ldphi[s];
+    const double* pv = a.phiv[s] + (a.g0 + g) * a.ldphiv[s];
+    for (int i = threadIdx.x; i < 4 * nop[s]; i += blockDim.x) {
+      const int k = i / nop[s], o = i - k * nop[s];
+      sphi[s][i] = o < a.no[s] ? p[k * a.phi_comp[s] + o] : 0.0;
+    }
+    for (int i = threadIdx.x; i < 3 * nvp[s]; i += blockDim.x) {
+      const int k = i / nvp[s], v = i - k * nvp[s];
+      sphiv[s][i] = v < a.nv[s] ? pv[(k + 1) * a.phiv_comp[s] + v] : 0.0;
+    }
+  }
+  double* red = cur;                     // [2][NWARPS][XB][NR] partial densities
+  double fk[NR];
+  {
+    const double* row = a.wf + (a.g0 + g) * (long)(NR * NR);
+#pragma unroll
+    for (int q = 0; q < NR; ++q) fk[q] = (lane < NR) ? row[lane * NR + q] : 0.0;
+  }
+  __syncthreads();
+  const long t_rows = a.t_rows ? a.t_rows : a.gb;
+  int buf = 0;
+  for (int x0 = 0; x0 < a.nvec; x0 += XB, buf ^= 1) {
+    double rho[XB][NR];
+#pragma unroll
+    for (int xi = 0; xi < XB; ++xi)
+#pragma unroll
+      for (int q = 0; q < NR; ++q) rho[xi][q] = 0.0;
+#pragma unroll
+    for (int s = 0; s < NCH; ++s) {
+      const int no = a.no[s], nv = a.nv[s];
+      const double* yb = a.Y[s] + g * a.ldY[s];
+      for (int o = (warp * 32 + lane) * W; o < no; o += NWARPS * 32 * W) {
+        double ph[NVAR][W];
+#pragma unroll
+        for (int k = 0; k < NVAR; ++k)
+#pragma unroll
+          for (int e = 0; e < W; ++e) ph[k][e] = sphi[s][k * nop[s] + o + e];
+#pragma unroll
+        for (int xi = 0; xi < XB; ++xi) {
+          if (x0 + xi < a.nvec) {
+            XcVec<W> y;
+            y.load(yb + (long)(x0 + xi) * no + o);
+#pragma unroll
+            for (int e = 0; e < W; ++e)
+#pragma unroll
+              for (int k = 0; k < NVAR; ++k) rho[xi][s * NVAR + k] += y.v[e] * ph[k][e];
+          }
+        }
+      }
+      for (int v = (warp * 32 + lane) * 2; v < nv; v += NWARPS * 64) {
+        double2 pv[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) pv[k] = *reinterpret_cast<const double2*>(sphiv[s] + k * nvp[s] + v);
+#pragma unroll
+        for (int xi = 0; xi < XB; ++xi) {
+          if (x0 + xi < a.nvec) {
+            XcVec<2> t;
+            t.load(a.T[s] + ((long)(x0 + xi) * t_rows + g) * a.ldT[s] + v);
+            const double t1 = (v + 1 < nv) ? t.v[1] : 0.0;       // past an odd nv the buffer holds no data
+#pragma unroll
+            for (int k = 0; k < 3; ++k) rho[xi][s * NVAR + 1 + k] += t.v[0] * pv[k].x + t1 * pv[k].y;
+          }
+        }
+      }
+    }
+    double* rb = red + (long)buf * NWARPS * XB * NR;
+#pragma unroll
+    for (int xi = 0; xi < XB; ++xi)
+#pragma unroll
+      for (int q = 0; q < NR; ++q) {
+        const double v = warp_sum(rho[xi][q]);
+        if (lane == 0) rb[(warp * XB + xi) * NR + q] = v;
+      }
+    __syncthreads();
+    double wv[XB][NR];
+#pragma unroll
+    for (int xi = 0; xi < XB; ++xi) {
+      // lane q < NR: total density component q of vector xi, then mine = sum_q' fk[q'] rho[q'] and a broadcast of the results
+      double tot = 0.0;
+      if (lane < NR)
+#pragma unroll
+        for (int w = 0; w < NWARPS; ++w) tot += rb[(w * XB + xi) * NR + lane];
+      double mine = 0.0;
+#pragma unroll
+      for (int q = 0; q < NR; ++q) mine += fk[q] * __shfl_sync(0xffffffffu, tot, q);
+#pragma unroll
+      for (int q = 0; q < NR; ++q) wv[xi][q] = __shfl_sync(0xffffffffu, mine, q);
+    }
+#pragma unroll
+    for (int s = 0; s < NCH; ++s) {
+      const int no = a.no[s], nv = a.nv[s];
+      double* yb = a.Y[s] + g * a.ldY[s];
+      for (int o = (warp * 32 + lane) * W; o < no; o += NWARPS * 32 * W) {
+        double ph[NVAR][W];
+#pragma unroll
+        for (int k = 0; k < NVAR; ++k)
+#pragma unroll
+          for (int e = 0; e < W; ++e) ph[k][e] = sphi[s][k * nop[s] + o + e];
+#pragma unroll
+        for (int xi = 0; xi < XB; ++xi) {
+          if (x0 + xi < a.nvec) {
+            XcVec<W> out;
+#pragma unroll
+            for (int e = 0; e < W; ++e) {
+              double acc = 0.0;
+#pragma unroll
+              for (int k = 0; k < NVAR; ++k) acc += wv[xi][s * NVAR + k] * ph[k][e];
+              out.v[e] = acc;
+            }
+            out.store(yb + (long)(x0 + xi) * no + o);
+          }
+        }
+      }
+      for (int v = (warp * 32 + lane) * 2; v < nv; v += NWARPS * 64) {
+        double2 pv[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) pv[k] = *reinterpret_cast<const double2*>(sphiv[s] + k * nvp[s] + v);
+#pragma unroll
+        for (int xi = 0; xi < XB; ++xi) {
+          if (x0 + xi < a.nvec) {
+            double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              acc.x += wv[xi][s * NVAR + 1 + k] * pv[k].x;
+              acc.y += wv[xi][s * NVAR + 1 + k] * pv[k].y;
+            }
+            *reinterpret_cast<double2*>(a.T[s] + ((long)(x0 + xi) * t_rows + g) * a.ldT[s] + v) = acc;   // the staged value past an odd nv is 0
+          }
+        }
+      }
+    }
+  }
+}
+
 // per-point kernel tables (once per solve)
 // UKS: wf[g][t*nvar+d][s*nvar+c] = w[g] * fxc[s,c,t,d,g]
 __global__ void build_wf_uks_kernel(double* __restrict__ wf, const double* __restrict__ fxc, const double* __restrict__ w, long ng,

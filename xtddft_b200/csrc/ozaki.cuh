@@ -407,6 +407,161 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const OzGemmPara
   }
 }
 
+// ---- the same contraction as a PERSISTENT kernel ------------------------------------------------------------------------------
+// One CTA per SM walks the (split, row tile, column tile, batch) items in launch order, so the barriers, the TMEM allocation and the
+// pipeline fill are paid once per SM instead of once per 128 x 64 tile, and the MMAs of the next group / tile run under the fp64
+// part of the epilogue: eight epilogue warps (two per TMEM lane quadrant, 32 columns each) first DRAIN the level accumulators into
+// fp64 registers, hand the accumulators back, and only then scale / accumulate / store.  This is what short contractions need
+// (the grid GEMMs: one accumulation group per tile; the non-persistent kernel showed the tensor pipe 63 % active there against 85 %
+// for the long exchange contraction).  No cluster multicast (measured: no gain at 2 CTAs).
+template <int S>
+__global__ void __launch_bounds__(OZ_K1_THREADS, 1) oz_gemm_p_kernel(const OzGemmParams p) {
+  constexpr int A_SLICE = OZ_BM * OZ_KB, B_SLICE = OZ_BN * OZ_KB;
+  constexpr int A_BYTES = S * A_SLICE, B_BYTES = S * B_SLICE, STAGE = A_BYTES + B_BYTES;
+  extern __shared__ __align__(128) uint8_t oz_smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(oz_smem + OZ_STAGES * STAGE);
+  uint64_t* empty = full + OZ_STAGES;
+  uint64_t* tmem_full = empty + OZ_STAGES;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ngroups = (p.nq + p.group - 1) / p.group;
+  const long per_batch = (long)p.nnt * p.nmt * p.splits;
+  const long nitems = per_batch * p.batches;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < OZ_STAGES; ++s) {
+      oz_mbar_init(&full[s], 1);
+      oz_mbar_init(&empty[s], 1);
+    }
+    oz_mbar_init(tmem_full, 1);
+    oz_mbar_init(tmem_empty, OZ_K1_THREADS - 64);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(oz_smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      long it = 0;
+      for (long item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const long zb = item / per_batch;
+        const int r = (int)(item - zb * per_batch);
+        const int nt = r % p.nnt, mt = (r / p.nnt) % p.nmt, sp = r / (p.nnt * p.nmt);
+        const int g0 = (int)((long)ngroups * sp / p.splits), g1 = (int)((long)ngroups * (sp + 1) / p.splits);
+        for (int g = g0; g < g1; ++g) {
+          const int q1 = min(p.nq, (g + 1) * p.group);
+          for (int q = g * p.group; q < q1; ++q) {
+            const int8_t* a = p.A + zb * p.a_bstride + (((long)q * p.nmt + mt) * p.nkb) * A_BYTES;
+            const int8_t* b = p.B + zb * p.b_bstride + (((long)(q + p.b_q0) * p.nnt + nt) * p.nkb) * B_BYTES;
+            for (int kb = 0; kb < p.nkb; ++kb, ++it) {
+              const int s = (int)(it % OZ_STAGES);
+              const uint32_t ph = (uint32_t)((it / OZ_STAGES) & 1);
+              oz_mbar_wait(&empty[s], ph ^ 1u);
+              oz_mbar_expect_tx(&full[s], STAGE);
+              uint8_t* sa = oz_smem + s * STAGE;
+              oz_bulk_load(sa, a + (long)kb * A_BYTES, A_BYTES, &full[s]);
+              oz_bulk_load(sa + A_BYTES, b + (long)kb * B_BYTES, B_BYTES, &full[s]);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24);
+      const uint32_t smem_base = oz_smem_u32(oz_smem);
+      long it = 0, n = 0;
+      for (long item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int r = (int)(item % per_batch);
+        const int sp = r / (p.nnt * p.nmt);
+        const int g0 = (int)((long)ngroups * sp / p.splits), g1 = (int)((long)ngroups * (sp + 1) / p.splits);
+        for (int g = g0; g < g1; ++g, ++n) {
+          if (n > 0) oz_mbar_wait(tmem_empty, (uint32_t)((n - 1) & 1));      // the epilogue has drained the previous group / tile
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const int q1 = min(p.nq, (g + 1) * p.group);
+          const long nsteps = (long)(q1 - g * p.group) * p.nkb;
+          for (long st = 0; st < nsteps; ++st, ++it) {
+            const int s = (int)(it % OZ_STAGES);
+            const uint32_t ph = (uint32_t)((it / OZ_STAGES) & 1);
+            oz_mbar_wait(&full[s], ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_base = smem_base + s * STAGE, b_base = a_base + A_BYTES;
+            const uint32_t later = st > 0 ? 1u : 0u;
+#pragma unroll
+            for (int i = 0; i < S; ++i) {
+              const uint64_t da = oz_smem_desc(a_base + i * A_SLICE, OZ_BM * 16, 128);
+#pragma unroll
+              for (int j0 = 0; j0 < S - i; j0 += 4) {
+                const int nj = (S - i - j0) < 4 ? (S - i - j0) : 4;
+                const uint64_t db = oz_smem_desc(b_base + j0 * (OZ_BN * 16), S * OZ_BN * 16, 128);
+                const uint32_t idesc = idesc0 | ((uint32_t)((nj * OZ_BN) >> 3) << 17);
+                oz_mma_i8(tmem_base + (uint32_t)((i + j0) * OZ_BN), da, db, idesc, (i > 0) ? 1u : later);
+              }
+            }
+            oz_commit(&empty[s]);
+          }
+          oz_commit(tmem_full);
+        }
+      }
+    }
+  } else {
+    const int quad = warp & 3, half = (warp - 2) >> 2;
+    const int row = quad * 32 + lane;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    constexpr int HC = OZ_BN / 2;
+    long n = 0;
+    for (long item = blockIdx.x; item < nitems; item += gridDim.x) {
+      const long zb = item / per_batch;
+      const int r = (int)(item - zb * per_batch);
+      const int nt = r % p.nnt, mt = (r / p.nnt) % p.nmt, sp = r / (p.nnt * p.nmt);
+      const int g0 = (int)((long)ngroups * sp / p.splits), g1 = (int)((long)ngroups * (sp + 1) / p.splits);
+      double acc[HC];
+#pragma unroll
+      for (int c = 0; c < HC; ++c) acc[c] = 0.0;
+      for (int g = g0; g < g1; ++g, ++n) {
+        const double sa = p.sa[zb * p.sa_bstride + (long)g * p.Mpad + mt * OZ_BM + row];
+        const double* sb = p.sb + zb * p.sb_bstride + (long)(g + p.b_q0 / p.group) * p.Npad + nt * OZ_BN + half * HC;
+        oz_mbar_wait(tmem_full, (uint32_t)(n & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        double v[HC];
+#pragma unroll
+        for (int k = 0; k < HC; ++k) v[k] = 0.0;
+#pragma unroll
+        for (int l = S - 1; l >= 0; --l) {
+          uint32_t rr[HC];
+#pragma unroll
+          for (int cc = 0; cc < HC; cc += 16) oz_tmem_ld16(taddr + (uint32_t)(l * OZ_BN + half * HC + cc), rr + cc);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int k = 0; k < HC; ++k)     // int32 -> fp64 through the 2^52 + 2^31 offset (no conversion instruction)
+            v[k] = fma(v[k], 0.00390625, __hiloint2double(0x43300000, (int)(rr[k] ^ 0x80000000u)) - 4503601774854144.0);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        oz_mbar_arrive(tmem_empty);                  // accumulators handed back: the next group's MMAs run under the lines below
+#pragma unroll
+        for (int k = 0; k < HC; ++k) acc[k] = fma(v[k], sa * sb[k], acc[k]);
+      }
+      double* w = p.W + zb * p.w_bstride + ((long)sp * p.Mpad + mt * OZ_BM + row) * p.Npad + nt * OZ_BN + half * HC;
+#pragma unroll
+      for (int c = 0; c < HC; c += 2) *reinterpret_cast<double2*>(w + c) = make_double2(p.alpha * acc[c], p.alpha * acc[c + 1]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // ---- fused half-transform: U = Loo . z on the INT8 tensor cores, written directly as the A planes of the contraction above ----
 //
 //   U[P][(x,i)][b] = sum_j Loo[P][i][j] zt[x][b][j]            (K = occupied count: a few k-steps per tile)
@@ -539,21 +694,28 @@ __global__ void __launch_bounds__(OZ_K1_THREADS, 1) oz_k1_kernel(const OzK1Param
       int8_t* dst = p.out + ((((long)P * p.nmt2 + (m >> 7)) * p.nkb2 + bt * 2) * S) * (long)A_SLICE + (long)(m & 127) * 16;
       oz_mbar_wait(tmem_full, (uint32_t)(n & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // Drain first, cut later: all levels of this thread's 32 columns are recombined into fp64 registers and the accumulators
+      // are handed back to the MMA warp BEFORE the digit extraction (two thirds of the epilogue's arithmetic), so the next
+      // tile's MMAs run under it.  (With the hand-back at the end of the epilogue the tensor pipe was active 43 % of the time.)
+      constexpr int HC = OZ_BN / 2;
+      double v[HC];
 #pragma unroll
-      for (int cc = 0; cc < OZ_BN / 2; cc += 16) {
-        const int c0 = half * (OZ_BN / 2) + cc;
-        double v[16];
+      for (int k = 0; k < HC; ++k) v[k] = 0.0;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) v[k] = 0.0;
+      for (int l = S - 1; l >= 0; --l) {
+        uint32_t r[HC];
 #pragma unroll
-        for (int l = S - 1; l >= 0; --l) {
-          uint32_t r[16];
-          oz_tmem_ld16(taddr + (uint32_t)(l * OZ_BN + c0), r);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int cc = 0; cc < HC; cc += 16) oz_tmem_ld16(taddr + (uint32_t)(l * OZ_BN + half * HC + cc), r + cc);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int k = 0; k < 16; ++k)     // int32 -> fp64 through the 2^52 + 2^31 offset (no conversion instruction)
-            v[k] = fma(v[k], 0.00390625, __hiloint2double(0x43300000, (int)(r[k] ^ 0x80000000u)) - 4503601774854144.0);
-        }
+        for (int k = 0; k < HC; ++k)     // int32 -> fp64 through the 2^52 + 2^31 offset (no conversion instruction)
+          v[k] = fma(v[k], 0.00390625, __hiloint2double(0x43300000, (int)(r[k] ^ 0x80000000u)) - 4503601774854144.0);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      oz_mbar_arrive(tmem_empty);
+#pragma unroll
+      for (int cc = 0; cc < HC; cc += 16) {
+        const int c0 = half * HC + cc;
         uint32_t pk[S][4];
 #pragma unroll
         for (int sl = 0; sl < S; ++sl)
@@ -561,7 +723,7 @@ __global__ void __launch_bounds__(OZ_K1_THREADS, 1) oz_k1_kernel(const OzK1Param
           for (int w = 0; w < 4; ++w) pk[sl][w] = 0u;
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-          double tt = v[k] * (f * sb[c0 + k]);            // U / output scale, |tt| < 64 by the a-priori bound
+          double tt = v[cc + k] * (f * sb[c0 + k]);       // U / output scale, |tt| < 64 by the a-priori bound
           int dg[S];
 #pragma unroll
           for (int sl = 0; sl < S; ++sl) {
@@ -588,8 +750,6 @@ __global__ void __launch_bounds__(OZ_K1_THREADS, 1) oz_k1_kernel(const OzK1Param
           for (int sl = 0; sl < S; ++sl) *reinterpret_cast<uint4*>(d + (long)sl * A_SLICE) = make_uint4(pk[sl][0], pk[sl][1], pk[sl][2], pk[sl][3]);
         }
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      oz_mbar_arrive(tmem_empty);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -786,7 +946,37 @@ inline int oz_cluster_width(int nnt) {
 }
 
 template <int S>
+inline int oz_gemm_p_launch(const OzGemmParams& p, cudaStream_t st) {
+  static bool attr_set[64] = {false};
+  static int sms[64] = {0};
+  int dev = 0;
+  XTD_CUDA(cudaGetDevice(&dev));
+  if (!attr_set[dev & 63]) {
+    XTD_CUDA(cudaFuncSetAttribute(oz_gemm_p_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oz_gemm_smem(S)));
+    XTD_CUDA(cudaDeviceGetAttribute(&sms[dev & 63], cudaDevAttrMultiProcessorCount, dev));
+    attr_set[dev & 63] = true;
+  }
+  const long items = (long)p.nmt * p.nnt * p.splits * p.batches;
+  const unsigned grid = (unsigned)std::min<long>(items, sms[dev & 63]);
+  oz_gemm_p_kernel<S><<<grid, OZ_K1_THREADS, oz_gemm_smem(S), st>>>(p);
+  XTD_COUNT_LAUNCH();
+  XTD_CUDA(cudaGetLastError());
+  return XTD_OK;
+}
+
+// XTD_OZ_PERSISTENT=0 selects the one-tile-per-CTA kernel (with its optional cluster multicast)
+inline bool oz_persistent() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("XTD_OZ_PERSISTENT");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
+}
+
+template <int S>
 inline int oz_gemm_launch(const OzGemmParams& p, cudaStream_t st) {
+  if (oz_persistent()) return oz_gemm_p_launch<S>(p, st);
   switch (oz_cluster_width(p.nnt)) {
     case 4: return oz_gemm_launch_cn<S, 4>(p, st);
     case 2: return oz_gemm_launch_cn<S, 2>(p, st);

@@ -1173,6 +1173,31 @@ static int launch_xc_split(const XcArgs2& a, cudaStream_t s) {
     XTD_CUDA(cudaFuncSetAttribute(xc_weight_split_kernel<XC_KIND_MCOL, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XC_SPLIT_SMEM_MAX));
     attr_set = true;
   }
+  // few trial vectors: the warps of a CTA share the point by orbital range (xc_weight_split_op_kernel); XTD_XC_OP_MAX_NVEC moves
+  // the switch-over (0: never)
+  static int op_max = getenv("XTD_XC_OP_MAX_NVEC") ? atoi(getenv("XTD_XC_OP_MAX_NVEC")) : 8;
+  if (a.nvec <= op_max) {
+    constexpr int NRK = (KIND == XC_KIND_UKS ? 2 : 1) * 4;
+    static bool op_attr_dev[64] = {false};
+    bool& op_set = op_attr_dev[dev & 63];
+    if (!op_set) {
+#define XTD_OP_ATTR(K, W_, XB_) \
+  XTD_CUDA(cudaFuncSetAttribute(xc_weight_split_op_kernel<K, W_, XB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XC_SPLIT_SMEM_MAX + 2 * 8 * 4 * 8 * 8))
+      XTD_OP_ATTR(XC_KIND_UKS, 1, 1); XTD_OP_ATTR(XC_KIND_UKS, 2, 1); XTD_OP_ATTR(XC_KIND_UKS, 1, 2); XTD_OP_ATTR(XC_KIND_UKS, 2, 2);
+      XTD_OP_ATTR(XC_KIND_UKS, 1, 4); XTD_OP_ATTR(XC_KIND_UKS, 2, 4);
+      XTD_OP_ATTR(XC_KIND_MCOL, 1, 1); XTD_OP_ATTR(XC_KIND_MCOL, 2, 1); XTD_OP_ATTR(XC_KIND_MCOL, 1, 2); XTD_OP_ATTR(XC_KIND_MCOL, 2, 2);
+      XTD_OP_ATTR(XC_KIND_MCOL, 1, 4); XTD_OP_ATTR(XC_KIND_MCOL, 2, 4);
+#undef XTD_OP_ATTR
+      op_set = true;
+    }
+    const int xb = a.nvec == 1 ? 1 : (a.nvec == 2 ? 2 : 4);
+    const size_t smem_op = smem + (size_t)2 * 8 * xb * NRK * 8;
+#define XTD_OP_LAUNCH(W_, XB_) xc_weight_split_op_kernel<KIND, W_, XB_><<<(unsigned)a.gb, 256, smem_op, s>>>(a)
+    if (even) { if (xb == 1) XTD_OP_LAUNCH(2, 1); else if (xb == 2) XTD_OP_LAUNCH(2, 2); else XTD_OP_LAUNCH(2, 4); }
+    else { if (xb == 1) XTD_OP_LAUNCH(1, 1); else if (xb == 2) XTD_OP_LAUNCH(1, 2); else XTD_OP_LAUNCH(1, 4); }
+#undef XTD_OP_LAUNCH
+    return XTD_OK;
+  }
   if (even) xc_weight_split_kernel<KIND, 2><<<(unsigned)a.gb, 32 * nwarps, smem, s>>>(a);
   else xc_weight_split_kernel<KIND, 1><<<(unsigned)a.gb, 32 * nwarps, smem, s>>>(a);
   return XTD_OK;

@@ -211,6 +211,8 @@ class SigmaEngine:
     def set_fxc(self, kind: str, fxc):
         if kind != "none":
             assert fxc.is_contiguous()
+            if self.plan.xc_scale != 1.0:       # the grid term is linear in the kernel table (Z-vector plans: hermi = 1 densities)
+                fxc = fxc * float(self.plan.xc_scale)
             # the ALDA0 kernel f[ng] is read on every call; the UKS / multicollinear tensors only by grid_commit
             (self._keep if kind == "alda0" else self._grid_keep).append(fxc)
         _lib.check(self.lib.xtd_set_fxc(self._h, _KIND[kind], _ptr(fxc) if kind != "none" else None), "xtd_set_fxc")
@@ -290,8 +292,6 @@ class SigmaEngine:
                 f = torch.from_numpy(np.ascontiguousarray(p.fxc_alda0[g0:g1])).to(eng.device)
             else:
                 f = torch.from_numpy(np.ascontiguousarray(p.fxc_mcol[..., g0:g1])).to(eng.device)
-            if plan.xc_scale != 1.0:            # the grid term is linear in the kernel table (Z-vector plans: hermi = 1 densities)
-                f = f * float(plan.xc_scale)
             eng.set_fxc(plan.xc_kind, f)
             del ao, w, f
             eng.grid_commit()                   # AO values are dropped before the tensor streams in

@@ -15,6 +15,8 @@ def plan_for(p, method: str):
         return planmod.build_sf_plan(p, isf=1, method=0)
     if method == "xsf":
         return planmod.build_sf_plan(p, isf=-1, method=0, sa=3, layout=planmod.LAYOUT_BLOCK, remove=True, hdiag_kind="xsf")
+    if method == "zvector":                 # the Z-vector operator on the same inputs as the X-TDA workloads
+        return planmod.build_zvector_plan(p)
     raise ValueError(method)
 
 
@@ -26,10 +28,10 @@ def default_workspace_bytes(dp: DeviceProblem, world: int = 1) -> int:
     p = dp.p
     pad = lambda n: (n + 15) // 16 * 16
     nv_i, no_i = p.nvir_b + 2, p.nocc_a + 2
-    resident = (dp.naux // world + 1) * (nv_i * pad(nv_i) + no_i * pad(no_i)) * 8 * (2 if dp.method == "xtda" else 1)
+    resident = (dp.naux // world + 1) * (nv_i * pad(nv_i) + no_i * pad(no_i)) * 8 * (2 if dp.method in ("xtda", "zvector") else 1)
     if dp.fxc_kind != "none":
         nve = 1 if dp.fxc_kind == "alda0" else dp.nvar
-        nch = 2 if dp.method == "xtda" else 1
+        nch = 2 if dp.method in ("xtda", "zvector") else 1
         resident += (dp.ng // world + 1) * (pad(nv_i) + pad(no_i)) * nve * nch * 8          # MO values on the grid
     return int(min(24 << 30, max(1 << 30, (free - resident) * 0.55)))
 
