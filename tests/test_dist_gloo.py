@@ -68,7 +68,7 @@ def _worker(rank, world, port, method, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("method", ["sf_down", "xtda", "xsf"])
+@pytest.mark.parametrize("method", ["sf_down", "xtda", "xsf", "zvector"])
 def test_two_rank_partial_sigma_allreduce(method, tmp_path):
     import torch.multiprocessing as mp
     world = 2

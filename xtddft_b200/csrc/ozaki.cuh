@@ -93,6 +93,69 @@ __global__ void oz_rowmax_kernel(double* __restrict__ scale, int rows_pad, const
 }
 
 // one thread: 16 consecutive k of one row -> S 16-byte chunks.  grid (2 nkb, rows_pad / 128, nq), block 128 (lane <-> row)
+// 16 consecutive elements t[k] (already divided by the row scale: |t| < 64) -> S balanced radix-256 digit planes, packed as the
+// 16-byte row chunk of every plane: x = sum_l d_l 2^(-8l), d_0 in [-64, 64], d_l in [-128, 127].
+// S <= 6: in integer arithmetic.  q = floor(t 2^(8(S-1))) lands in the low mantissa bits of RD(t 2^(8(S-1)) + 1.5 2^52) (one FMA;
+// |q| < 2^46), and adding 128 at every lower byte position turns the bytes of q into the balanced digits,
+//   q + B = d_0 2^(8(S-1)) + sum_{l>=1} (d_l + 128) 2^(8(S-1-l)),
+// the same digits as floor-then-carry (the representation is unique); (d_l + 128) ^ 0x80 is the int8 pattern of d_l.  One FMA, one
+// 64-bit add and a few byte permutes per element instead of three fp64 operations and a carry step per digit (the fused
+// half-transform's epilogue was bound by exactly that arithmetic: two warps per scheduler, ~85 dependent instructions per element).
+// S = 7, 8 (q would not fit 51 bits): digit by digit, MSB first with round-down, then the carry pass.
+template <int S>
+__device__ __forceinline__ void oz_digits16(const double (&t)[16], uint32_t (&pk)[S][4]) {
+  const double magic = 6755399441055744.0;   // 1.5 * 2^52: RD(x + magic) has floor(x) in its low mantissa bits (two's complement)
+  if constexpr (S <= 6) {
+    constexpr double SCL = (double)(1ull << (8 * (S - 1)));
+    constexpr unsigned long long BAL = 128ull * (((1ull << (8 * (S - 1))) - 1ull) / 255ull);
+    constexpr unsigned long long CADD = BAL - 0x4338000000000000ull;      // minus the bit pattern of 1.5 * 2^52
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      uint32_t lo[4], hi[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const unsigned long long q = (unsigned long long)__double_as_longlong(__fma_rd(t[4 * w + j], SCL, magic)) + CADD;
+        lo[j] = (uint32_t)q;
+        hi[j] = (uint32_t)(q >> 32);
+      }
+#pragma unroll
+      for (int pos = 0; pos < S; ++pos) {                 // byte position from the least significant digit
+        const uint32_t* src = pos < 4 ? lo : hi;
+        const uint32_t sel = (uint32_t)(pos & 3) | ((uint32_t)(4 + (pos & 3)) << 4);
+        const uint32_t t01 = __byte_perm(src[0], src[1], sel), t23 = __byte_perm(src[2], src[3], sel);
+        pk[S - 1 - pos][w] = __byte_perm(t01, t23, 0x5410) ^ (pos < S - 1 ? 0x80808080u : 0u);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int sl = 0; sl < S; ++sl)
+#pragma unroll
+      for (int w = 0; w < 4; ++w) pk[sl][w] = 0u;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      double tt = t[k];
+      int dg[S];
+#pragma unroll
+      for (int sl = 0; sl < S; ++sl) {
+        const double u = (sl == 0) ? __dadd_rd(tt, magic) : __fma_rd(tt, 256.0, magic);      // floor: the remainder stays in [0, 1)
+        const double qd = u - magic;
+        tt = (sl == 0) ? (tt - qd) : fma(tt, 256.0, -qd);
+        dg[sl] = __double2loint(u);             // floor(t) in [-64, 63], then digits in [0, 255]
+      }
+      int carry = 0;                            // balance: [0, 255] -> [-128, 127] with a carry into the next higher digit
+#pragma unroll
+      for (int sl = S - 1; sl >= 1; --sl) {
+        const int vv = dg[sl] + carry;
+        carry = vv >= 128 ? 1 : 0;
+        dg[sl] = vv - (carry << 8);
+      }
+      dg[0] += carry;
+#pragma unroll
+      for (int sl = 0; sl < S; ++sl) pk[sl][k >> 2] |= ((uint32_t)dg[sl] & 0xffu) << ((k & 3) * 8);
+    }
+  }
+}
+
 template <int S, bool TRANS>
 __global__ void __launch_bounds__(128) oz_slice_kernel(int8_t* __restrict__ out, const double* __restrict__ scale, int rows_pad,
                                                        const double* __restrict__ X, long ld, long sq, int rows, int K, int RT, int nkb,
@@ -131,34 +194,10 @@ __global__ void __launch_bounds__(128) oz_slice_kernel(int8_t* __restrict__ out,
   }
   // 1 / scale for a power of two: flip the exponent
   const double inv = sc > 0.0 ? __hiloint2double(0x7fe00000 - __double2hiint(sc), 0) : 0.0;
-  const double magic = 6755399441055744.0;   // 1.5 * 2^52: RD(t + magic) has floor(t) in its low mantissa bits (two's complement)
   uint32_t pk[S][4];
 #pragma unroll
-  for (int sl = 0; sl < S; ++sl)
-#pragma unroll
-    for (int w = 0; w < 4; ++w) pk[sl][w] = 0u;
-#pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    double t = x[k] * inv;                    // |t| < 64
-    int dg[S];
-#pragma unroll
-    for (int sl = 0; sl < S; ++sl) {
-      const double u = (sl == 0) ? __dadd_rd(t, magic) : __fma_rd(t, 256.0, magic);      // floor: the remainder stays in [0, 1)
-      const double qd = u - magic;
-      t = (sl == 0) ? (t - qd) : fma(t, 256.0, -qd);
-      dg[sl] = __double2loint(u);             // floor(t) in [-64, 63], then digits in [0, 255]
-    }
-    int carry = 0;                            // balance: [0, 255] -> [-128, 127] with a carry into the next higher digit
-#pragma unroll
-    for (int sl = S - 1; sl >= 1; --sl) {
-      const int v = dg[sl] + carry;
-      carry = v >= 128 ? 1 : 0;
-      dg[sl] = v - (carry << 8);
-    }
-    dg[0] += carry;
-#pragma unroll
-    for (int sl = 0; sl < S; ++sl) pk[sl][k >> 2] |= ((uint32_t)dg[sl] & 0xffu) << ((k & 3) * 8);
-  }
+  for (int k = 0; k < 16; ++k) x[k] *= inv;   // |t| < 64
+  oz_digits16<S>(x, pk);
   // plane-major image (A): [plane][chunk][row]; stacked image (B): [chunk][plane][row]
   int8_t* dst = out + ((((long)q * nrt + rt) * nkb + (c2 >> 1)) * S) * ((long)RT * OZ_KB) + (long)r * 16 +
                 (stacked ? (long)(c2 & 1) * S * RT * 16 : (long)(c2 & 1) * RT * 16);
@@ -717,32 +756,10 @@ __global__ void __launch_bounds__(OZ_K1_THREADS, 1) oz_k1_kernel(const OzK1Param
       for (int cc = 0; cc < HC; cc += 16) {
         const int c0 = half * HC + cc;
         uint32_t pk[S][4];
+        double tt[16];
 #pragma unroll
-        for (int sl = 0; sl < S; ++sl)
-#pragma unroll
-          for (int w = 0; w < 4; ++w) pk[sl][w] = 0u;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          double tt = v[cc + k] * (f * sb[c0 + k]);       // U / output scale, |tt| < 64 by the a-priori bound
-          int dg[S];
-#pragma unroll
-          for (int sl = 0; sl < S; ++sl) {
-            const double u = (sl == 0) ? __dadd_rd(tt, magic) : __fma_rd(tt, 256.0, magic);
-            const double qd = u - magic;
-            tt = (sl == 0) ? (tt - qd) : fma(tt, 256.0, -qd);
-            dg[sl] = __double2loint(u);
-          }
-          int carry = 0;
-#pragma unroll
-          for (int sl = S - 1; sl >= 1; --sl) {
-            const int vv = dg[sl] + carry;
-            carry = vv >= 128 ? 1 : 0;
-            dg[sl] = vv - (carry << 8);
-          }
-          dg[0] += carry;
-#pragma unroll
-          for (int sl = 0; sl < S; ++sl) pk[sl][k >> 2] |= ((uint32_t)dg[sl] & 0xffu) << ((k & 3) * 8);
-        }
+        for (int k = 0; k < 16; ++k) tt[k] = v[cc + k] * (f * sb[c0 + k]);       // U / output scale, |tt| < 64 by the a-priori bound
+        oz_digits16<S>(tt, pk);
         if (valid && bt * 2 + (c0 >> 5) < p.nkb2) {     // (a column tile may reach past the last k block of the output operand)
           // columns c0 .. c0+15 of this tile = k block (bt * 2 + c0 / 32) of the output operand, 16-byte chunk (c0 / 16) & 1
           int8_t* d = dst + (long)(c0 >> 5) * S * A_SLICE + ((c0 >> 4) & 1) * (OZ_BM * 16);
@@ -964,19 +981,24 @@ inline int oz_gemm_p_launch(const OzGemmParams& p, cudaStream_t st) {
   return XTD_OK;
 }
 
-// XTD_OZ_PERSISTENT=0 selects the one-tile-per-CTA kernel (with its optional cluster multicast)
-inline bool oz_persistent() {
+// Which kernel runs a contraction: the persistent one pays off when a tile holds one or two accumulation groups (grid GEMMs, short
+// contractions: config 5 grid GEMMs 163 -> 148 ms at a LOWER clock), the one-tile-per-CTA kernel with its cluster multicast of the A
+// tile for long contractions (exchange: 587 vs 646 ms -- the step is power-capped and the multicast halves the A traffic per SM).
+// XTD_OZ_PERSISTENT = 0 never / 1 always / unset: by the number of groups per tile.
+inline bool oz_persistent(const OzGemmParams& p) {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("XTD_OZ_PERSISTENT");
-    v = e ? atoi(e) : 1;
+    v = e ? atoi(e) : 2;
   }
-  return v != 0;
+  if (v != 2) return v != 0;
+  const int ngroups = (p.nq + p.group - 1) / p.group;
+  return ngroups <= 2 * p.splits;
 }
 
 template <int S>
 inline int oz_gemm_launch(const OzGemmParams& p, cudaStream_t st) {
-  if (oz_persistent()) return oz_gemm_p_launch<S>(p, st);
+  if (oz_persistent(p)) return oz_gemm_p_launch<S>(p, st);
   switch (oz_cluster_width(p.nnt)) {
     case 4: return oz_gemm_launch_cn<S, 4>(p, st);
     case 2: return oz_gemm_launch_cn<S, 2>(p, st);

@@ -104,7 +104,7 @@ constexpr long XC_SPLIT_SMEM_MAX = 200 * 1024;   // shared memory of the split-g
 // contraction lengths below this stay on the FP64 DMMA GEMM where a kernel offers the choice (XTD_OZ_SHORT_K overrides; tests use 0)
 static int oz_short_k() {
   const char* e = getenv("XTD_OZ_SHORT_K");
-  return e ? atoi(e) : 512;
+  return e ? atoi(e) : 100;
 }
 #define OZ_SHORT_K (oz_short_k())
 constexpr int OZ_XC_KQ = 8192;   // grid points per int32 accumulation group of the backward grid GEMM (8192 * S * 2^14 < 2^31)
