@@ -374,14 +374,15 @@ __global__ void __launch_bounds__(512, 2) xc_weight_split_kernel(const XcArgs2 a
       sphiv[s] = cur; cur += 3 * nvp[s];
       const double* p = a.phi[s] + (a.g0 + g) * a.ldphi[s];
       const double* pv = a.phiv[s] + (a.g0 + g) * a.ldphiv[s];
-      for (int i = threadIdx.x; i < 4 * nop[s]; i += blockDim.x) {
-        const int k = i / nop[s], o = i - k * nop[s];
-        sphi[s][i] = o < a.no[s] ? p[k * a.phi_comp[s] + o] : 0.0;
-      }
-      for (int i = threadIdx.x; i < 3 * nvp[s]; i += blockDim.x) {
-        const int k = i / nvp[s], v = i - k * nvp[s];
-        sphiv[s][i] = v < a.nv[s] ? pv[(k + 1) * a.phiv_comp[s] + v] : 0.0;
-      }
+      // 16-byte loads, one independent load per component in flight (the rows are padded with zeros past an odd orbital count)
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        for (int o = threadIdx.x * 2; o < nop[s]; o += blockDim.x * 2)
+          *reinterpret_cast<double2*>(sphi[s] + k * nop[s] + o) = *reinterpret_cast<const double2*>(p + k * a.phi_comp[s] + o);
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        for (int v = threadIdx.x * 2; v < nvp[s]; v += blockDim.x * 2)
+          *reinterpret_cast<double2*>(sphiv[s] + k * nvp[s] + v) = *reinterpret_cast<const double2*>(pv + (k + 1) * a.phiv_comp[s] + v);
     }
   }
   double fk[(KIND == XC_KIND_UKS) ? NR : NVAR];
@@ -495,14 +496,15 @@ __global__ void __launch_bounds__(256, (XB >= 4 ? 2 : 3)) xc_weight_split_op_ker
     sphiv[s] = cur; cur += 3 * nvp[s];
     const double* p = a.phi[s] + (a.g0 + g) * a.ldphi[s];
     const double* pv = a.phiv[s] + (a.g0 + g) * a.ldphiv[s];
-    for (int i = threadIdx.x; i < 4 * nop[s]; i += blockDim.x) {
-      const int k = i / nop[s], o = i - k * nop[s];
-      sphi[s][i] = o < a.no[s] ? p[k * a.phi_comp[s] + o] : 0.0;
-    }
-    for (int i = threadIdx.x; i < 3 * nvp[s]; i += blockDim.x) {
-      const int k = i / nvp[s], v = i - k * nvp[s];
-      sphiv[s][i] = v < a.nv[s] ? pv[(k + 1) * a.phiv_comp[s] + v] : 0.0;
-    }
+    // 16-byte loads, one independent load per component in flight (the rows are padded with zeros past an odd orbital count)
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      for (int o = threadIdx.x * 2; o < nop[s]; o += blockDim.x * 2)
+        *reinterpret_cast<double2*>(sphi[s] + k * nop[s] + o) = *reinterpret_cast<const double2*>(p + k * a.phi_comp[s] + o);
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      for (int v = threadIdx.x * 2; v < nvp[s]; v += blockDim.x * 2)
+        *reinterpret_cast<double2*>(sphiv[s] + k * nvp[s] + v) = *reinterpret_cast<const double2*>(pv + (k + 1) * a.phiv_comp[s] + v);
   }
   double* red = cur;                     // [2][NWARPS][XB][NR] partial densities
   double fk[NR];
