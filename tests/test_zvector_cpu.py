@@ -91,3 +91,23 @@ def test_solver_control_flow_against_dense_solve(restricted):
     z, conv, cycles, res = solve_linear(it.sigma, b, pl.hdiag, tol=1e-11, max_cycle=pl.ext_dim, backend=NumpyVectors(pl.ext_dim))
     assert conv and cycles < pl.ext_dim and res < 1e-11
     assert np.abs(z - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("tag", ["roks_gga_no2", "uks_gga_no2"])
+def test_from_mean_field_object(golden_dir, tag):
+    """`ZVector(mf)` takes the mean-field object through `adapters.from_pyscf(kernel="uks")`: on the stand-in object the reference's
+    `grad_elec` was run on, what the adapter extracts, compiled to the Z-vector plan, reproduces the reference's closure."""
+    from adapter_fakes import fake_scf, packed_df
+    from xtddft_b200 import adapters
+    d, p = load_case(golden_dir, tag)
+    with fake_scf() as (FakeROKS, FakeUKS):
+        mf = (FakeROKS if p.restricted else FakeUKS)(p)
+        mf.with_df = packed_df(p)
+        q = adapters.problem_from_mf(mf, kernel="uks")
+    il = np.tril_indices(p.nao)
+    full = np.zeros((q.naux, p.nao, p.nao))
+    full[:, il[0], il[1]] = q.cderi_packed
+    full[:, il[1], il[0]] = q.cderi_packed
+    q.cderi, q.cderi_packed = full, None
+    it = PlanInterpreter(planmod.build_zvector_plan(q, with_diag=False), q)
+    assert _rel(it.sigma(d["x"]), d["ax"]) < 1e-12
