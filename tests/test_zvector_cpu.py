@@ -111,3 +111,23 @@ def test_from_mean_field_object(golden_dir, tag):
     q.cderi, q.cderi_packed = full, None
     it = PlanInterpreter(planmod.build_zvector_plan(q, with_diag=False), q)
     assert _rel(it.sigma(d["x"]), d["ax"]) < 1e-12
+
+
+def test_solver_edge_cases():
+    """Zero right-hand side, an exhausted cycle budget (reported, not raised), a non-symmetric operator, and a right-hand side that is
+    an eigenvector of the preconditioned operator (one cycle)."""
+    n = 40
+    rng = np.random.default_rng(11)
+    a = np.diag(np.linspace(1.0, 3.0, n)) + 0.05 * rng.standard_normal((n, n))          # non-symmetric, diagonally dominant
+    op = lambda x: x @ a.T
+    vb = NumpyVectors(n)
+    z, conv, cycles, res = solve_linear(op, np.zeros(n), np.diagonal(a), tol=1e-12, backend=vb)
+    assert conv and cycles == 0 and res == 0.0 and not z.any()
+    b = rng.standard_normal(n)
+    z, conv, cycles, res = solve_linear(op, b, np.diagonal(a), tol=1e-12, max_cycle=3, backend=vb)
+    assert not conv and cycles == 3 and res > 1e-12
+    z, conv, cycles, res = solve_linear(op, b, np.diagonal(a), tol=1e-12, max_cycle=n, backend=vb)
+    assert conv and np.abs(z - np.linalg.solve(a, b)).max() < 1e-10
+    d = np.linspace(1.0, 3.0, n)
+    z, conv, cycles, res = solve_linear(lambda x: x * d, b, d, tol=1e-12, backend=vb)     # exact preconditioner
+    assert conv and cycles == 1 and np.abs(z - b / d).max() < 1e-13
