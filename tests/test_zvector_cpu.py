@@ -103,7 +103,8 @@ def test_from_mean_field_object(golden_dir, tag):
     with fake_scf() as (FakeROKS, FakeUKS):
         mf = (FakeROKS if p.restricted else FakeUKS)(p)
         mf.with_df = packed_df(p)
-        q = adapters.problem_from_mf(mf, kernel="uks")
+        q = adapters.problem_from_mf(mf, kernel="uks", rohf_fock="device")       # the call `ZVector(mf)` makes
+    assert q.fock_hf is None
     il = np.tril_indices(p.nao)
     full = np.zeros((q.naux, p.nao, p.nao))
     full[:, il[0], il[1]] = q.cderi_packed

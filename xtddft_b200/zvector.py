@@ -98,7 +98,8 @@ class ZVector:
 
     def __init__(self, mf, *, with_diag: bool = True, max_nvec: int = 4, workspace_bytes: Optional[int] = None, distributed: bool = True):
         from .drivers_common import make_engine
-        self.problem = p = problem_from_mf(mf, kernel="uks")
+        # the Z-vector plan uses the KS Fock blocks only: the ROHF-form Fock build of the spin-adaptation terms is skipped
+        self.problem = p = problem_from_mf(mf, kernel="uks", rohf_fock="device")
         self.restricted = bool(p.restricted)
         self.nc, self.no, self.nv = p.nc, p.no, p.nv
         self.plan = planmod.build_zvector_plan(p, with_diag=with_diag)
