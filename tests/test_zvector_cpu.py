@@ -132,3 +132,30 @@ def test_solver_edge_cases():
     d = np.linspace(1.0, 3.0, n)
     z, conv, cycles, res = solve_linear(lambda x: x * d, b, d, tol=1e-12, backend=vb)     # exact preconditioner
     assert conv and cycles == 1 and np.abs(z - b / d).max() < 1e-13
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_rhs_plans_against_the_reference(golden_dir, tag):
+    """The right-hand side assembled from two engine plans on the whole MO space (general J / K / f_xc response of the relaxed
+    difference densities, spin-flip exchange of the transition density) reproduces the `w` / `(wvoa, wvob)` the reference's own
+    `grad_elec` built (tests/golden/make_golden_zvector.py)."""
+    from xtddft_b200.zvector import assemble_rhs
+    d, p = load_case(golden_dir, tag)
+    resp = PlanInterpreter(planmod.build_mo_response_plan(p, range_separated=False), p)
+    sfx = PlanInterpreter(planmod.build_mo_sf_exchange_plan(p), p) if p.hyb != 0.0 else None
+    rhs = assemble_rhs(p, d["amp"].reshape(p.nc, p.nv), lambda t: resp.sigma(t.reshape(1, -1))[0],
+                       (lambda x: sfx.sigma(x.reshape(1, -1))[0]) if sfx is not None else None)
+    assert _rel(rhs, d["rhs"]) < 1e-12
+
+
+def test_mo_response_plan_against_oracle():
+    """The whole-MO-space plan is the general `vresp`: for arbitrary (non-symmetric) MO-basis densities, all blocks, with the
+    range-separated part."""
+    from oracle.sigma import response_uks
+    p = make_problem(11, 3, 2, 6, 9, 30, xctype="GGA", hyb=0.25, restricted=False, seed=91, omega=0.33, alpha=0.65)
+    it = PlanInterpreter(planmod.build_mo_response_plan(p), p)
+    t = np.random.default_rng(2).standard_normal((2, p.nmo, p.nmo))
+    dm = np.stack([p.mo_coeff[s] @ t[s] @ p.mo_coeff[s].T for s in (0, 1)])
+    v1 = response_uks(p, dm[:, None])[:, 0]
+    ref = np.stack([p.mo_coeff[s].T @ v1[s] @ p.mo_coeff[s] for s in (0, 1)])
+    assert _rel(it.sigma(t.reshape(1, -1))[0].reshape(2, p.nmo, p.nmo), ref) < 1e-12

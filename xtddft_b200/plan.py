@@ -632,3 +632,56 @@ def build_zvector_plan(p: ProblemData, with_diag: bool = True) -> Plan:
     plan.layout_entries, plan.layout_coefs = ent, np.ones(ent.shape[0])
     plan.meta = dict(nc=nc, no=no, nv=nv, o2off=o2off, v2off=v2off)
     return plan
+
+
+# --------------------------------------------------------------------------------------------------
+# Right-hand side of the Z-vector equation: responses of densities with occupied-occupied / virtual-virtual blocks
+# --------------------------------------------------------------------------------------------------
+def build_mo_response_plan(p: ProblemData, range_separated: bool = True) -> Plan:
+    """`vresp(D)` for ARBITRARY MO-basis densities, all blocks out: one "vector" is [T_a (nmo x nmo) | T_b (nmo x nmo)] row-major,
+    D_s = C_s T_s C_s^T, and the result is C_s^T (f_xc[D] + J[D_a + D_b] - hyb K[D_s]) C_s in the same layout.
+
+    The channels of the engine are index SETS, not "occupied" and "virtual": with both sets = all MOs of a spin the direct exchange
+    term is the general K build, a full-width Coulomb block the general J build and the MO-on-grid contraction the general f_xc
+    response.  This is what the Q matrix of the gradients needs for the relaxed difference densities T (virtual-virtual block for
+    alpha, occupied-occupied for beta: `mf.get_jk(mol, (dmzvva, dmzoob), hermi=1)` + `f1oo`, grad_hb/tdroks_sfu.py:241-251,
+    tduks_sfu.py:219-229) and the W matrix for the occupied-occupied projection of G[Z^S] (:339-351).  A one-off per state, so the
+    MO-resident tensor of the whole MO space (naux x nmo^2 per spin) is affordable up to ~1000 basis functions on one GPU; shard beyond.
+    `range_separated=False` leaves the long-range exchange out, as the reference's Q matrix does (`vk * hyb` only, tdroks_sfu.py:247-251)."""
+    nmo = p.nmo
+    idx = np.arange(nmo, dtype=np.int32)
+    chs = [ChannelSpec(s, idx.copy(), s, idx.copy(), [(0, nmo)], [(0, nmo)]) for s in (0, 1)]
+    plan = Plan("mo_response", chs)
+    if p.has_df:
+        plan.j_blocks = [JBlock(0, 0, nmo, 0, nmo), JBlock(1, 0, nmo, 0, nmo)]
+        plan.j_mix = np.ones((2, 2))
+        if p.hybrid:
+            for ci in (0, 1):
+                plan.k_terms.append(KTerm(0, ci, np.full((1, 1, 1, 1), -p.hyb)))
+                if range_separated and p.omega != 0.0 and p.has_df_lr:
+                    plan.k_terms.append(KTerm(1, ci, np.full((1, 1, 1, 1), -(p.alpha - p.hyb))))
+    if p.xctype != "HF":
+        plan.xc_kind = "uks_tau" if p.xctype == "MGGA" else "uks"
+    n2 = nmo * nmo
+    ii, aa = np.meshgrid(np.arange(nmo), np.arange(nmo), indexing="ij")
+    ent = np.concatenate([np.stack([s * n2 + np.arange(n2), np.full(n2, s), ii.ravel(), aa.ravel()], axis=1) for s in (0, 1)])
+    plan.ext_dim, plan.layout_entries, plan.layout_coefs = 2 * n2, ent.astype(np.int64), np.ones(2 * n2)
+    plan.hdiag = np.ones(2 * n2)
+    plan.meta = dict(nmo=nmo)
+    return plan
+
+
+def build_mo_sf_exchange_plan(p: ProblemData) -> Plan:
+    """K[X] of a spin-flip density X = C_b z C_a^T in the mixed MO basis: one "vector" is z (nmo_b x nmo_a) row-major, the result is
+    C_b^T K[X] C_a (`mf.get_k(mol, dmt, hermi=0)` projected as `veff0mo`, grad_hb/tdroks_sfu.py:249-254; unscaled: multiply by hyb)."""
+    nmo = p.nmo
+    idx = np.arange(nmo, dtype=np.int32)
+    plan = Plan("mo_sf_exchange", [ChannelSpec(1, idx.copy(), 0, idx.copy(), [(0, nmo)], [(0, nmo)])])
+    plan.k_terms = [KTerm(0, 0, np.ones((1, 1, 1, 1)))]
+    n2 = nmo * nmo
+    ii, aa = np.meshgrid(np.arange(nmo), np.arange(nmo), indexing="ij")
+    ent = np.stack([np.arange(n2), np.zeros(n2, dtype=np.int64), ii.ravel(), aa.ravel()], axis=1)
+    plan.ext_dim, plan.layout_entries, plan.layout_coefs = n2, ent.astype(np.int64), np.ones(n2)
+    plan.hdiag = np.ones(n2)
+    plan.meta = dict(nmo=nmo)
+    return plan

@@ -83,6 +83,41 @@ def solve_linear(aop, b, hdiag, *, tol: float = 1e-12, max_cycle: int = 40, lind
     return vb.to_host(x)[0], bool(conv), k, res
 
 
+def assemble_rhs(p, v, apply_response, apply_sf_exchange):
+    """Right-hand side of the Z-vector equation for the spin-flip-up TDA state with amplitudes v[nc, nv], collinear kernel
+    (`collinear_samples <= 0`: f1vo = k1ao = 0) -- grad_hb/tdroks_sfu.py:207-274 (ROKS: `w`), grad_hb/tduks_sfu.py:205-244 (UKS:
+    `(wvoa, wvob)`, returned stacked).  The contractions run as two engine plans on MO-basis matrices:
+
+      apply_response(t[2, nmo, nmo]) -> C_s^T (f_xc[T] + J[T_a + T_b] - hyb K[T_s]) C_s      (plan.build_mo_response_plan)
+      apply_sf_exchange(x[nmo, nmo]) -> C_b^T K[C_b x C_a^T] C_a                              (plan.build_mo_sf_exchange_plan)
+
+    what is left here is the block bookkeeping of the reference (a few small einsums on nmo x nmo matrices)."""
+    nc, no, nv, nmo = p.nc, p.no, p.nv, p.nmo
+    na, nb = nc + no, nc
+    v = np.asarray(v, dtype=np.float64).reshape(nc, nv)
+    dvva = v.T @ v                                   # T_ab  (:210)
+    doob = -(v @ v.T)                                # T_ij  (:211)
+    t = np.zeros((2, nmo, nmo))
+    t[0, na:, na:] = dvva
+    t[1, :nb, :nb] = doob
+    g = np.asarray(apply_response(t)).reshape(2, nmo, nmo)           # veff0doo in the MO basis (:247-251)
+    wvoa = g[0][na:, :na].copy()
+    wvob = g[1][nb:, :nb].copy()
+    if p.hyb != 0.0:
+        x = np.zeros((nmo, nmo))
+        x[:nb, na:] = v                              # X: beta occupied -> alpha virtual (:214)
+        veff0mo = -p.hyb * np.asarray(apply_sf_exchange(x)).reshape(nmo, nmo)      # (:249,254)
+        wvoa -= np.einsum("jk,jc->ck", veff0mo[:nc, :na], v)
+        wvob += np.einsum("ac,ka->ck", veff0mo.T[na:, nc:], v)
+    if not p.restricted:
+        return np.hstack([wvoa.ravel(), wvob.ravel()])
+    fa, fb = p.fock_ks
+    wvoa -= np.einsum("ac,ka->ck", dvva, fa[:na, na:])              # (:256)
+    wvob += np.einsum("jk,jc->ck", doob, fb[:nc, nc:])              # (:258; the pure branch's :269 is a shape error, DESIGN section 9)
+    wvc = wvoa[:, :nc] + wvob[no:, :]
+    return np.hstack([wvc.ravel(), wvoa[:, nc:].ravel(), wvob[:no, :].ravel()]) * 2
+
+
 class ZVector:
     """Operator and solver of the Z-vector equation for one mean-field reference.
 
@@ -122,6 +157,21 @@ class ZVector:
                                                                     max_cycle=max_cycle or self.cphf_max_cycle, lindep=lindep,
                                                                     verbose=verbose)
         return z
+
+    def rhs(self, v, workspace_bytes: Optional[int] = None):
+        """Right-hand side for the state with spin-flip-up amplitudes v[nc, nv] (collinear kernel), through two more engine plans on
+        the whole MO space (`assemble_rhs`); the engines are built on the first call.  CPU-verified against the reference's own
+        right-hand sides through the plan interpreter (tests/test_zvector_cpu.py); first GPU run pending."""
+        from .drivers_common import make_engine
+        if getattr(self, "_rhs_engines", None) is None:
+            p = self.problem
+            self._rhs_engines = (make_engine(planmod.build_mo_response_plan(p, range_separated=False), p, max_nvec=1,
+                                             workspace_bytes=workspace_bytes),
+                                 make_engine(planmod.build_mo_sf_exchange_plan(p), p, max_nvec=1, workspace_bytes=workspace_bytes)
+                                 if p.hyb != 0.0 else None)
+        resp, sfx = self._rhs_engines
+        return assemble_rhs(self.problem, v, lambda t: resp.sigma_host(t.reshape(1, -1))[0],
+                            (lambda x: sfx.sigma_host(x.reshape(1, -1))[0]) if sfx is not None else None)
 
     def split(self, z):
         """The rotation blocks the reference continues with: ROKS (zvc, zvo, zoc) (tdroks_sfu.py:328-330), UKS (z1a, z1b)."""
