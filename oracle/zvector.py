@@ -38,6 +38,20 @@ def internal_densities(p, v):
     return dvva, doob, va @ dvva @ va.T, ob @ doob @ ob.T, ob @ v @ va.T
 
 
+def _rhs_intermediates(p, v):
+    """veff0doo (AO, both spins) and veff0mo of rhs_common, for the W matrix."""
+    dvva, doob, dmzvva, dmzoob, dmt = internal_densities(p, v)
+    dmoo = np.stack([dmzvva, dmzoob])
+    f1oo = numint.nr_uks_fxc(p.ao, p.weights, p.fxc_uks, dmoo[:, None])[:, 0] if p.xctype != "HF" else np.zeros_like(dmoo)
+    vj = jk.get_j(p.cderi, dmoo)
+    veff0doo = (vj[0] + vj[1])[None] + f1oo
+    vk1 = np.zeros_like(dmt)
+    if p.hyb != 0.0:
+        veff0doo = veff0doo - p.hyb * jk.get_k(p.cderi, dmoo)
+        vk1 = p.hyb * jk.get_k(p.cderi, dmt)
+    return veff0doo, p.mo_coeff[1].T @ (-vk1) @ p.mo_coeff[0]
+
+
 def rhs_common(p, v):
     """The part of the Q matrix both references share (tdroks_sfu.py:241-255,257 / tduks_sfu.py:219-234), collinear kernel
     (`collinear_samples <= 0`: f1vo = 0, k1ao = 0): veff0doo = J[T_a + T_b] - hyb K[T_s] + f_xc[T]; veff0mo = C_b^T (-hyb K[X]) C_a."""
@@ -166,3 +180,78 @@ def uks_solve(p, wvoa, wvob):
     h1 = np.hstack([wvoa.ravel(), wvob.ravel()])
     a = dense_operator(uks_fvind(p), h1.size) + np.diag(uks_gaps(p))
     return np.linalg.solve(a, -h1)
+
+
+def roks_w_matrix(p, v, z):
+    """W matrix `im0` (AO basis) of tdroks_sfu.py:328-356 from the solution z = [zvc | zvo | zoc] of the Z-vector equation."""
+    nc, no, nv = p.nc, p.no, p.nv
+    na = nc + no
+    oa, va, ob, vb = _orbitals(p)
+    fa, fb = p.fock_ks
+    f = sym_fock(p)
+    dvva, doob, _, _, _ = internal_densities(p, v)
+    veff0doo, veff0mo = _rhs_intermediates(p, v)
+    z = np.asarray(z).ravel()
+    zvc = z[:nv * nc].reshape(nv, nc)
+    zvo = z[nv * nc:nv * nc + nv * no].reshape(nv, no)
+    zoc = z[nv * nc + nv * no:].reshape(no, nc)
+    z1a, z1b = np.hstack((zvc, zvo)), np.vstack((zoc, zvc))
+    z1ao = np.stack([va @ z1a @ oa.T, vb @ z1b @ ob.T])
+    veff = response_uks(p, ((z1ao + z1ao.transpose(0, 2, 1)) / 2)[:, None])[:, 0]
+    n = p.nmo
+    im0a, im0b = np.zeros((n, n)), np.zeros((n, n))
+    im0a[:na, :na] += fa[:na, :na]
+    im0b[:nc, :nc] += fb[:nc, :nc]
+    im0a[:na, :na] += oa.T @ (veff0doo[0] + veff[0]) @ oa
+    im0a[na:, na:] = es("ac,bc->ab", dvva, fa[na:, na:])
+    im0a[na:, na:] += es("ia,ib->ab", v, veff0mo[:nc, na:])
+    im0a[na:, :na] = es("aj,ij->ai", z1a, fa[:na, :na])
+    im0a[na:, :na] += es("ac,ic->ai", dvva, fa[:na, na:]) * 2
+    im0a[na:, :na] += es("ia,ij->aj", v, veff0mo[:nc, :na]) * 2
+    im0b[:nc, :nc] += ob.T @ (veff0doo[1] + veff[1]) @ ob
+    im0b[:nc, :nc] += es("ik,kj->ij", doob, fb[:nc, :nc])
+    im0b[:nc, :nc] += es("ia,ja->ij", v, veff0mo[:nc, na:])
+    im0b[nc:, :nc] = es("aj,ij->ai", z1b, fb[:nc, :nc])
+    im0b[nc:na, :nc] += es("bt,bi->ti", zvo, f["avc"])
+    return p.mo_coeff[0] @ (im0a + im0b) @ p.mo_coeff[0].T
+
+
+def uks_w_matrix(p, v, z):
+    """W matrix `im0` (AO basis) of tduks_sfu.py:266-299 from the stacked solution z = [z1a (nv, nocc_a) | z1b (nvir_b, nocc_b)] that
+    `ucphf.solve` returns (one half of Z)."""
+    nc, no, nv = p.nc, p.no, p.nv
+    na, nb = nc + no, nc
+    oa, va, ob, vb = _orbitals(p)
+    ea, eb = p.mo_energy
+    dvva, doob, _, _, _ = internal_densities(p, v)
+    veff0doo, veff0mo = _rhs_intermediates(p, v)
+    z = np.asarray(z).ravel()
+    z1a = z[:nv * na].reshape(nv, na)
+    z1b = z[nv * na:].reshape(no + nv, nb)
+    z1ao = np.stack([va @ z1a @ oa.T, vb @ z1b @ ob.T])
+    veff = response_uks(p, (z1ao + z1ao.transpose(0, 2, 1))[:, None])[:, 0]
+    n = p.nmo
+    im0a = np.zeros((n, n))
+    im0a[:na, :na] = oa.T @ (veff0doo[0] + veff[0]) @ oa
+    im0a[na:, na:] = es("jd,jc->dc", veff0mo[:nc, na:], v)
+    im0a[:na, na:] = es("jk,jc->kc", veff0mo[:nc, :na], v) * 2
+    im0b = np.zeros((n, n))
+    im0b[:nc, :nc] = ob.T @ (veff0doo[1] + veff[1]) @ ob
+    im0b[:nc, :nc] += es("al,ka->lk", veff0mo.T[na:, :nc], v)
+    zeta_a = (ea[:, None] + ea) * 0.5
+    zeta_a[:na, na:] = ea[na:]
+    zeta_a[na:, :na] = ea[:na]
+    dm1a = np.zeros((n, n))
+    dm1a[na:, na:] = dvva
+    dm1a[na:, :na] = z1a * 2
+    dm1a[:na, :na] += np.eye(na)
+    im0a = p.mo_coeff[0] @ (im0a + zeta_a * dm1a) @ p.mo_coeff[0].T
+    zeta_b = (eb[:, None] + eb) * 0.5
+    zeta_b[nc:, :nc] = eb[:nc]
+    zeta_b[:nc, nc:] = eb[nc:]
+    dm1b = np.zeros((n, n))
+    dm1b[:nc, :nc] = doob
+    dm1b[nc:, :nc] = z1b * 2
+    dm1b[:nc, :nc] += np.eye(nc)
+    im0b = p.mo_coeff[1] @ (im0b + zeta_b * dm1b) @ p.mo_coeff[1].T
+    return im0a + im0b

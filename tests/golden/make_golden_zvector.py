@@ -6,9 +6,11 @@ REFERENCE's own `grad_elec` functions from /root/reference (build container only
                                  side `w` (:207-274), the ROHF orbital-Hessian closure `matvec` (:284-321)
   xtddft/grad_hb/tduks_sfu.py    grad_elec: right-hand side (wvoa, wvob) (:205-244), the closure `fvind` (:249-258)
 
-Both functions are run verbatim up to their solver call (`lib.solve` / `ucphf.solve`), which the stub intercepts: it applies the
-closure it was handed to seeded vectors, records the right-hand side, and stops the function (everything after the solve -- the W
-matrix and the integral derivatives -- needs libcint derivative integrals and is out of scope).
+Both functions are run verbatim.  Their solver call (`lib.solve` / `ucphf.solve`) is a stub that records the closure and the right-hand side
+it was handed and returns the unique solution of the equation (dense LAPACK solve of that closure); grad_elec then builds its W matrix
+`im0` from it with its own code (tdroks_sfu.py:335-356, tduks_sfu.py:266-299) and is stopped at `nuc_grad_method()` -- the integral
+derivatives that follow need libcint and are out of scope.  The fixture holds: seeded vectors and the closure's images (x, ax), the
+right-hand side (rhs), the solution (z) and the W matrix (im0).
 
 What is NOT in the reference tree and is supplied by stubs coded from the published definitions (as in make_golden.py):
 `mf.gen_response(hermi=1)` (pyscf `_gen_uhf_response`: nr_uks_fxc + J - hyb K), `ni.eval_rho`, `ni.eval_xc_eff` (returns the
@@ -36,17 +38,26 @@ class Captured(Exception):
 
 
 class Capture:
-    """Stands in for `lib.solve` / `ucphf.solve`: keeps the operator closure and the right-hand side, then stops grad_elec."""
+    """Stands in for `lib.solve` / `ucphf.solve`: keeps the operator closure and the right-hand side and returns the (unique) solution
+    of the equation the real solver iterates on, from a dense LAPACK solve of the closure it was handed.  grad_elec then continues
+    with its own code (W matrix) until `nuc_grad_method()`, where the stub stops it; the locals of its frame are read from the traceback."""
     def __init__(self):
         self.op = self.rhs = None
 
     def lib_solve(self, aop, b, *a, **k):
         self.op, self.rhs = aop, np.array(b)
-        raise Captured()
+        dense = np.stack([aop(e) for e in np.eye(b.size)], axis=1)
+        return np.linalg.solve(dense, b)
 
     def ucphf_solve(self, fvind, mo_energy, mo_occ, h1, *a, **k):
+        """pyscf.scf.ucphf.solve (solve_nos1): (e_a - e_i) z + fvind(z) = -h1; returns ((z_a [nvir_a, nocc_a], z_b), None)."""
         self.op, self.rhs = fvind, [np.array(h1[0]), np.array(h1[1])]
-        raise Captured()
+        h = np.hstack([h1[0].ravel(), h1[1].ravel()])
+        gaps = np.hstack([(mo_energy[s][mo_occ[s] == 0][:, None] - mo_energy[s][mo_occ[s] > 0][None, :]).ravel() for s in (0, 1)])
+        dense = np.stack([fvind(e[None]) for e in np.eye(h.size)], axis=1) + np.diag(gaps)
+        z = np.linalg.solve(dense, -h)
+        n0 = h1[0].size
+        return (z[:n0].reshape(h1[0].shape), z[n0:].reshape(h1[1].shape)), None
 
 
 CAP = Capture()
@@ -175,6 +186,10 @@ def main():
         mf._numint = GradNumInt(p)
         mf.mol.nbas = p.nao
         mf.gen_response = types.MethodType(gen_response, mf)
+
+        def stop(*a, **k):
+            raise Captured()
+        mf.nuc_grad_method = stop
         nc, no, nv = p.nc, p.no, p.nv
         occ = np.zeros((2, p.nmo))
         occ[0, :nc + no] = 1
@@ -187,9 +202,15 @@ def main():
                                    verbose=0, stdout=sys.stdout)
         try:
             (roks if c["restricted"] else uks).grad_elec(td)
-            raise RuntimeError("the solver stub was not reached")
-        except Captured:
-            pass
+            raise RuntimeError("the stop stub was not reached")
+        except Captured as e:
+            tb = e.__traceback__
+            frame = None
+            while tb is not None:                      # the frame of grad_elec holds the solution and the W matrix it built from it
+                if tb.tb_frame.f_code.co_name == "grad_elec":
+                    frame = tb.tb_frame
+                tb = tb.tb_next
+            loc = frame.f_locals
         dim = nv * nc + nv * no + no * nc if c["restricted"] else nv * (nc + no) + (no + nv) * nc
         x = np.random.default_rng(c["seed"] + 100).standard_normal((3, dim))
         if c["restricted"]:
@@ -198,7 +219,11 @@ def main():
         else:
             ax = np.stack([CAP.op(xi[None]) for xi in x])
             rhs = np.hstack([CAP.rhs[0].ravel(), CAP.rhs[1].ravel()])
-        np.savez(os.path.join(OUT, f"zvector_{c['tag']}.npz"), x=x, ax=ax, rhs=rhs, amp=amp[:, 0],
+        if c["restricted"]:
+            zsol = np.array(loc["z"])
+        else:
+            zsol = np.hstack([np.array(loc["z1a"]).ravel(), np.array(loc["z1b"]).ravel()])
+        np.savez(os.path.join(OUT, f"zvector_{c['tag']}.npz"), x=x, ax=ax, rhs=rhs, amp=amp[:, 0], z=zsol, im0=np.array(loc["im0"]),
                  params=np.array([nc, no, nv, c["naux"], c["ng"], c["seed"], int(c["restricted"])]), xctype=c["xctype"], hyb=c["hyb"])
         print("zvector", c["tag"], dim, float(np.abs(ax).max()), float(np.abs(rhs).max()))
 

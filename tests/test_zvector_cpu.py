@@ -135,17 +135,32 @@ def test_solver_edge_cases():
 
 
 @pytest.mark.parametrize("tag", TAGS)
-def test_rhs_plans_against_the_reference(golden_dir, tag):
-    """The right-hand side assembled from two engine plans on the whole MO space (general J / K / f_xc response of the relaxed
-    difference densities, spin-flip exchange of the transition density) reproduces the `w` / `(wvoa, wvob)` the reference's own
-    `grad_elec` built (tests/golden/make_golden_zvector.py)."""
-    from xtddft_b200.zvector import assemble_rhs
+def test_rhs_and_w_matrix_plans_against_the_reference(golden_dir, tag):
+    """The right-hand side and the W matrix assembled from engine plans on the whole MO space (general J / K / f_xc response of the
+    relaxed difference densities and of the symmetrised Z-vector density, spin-flip exchange of the transition density) reproduce the
+    `w` / `(wvoa, wvob)` and the `im0` that the reference's own `grad_elec` built (tests/golden/make_golden_zvector.py)."""
+    from xtddft_b200.zvector import assemble_rhs, assemble_w, rhs_intermediates
     d, p = load_case(golden_dir, tag)
     resp = PlanInterpreter(planmod.build_mo_response_plan(p, range_separated=False), p)
     sfx = PlanInterpreter(planmod.build_mo_sf_exchange_plan(p), p) if p.hyb != 0.0 else None
-    rhs = assemble_rhs(p, d["amp"].reshape(p.nc, p.nv), lambda t: resp.sigma(t.reshape(1, -1))[0],
-                       (lambda x: sfx.sigma(x.reshape(1, -1))[0]) if sfx is not None else None)
-    assert _rel(rhs, d["rhs"]) < 1e-12
+    inter = rhs_intermediates(p, d["amp"].reshape(p.nc, p.nv), lambda t: resp.sigma(t.reshape(1, -1))[0],
+                              (lambda x: sfx.sigma(x.reshape(1, -1))[0]) if sfx is not None else None)
+    assert _rel(assemble_rhs(p, None, None, None, inter=inter), d["rhs"]) < 1e-12
+    full = PlanInterpreter(planmod.build_mo_response_plan(p), p)
+    assert _rel(assemble_w(p, d["z"], inter, lambda t: full.sigma(t.reshape(1, -1))[0]), d["im0"]) < 1e-12
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_oracle_solution_and_w_matrix_against_the_reference(golden_dir, tag):
+    d, p = load_case(golden_dir, tag)
+    v = d["amp"].reshape(p.nc, p.nv)
+    if p.restricted:
+        z, w = ozv.roks_solve(p, d["rhs"]), ozv.roks_w_matrix(p, v, d["z"])
+    else:
+        n0 = p.nv * (p.nc + p.no)
+        z = ozv.uks_solve(p, d["rhs"][:n0].reshape(p.nv, -1), d["rhs"][n0:].reshape(p.no + p.nv, -1))
+        w = ozv.uks_w_matrix(p, v, d["z"])
+    assert _rel(z, d["z"]) < 1e-11 and _rel(w, d["im0"]) < 1e-12
 
 
 def test_mo_response_plan_against_oracle():

@@ -83,32 +83,44 @@ def solve_linear(aop, b, hdiag, *, tol: float = 1e-12, max_cycle: int = 40, lind
     return vb.to_host(x)[0], bool(conv), k, res
 
 
-def assemble_rhs(p, v, apply_response, apply_sf_exchange):
-    """Right-hand side of the Z-vector equation for the spin-flip-up TDA state with amplitudes v[nc, nv], collinear kernel
-    (`collinear_samples <= 0`: f1vo = k1ao = 0) -- grad_hb/tdroks_sfu.py:207-274 (ROKS: `w`), grad_hb/tduks_sfu.py:205-244 (UKS:
-    `(wvoa, wvob)`, returned stacked).  The contractions run as two engine plans on MO-basis matrices:
+def rhs_intermediates(p, v, apply_response, apply_sf_exchange) -> dict:
+    """The contractions behind the right-hand side and the W matrix of one state (collinear kernel: f1vo = k1ao = 0), as two engine
+    plans on MO-basis matrices:
 
       apply_response(t[2, nmo, nmo]) -> C_s^T (f_xc[T] + J[T_a + T_b] - hyb K[T_s]) C_s      (plan.build_mo_response_plan)
       apply_sf_exchange(x[nmo, nmo]) -> C_b^T K[C_b x C_a^T] C_a                              (plan.build_mo_sf_exchange_plan)
 
-    what is left here is the block bookkeeping of the reference (a few small einsums on nmo x nmo matrices)."""
+    applied to the relaxed difference densities T_vv = v^T v (alpha), T_oo = -v v^T (beta) and to the transition density X = v
+    (grad_hb/tdroks_sfu.py:207-214,241-254; tduks_sfu.py:205-212,219-232)."""
     nc, no, nv, nmo = p.nc, p.no, p.nv, p.nmo
     na, nb = nc + no, nc
     v = np.asarray(v, dtype=np.float64).reshape(nc, nv)
-    dvva = v.T @ v                                   # T_ab  (:210)
-    doob = -(v @ v.T)                                # T_ij  (:211)
+    dvva = v.T @ v                                   # T_ab
+    doob = -(v @ v.T)                                # T_ij
     t = np.zeros((2, nmo, nmo))
     t[0, na:, na:] = dvva
     t[1, :nb, :nb] = doob
-    g = np.asarray(apply_response(t)).reshape(2, nmo, nmo)           # veff0doo in the MO basis (:247-251)
-    wvoa = g[0][na:, :na].copy()
-    wvob = g[1][nb:, :nb].copy()
+    g = np.asarray(apply_response(t)).reshape(2, nmo, nmo).copy()   # veff0doo in the MO basis
+    veff0mo = np.zeros((nmo, nmo))
     if p.hyb != 0.0:
         x = np.zeros((nmo, nmo))
-        x[:nb, na:] = v                              # X: beta occupied -> alpha virtual (:214)
-        veff0mo = -p.hyb * np.asarray(apply_sf_exchange(x)).reshape(nmo, nmo)      # (:249,254)
-        wvoa -= np.einsum("jk,jc->ck", veff0mo[:nc, :na], v)
-        wvob += np.einsum("ac,ka->ck", veff0mo.T[na:, nc:], v)
+        x[:nb, na:] = v                              # X: beta occupied -> alpha virtual
+        veff0mo = -p.hyb * np.asarray(apply_sf_exchange(x)).reshape(nmo, nmo)
+    return dict(v=v, dvva=dvva, doob=doob, g=g, veff0mo=veff0mo)
+
+
+def assemble_rhs(p, v, apply_response, apply_sf_exchange, inter: Optional[dict] = None):
+    """Right-hand side of the Z-vector equation for the spin-flip-up TDA state with amplitudes v[nc, nv] -- grad_hb/tdroks_sfu.py:246-274
+    (ROKS: `w`), grad_hb/tduks_sfu.py:223-234 (UKS: `(wvoa, wvob)`, returned stacked): the block bookkeeping of the reference (a few small
+    einsums on nmo x nmo matrices) on top of `rhs_intermediates`."""
+    nc, no = p.nc, p.no
+    na, nb = nc + no, nc
+    it = inter if inter is not None else rhs_intermediates(p, v, apply_response, apply_sf_exchange)
+    v, dvva, doob, g, veff0mo = it["v"], it["dvva"], it["doob"], it["g"], it["veff0mo"]
+    wvoa = g[0][na:, :na].copy()
+    wvob = g[1][nb:, :nb].copy()
+    wvoa -= np.einsum("jk,jc->ck", veff0mo[:nc, :na], v)
+    wvob += np.einsum("ac,ka->ck", veff0mo.T[na:, nc:], v)
     if not p.restricted:
         return np.hstack([wvoa.ravel(), wvob.ravel()])
     fa, fb = p.fock_ks
@@ -116,6 +128,65 @@ def assemble_rhs(p, v, apply_response, apply_sf_exchange):
     wvob += np.einsum("jk,jc->ck", doob, fb[:nc, nc:])              # (:258; the pure branch's :269 is a shape error)
     wvc = wvoa[:, :nc] + wvob[no:, :]
     return np.hstack([wvc.ravel(), wvoa[:, nc:].ravel(), wvob[:no, :].ravel()]) * 2
+
+
+def assemble_w(p, z, inter: dict, apply_response_z):
+    """The W matrix `im0` (AO basis) that multiplies the overlap derivatives: grad_hb/tdroks_sfu.py:328-356 (ROKS, z = [zvc | zvo | zoc])
+    / tduks_sfu.py:266-299 (UKS, z = the stacked halves `ucphf.solve` returns).  `apply_response_z(t[2, nmo, nmo])` is the full
+    `vresp` on MO-basis matrices (plan.build_mo_response_plan with the range-separated part): one application to the symmetrised
+    Z-vector density; the rest is the reference's block bookkeeping."""
+    nc, no, nv, nmo = p.nc, p.no, p.nv, p.nmo
+    na, nb = nc + no, nc
+    v, dvva, doob, g, veff0mo = inter["v"], inter["dvva"], inter["doob"], inter["g"], inter["veff0mo"]
+    z = np.asarray(z, dtype=np.float64).ravel()
+    zs = np.zeros((2, nmo, nmo))
+    if p.restricted:
+        zvc = z[:nv * nc].reshape(nv, nc)
+        zvo = z[nv * nc:nv * nc + nv * no].reshape(nv, no)
+        zoc = z[nv * nc + nv * no:].reshape(no, nc)
+        z1a, z1b = np.hstack((zvc, zvo)), np.vstack((zoc, zvc))
+    else:
+        z1a, z1b = z[:nv * na].reshape(nv, na), z[nv * na:].reshape(no + nv, nb)
+    zs[0, na:, :na] = z1a
+    zs[1, nb:, :nb] = z1b
+    zs = zs + zs.transpose(0, 2, 1)
+    if p.restricted:
+        zs *= 0.5                                                    # (:339) Z^S = (z + z^T) / 2; UKS (:270): z + z^T
+    veff = np.asarray(apply_response_z(zs)).reshape(2, nmo, nmo)
+    ca, cb = p.mo_coeff
+    im0a, im0b = np.zeros((nmo, nmo)), np.zeros((nmo, nmo))
+    if p.restricted:
+        fa, fb = p.fock_ks
+        favc = 0.5 * (fa[na:, :nc] + fa[:nc, na:].T)                # symmetrised block (:227)
+        im0a[:na, :na] = fa[:na, :na] + (g[0] + veff[0])[:na, :na]
+        im0b[:nc, :nc] = fb[:nc, :nc] + (g[1] + veff[1])[:nc, :nc]
+        im0a[na:, na:] = np.einsum("ac,bc->ab", dvva, fa[na:, na:]) + np.einsum("ia,ib->ab", v, veff0mo[:nc, na:])
+        im0a[na:, :na] = (np.einsum("aj,ij->ai", z1a, fa[:na, :na]) + 2 * np.einsum("ac,ic->ai", dvva, fa[:na, na:])
+                          + 2 * np.einsum("ia,ij->aj", v, veff0mo[:nc, :na]))
+        im0b[:nc, :nc] += np.einsum("ik,kj->ij", doob, fb[:nc, :nc]) + np.einsum("ia,ja->ij", v, veff0mo[:nc, na:])
+        im0b[nc:, :nc] = np.einsum("aj,ij->ai", z1b, fb[:nc, :nc])
+        im0b[nc:na, :nc] += np.einsum("bt,bi->ti", zvo, favc)
+        return ca @ (im0a + im0b) @ ca.T
+    ea, eb = p.mo_energy
+    im0a[:na, :na] = (g[0] + veff[0])[:na, :na]
+    im0a[na:, na:] = np.einsum("jd,jc->dc", veff0mo[:nc, na:], v)
+    im0a[:na, na:] = np.einsum("jk,jc->kc", veff0mo[:nc, :na], v) * 2
+    im0b[:nc, :nc] = (g[1] + veff[1])[:nc, :nc] + np.einsum("al,ka->lk", veff0mo.T[na:, :nc], v)
+    zeta_a = (ea[:, None] + ea) * 0.5
+    zeta_a[:na, na:] = ea[na:]
+    zeta_a[na:, :na] = ea[:na]
+    dm1a = np.zeros((nmo, nmo))
+    dm1a[na:, na:] = dvva
+    dm1a[na:, :na] = z1a * 2
+    dm1a[:na, :na] += np.eye(na)
+    zeta_b = (eb[:, None] + eb) * 0.5
+    zeta_b[nc:, :nc] = eb[:nc]
+    zeta_b[:nc, nc:] = eb[nc:]
+    dm1b = np.zeros((nmo, nmo))
+    dm1b[:nc, :nc] = doob
+    dm1b[nc:, :nc] = z1b * 2
+    dm1b[:nc, :nc] += np.eye(nc)
+    return ca @ (im0a + zeta_a * dm1a) @ ca.T + cb @ (im0b + zeta_b * dm1b) @ cb.T
 
 
 class ZVector:
@@ -158,20 +229,32 @@ class ZVector:
                                                                     verbose=verbose)
         return z
 
-    def rhs(self, v, workspace_bytes: Optional[int] = None):
-        """Right-hand side for the state with spin-flip-up amplitudes v[nc, nv] (collinear kernel), through two more engine plans on
-        the whole MO space (`assemble_rhs`); the engines are built on the first call.  CPU-verified against the reference's own
-        right-hand sides through the plan interpreter (tests/test_zvector_cpu.py); first GPU run pending."""
+    def _mo_engines(self, workspace_bytes: Optional[int] = None):
         from .drivers_common import make_engine
         if getattr(self, "_rhs_engines", None) is None:
             p = self.problem
-            self._rhs_engines = (make_engine(planmod.build_mo_response_plan(p, range_separated=False), p, max_nvec=1,
-                                             workspace_bytes=workspace_bytes),
-                                 make_engine(planmod.build_mo_sf_exchange_plan(p), p, max_nvec=1, workspace_bytes=workspace_bytes)
-                                 if p.hyb != 0.0 else None)
-        resp, sfx = self._rhs_engines
-        return assemble_rhs(self.problem, v, lambda t: resp.sigma_host(t.reshape(1, -1))[0],
-                            (lambda x: sfx.sigma_host(x.reshape(1, -1))[0]) if sfx is not None else None)
+            resp = make_engine(planmod.build_mo_response_plan(p, range_separated=False), p, max_nvec=1, workspace_bytes=workspace_bytes)
+            rsh = p.omega != 0.0 and p.has_df_lr
+            full = make_engine(planmod.build_mo_response_plan(p), p, max_nvec=1, workspace_bytes=workspace_bytes) if rsh else resp
+            sfx = (make_engine(planmod.build_mo_sf_exchange_plan(p), p, max_nvec=1, workspace_bytes=workspace_bytes)
+                   if p.hyb != 0.0 else None)
+            self._rhs_engines = (resp, sfx, full)
+        return self._rhs_engines
+
+    def rhs(self, v, workspace_bytes: Optional[int] = None):
+        """Right-hand side for the state with spin-flip-up amplitudes v[nc, nv] (collinear kernel), through two more engine plans on
+        the whole MO space (`assemble_rhs`); the engines are built on the first call and the intermediates kept for `w_matrix`.
+        CPU-verified against the reference's own right-hand sides through the plan interpreter (tests/test_zvector_cpu.py); first GPU
+        run pending."""
+        resp, sfx, _ = self._mo_engines(workspace_bytes)
+        self._inter = rhs_intermediates(self.problem, v, lambda t: resp.sigma_host(t.reshape(1, -1))[0],
+                                        (lambda x: sfx.sigma_host(x.reshape(1, -1))[0]) if sfx is not None else None)
+        return assemble_rhs(self.problem, v, None, None, inter=self._inter)
+
+    def w_matrix(self, z):
+        """W matrix `im0` (AO basis) from the solution of the Z-vector equation of the state `rhs` was last called for (same status)."""
+        _, _, full = self._mo_engines()
+        return assemble_w(self.problem, z, self._inter, lambda t: full.sigma_host(t.reshape(1, -1))[0])
 
     def split(self, z):
         """The rotation blocks the reference continues with: ROKS (zvc, zvo, zoc) (tdroks_sfu.py:328-330), UKS (z1a, z1b)."""
