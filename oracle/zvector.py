@@ -2,9 +2,10 @@
 
   * ROKS reference  xtddft/grad_hb/tdroks_sfu.py:184-333 (`grad_elec`): internal variables (:207-234), the XC pieces of the
                     right-hand side (`_contract_xc_kernel`, :59-181, collinear kernel), the Q matrix / right-hand side `w`
-                    (:236-274), the ROHF orbital-Hessian `matvec` (:283-321) and the `lib.solve` call (:324-327)
-  * UKS reference   xtddft/grad_hb/tduks_sfu.py:184-264: right-hand side (wvoa, wvob) (:205-244), `fvind` (:246-258) and the
-                    `ucphf.solve` call (:261-263)
+                    (:236-274), the ROHF orbital-Hessian `matvec` (:283-321), the `lib.solve` call (:324-327) and the W matrix
+                    `im0` (:328-356)
+  * UKS reference   xtddft/grad_hb/tduks_sfu.py:184-299: right-hand side (wvoa, wvob) (:205-244), `fvind` (:246-258), the
+                    `ucphf.solve` call (:261-263) and the W matrix (:266-299)
 
 on a `ProblemData` (NumPy), by the reference's AO route: back-transform the rotation blocks to AO densities, symmetrise, apply the
 hermi = 1 response `vresp` (grid f_xc + J - hyb K), project on the occupied-virtual blocks.  TEST INFRASTRUCTURE ONLY (see
